@@ -1,0 +1,100 @@
+/*
+ * b200rec.h -- C ABI of libb200rec.so, the B200 (sm_100a) compute core that replaces the reference's
+ * three Cython extension classes and the inline numpy hot loops of IALS / EASE_R / P3alpha / RP3beta.
+ *
+ * Boundary.  Every entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout).  Conventions:
+ *   - every function returns 0 on success or a negative B200_E_* code; b200_last_error() gives the text
+ *     (thread-local).  No C++ exception crosses the boundary.
+ *   - plain pointers and sizes only; the caller owns every buffer it passes; handles own their device memory.
+ *   - pointers named h_* are HOST pointers (pageable or pinned), d_* are DEVICE pointers on the current
+ *     CUDA device; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - the library uses the calling thread's current CUDA device (one process per GPU).
+ *   - there is no CPU fallback: without a usable CUDA device every call fails with B200_E_CUDA.
+ */
+#ifndef B200REC_H_
+#define B200REC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_E_INVALID (-1) /* bad argument (the Python shim raises ValueError with the reference's text) */
+#define B200_E_CUDA (-2)    /* CUDA runtime / launch failure (RuntimeError) */
+#define B200_E_NOMEM (-3)   /* device or host allocation failed */
+#define B200_E_UNSUPPORTED (-4)
+
+const char* b200_last_error(void);
+int b200_version(void);
+/* number of kernels of this library launched by the calling process so far (bench.py "gpu_launches") */
+int64_t b200_launch_count(void);
+/* fills name (<=256 bytes), SM count, and total device memory of the current device */
+int b200_device_info(char* name, int name_len, int* sm_count, int64_t* total_mem);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1: sparse column-column similarity with top-K  (hot path i)
+ * replaces  Base/Similarity/Cython/Compute_Similarity_Cython.pyx:52-611
+ *           (ctor :73-216, computeItemSimilarities :327-408, compute_similarity :413-611)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200_sim_s* b200_sim_t;
+
+enum b200_sim_kind {
+  B200_SIM_COSINE = 0,     /* pyx:138, :484-485 / :505-507 */
+  B200_SIM_ADJUSTED = 1,   /* pyx:119, :277-312 */
+  B200_SIM_ASYMMETRIC = 2, /* pyx:121, :176-180, :479-481 */
+  B200_SIM_PEARSON = 3,    /* pyx:123, :236-273 */
+  B200_SIM_JACCARD = 4,    /* jaccard == tanimoto, pyx:125-128, :488-491 */
+  B200_SIM_DICE = 5,       /* pyx:130-132, :493-496 */
+  B200_SIM_TVERSKY = 6     /* pyx:134-136, :498-503 */
+};
+
+/* Build the device-side representation of dataMatrix (n_rows x n_cols CSR, int32 indices sorted per row,
+ * fp32 data, no explicit zeros -- what BaseRecommender.__init__ guarantees, Base/BaseRecommender.py:23-24).
+ * Does what the reference constructor does (pyx:147-209): TopK=min(topK,n_cols), the per-kind data
+ * transform, column norms, row weights, CSR + CSC copies -- on the GPU.
+ *   shrink      : already truncated to an integer value by the caller if it mirrors pyx:65
+ *   normalize   : ignored (forced 0) for the set kinds, as pyx:128,132,136
+ *   h_row_weights: NULL or n_rows floats (pyx:184-194)
+ * topK must be >= 1 here; the dense (TopK==0, pyx:510-513) and full-Gram (EASE_R, topK=n_cols) outputs go
+ * through b200_sim_compute_dense(). */
+int b200_sim_create(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* h_indptr,
+                    const int32_t* h_indices, const float* h_data, int kind, int topK, float shrink,
+                    int normalize, float asymmetric_alpha, float tversky_alpha, float tversky_beta,
+                    const float* h_row_weights, void* stream);
+int b200_sim_destroy(b200_sim_t h);
+
+/* effective K (min(topK, n_cols)), window geometry and path chosen at create time */
+int b200_sim_info(b200_sim_t h, int* K, int* n_windows, int* window_cells, int* binary_path, int* signed_data);
+
+/* compute_similarity(start_col, end_col) (pyx:413-611) for columns [start_col, end_col):
+ * for local column c = col - start_col, slots [c*K, c*K + cnt[c]) of idx/val hold the neighbours j and
+ * similarities W[j, col]; unused slots hold idx -1 / val 0.  Neighbours are the K largest similarities
+ * among all columns (zeros outrank negatives and are not emitted -- Compute_Similarity_Python.py:335-345),
+ * ties broken by ascending neighbour index.  Slot order within a column is unspecified.
+ * The d_ variant leaves results on the device (the NCCL all-gather send buffer in multi-GPU runs). */
+int b200_sim_compute_device(b200_sim_t h, int start_col, int end_col, int32_t* d_idx, float* d_val,
+                            int32_t* d_cnt, void* stream);
+int b200_sim_compute(b200_sim_t h, int start_col, int end_col, int32_t* h_idx, float* h_val, int32_t* h_cnt);
+
+/* Assemble the scipy-canonical CSR of W (n_cols x n_cols, row j = neighbour, column = target column, sorted
+ * column indices per row, fp32 -- what pyx:603-611 returns) from a top-K table holding ALL columns
+ * (e.g. after the all-gather).  Two calls: _count returns nnz; _fill writes indptr[n_cols+1], indices[nnz],
+ * data[nnz] into host buffers.  d_idx/d_val/d_cnt are device pointers of shape [n_cols*K],[n_cols*K],[n_cols]. */
+int b200_topk_table_to_csr_count(int n_cols, int K, const int32_t* d_cnt, int64_t* nnz_out, void* stream);
+int b200_topk_table_to_csr_fill(int n_cols, int K, const int32_t* d_idx, const float* d_val,
+                                const int32_t* d_cnt, int64_t nnz, int32_t* h_indptr, int32_t* h_indices,
+                                float* h_data, void* stream);
+
+/* duration in milliseconds of the last top-K kernel launched through this handle, measured with CUDA
+ * events on the launching stream (bench.py roofline leg) */
+int b200_sim_last_kernel_ms(b200_sim_t h, float* ms);
+/* sum over columns [start,end) of the gathered-entry count  sum_{u in col} len_u  (SURVEY 8(d) bytes model) */
+int b200_sim_work(b200_sim_t h, int start_col, int end_col, int64_t* gathered_entries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REC_H_ */

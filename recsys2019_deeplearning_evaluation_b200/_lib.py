@@ -1,0 +1,88 @@
+"""ctypes binding of libb200rec.so (include/b200rec.h).  There is no CPU fallback: a missing library or a
+missing CUDA device is an error, never a silent detour (SURVEY.md Appendix A quirk 5 / north_star)."""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libb200rec.so")
+
+c_int_p = ctypes.POINTER(ctypes.c_int32)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_i64_p = ctypes.POINTER(ctypes.c_int64)
+c_void = ctypes.c_void_p
+
+# name -> (restype, argtypes); every symbol include/b200rec.h declares
+SIGNATURES = {
+    "b200_last_error": (ctypes.c_char_p, []),
+    "b200_version": (ctypes.c_int, []),
+    "b200_launch_count": (ctypes.c_int64, []),
+    "b200_device_info": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, c_int_p, c_i64_p]),
+    "b200_sim_create": (ctypes.c_int, [ctypes.POINTER(c_void), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                       c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                       ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void, c_void]),
+    "b200_sim_destroy": (ctypes.c_int, [c_void]),
+    "b200_sim_info": (ctypes.c_int, [c_void, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "b200_sim_compute_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void]),
+    "b200_sim_compute": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
+    "b200_topk_table_to_csr_count": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_void, c_i64_p, c_void]),
+    "b200_topk_table_to_csr_fill": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, ctypes.c_int64,
+                                                   c_void, c_void, c_void, c_void]),
+    "b200_sim_last_kernel_ms": (ctypes.c_int, [c_void, c_float_p]),
+    "b200_sim_work": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, c_i64_p]),
+}
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libb200rec.so (building is the job of __graft_entry__.build / build.py, never done implicitly here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error("libb200rec.so is missing (%s): run `python -m recsys2019_deeplearning_evaluation_b200.build`; "
+                        "there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = load().b200_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -3:
+        raise MemoryError(msg)
+    raise B200Error("libb200rec error %d: %s" % (rc, msg))
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_void)
+
+
+def launch_count():
+    return int(load().b200_launch_count())
+
+
+def device_info():
+    name = ctypes.create_string_buffer(256)
+    sms = ctypes.c_int32()
+    mem = ctypes.c_int64()
+    check(load().b200_device_info(name, 256, ctypes.byref(sms), ctypes.byref(mem)))
+    return name.value.decode(), int(sms.value), int(mem.value)

@@ -1,0 +1,136 @@
+"""Parity of the CUDA similarity path (through the C ABI) against the fp64 oracle -- `-m gpu`.
+
+Index sets must be identical where the oracle's K-th value is separated (tie-aware, see
+oracle.similarity_oracle.check_topk_against_dense); values within 1e-4 relative (north_star tolerance)."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle.similarity_oracle import SimilarityOracle, check_topk_against_dense
+from recsys2019_deeplearning_evaluation_b200.synth import synth_urm
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4  # north_star: "within 1e-4 relative for float similarities"
+
+
+def _gpu_cls():
+    from recsys2019_deeplearning_evaluation_b200.similarity import Compute_Similarity_Cython
+    return Compute_Similarity_Cython
+
+
+def _check(X, cols=None, **kw):
+    sim = _gpu_cls()(X, **kw)
+    W = sim.compute_similarity()
+    assert sps.isspmatrix_csr(W) and W.dtype == np.float32 and W.shape == (X.shape[1], X.shape[1])
+    assert W.has_sorted_indices or (W.sorted_indices().indices == W.indices).all()
+    assert (W.data != 0).all() and W.diagonal().sum() == 0
+    orc = SimilarityOracle(X, **kw)
+    cols = np.arange(X.shape[1]) if cols is None else cols
+    ties = check_topk_against_dense(W, orc, cols, rtol=RTOL)
+    return W, sim, ties
+
+
+@pytest.mark.parametrize("kind", ["cosine", "asymmetric", "jaccard", "tanimoto", "dice", "tversky", "adjusted", "pearson"])
+@pytest.mark.parametrize("values", ["continuous", "binary", "ratings"])
+def test_kinds_small(kind, values):
+    X = synth_urm(700, 300, 0.04, seed=3, values=values)
+    _check(X, topK=25, shrink=7, normalize=True, similarity=kind, asymmetric_alpha=0.3, tversky_alpha=0.7,
+           tversky_beta=1.3)
+
+
+@pytest.mark.parametrize("kind", ["cosine", "asymmetric", "adjusted"])
+@pytest.mark.parametrize("shrink", [0, 50])
+def test_no_normalize(kind, shrink):
+    X = synth_urm(500, 200, 0.05, seed=5, values="continuous")
+    _check(X, topK=10, shrink=shrink, normalize=False, similarity=kind)
+
+
+def test_exact_index_sets_continuous_c1():
+    """BASELINE.json configs[0] shape, continuous values (tie-free): index sets identical to the oracle."""
+    X = synth_urm(10_000, 5_000, 0.01, seed=42, values="continuous")
+    W, sim, ties = _check(X, cols=np.arange(0, 5000, 7), topK=200, shrink=100, normalize=True, similarity="cosine")
+    assert ties == 0
+    assert not sim.binary_path and sim.n_windows == 1
+    assert W.nnz == 5000 * 200
+
+
+def test_binary_c1_tie_aware():
+    X = synth_urm(10_000, 5_000, 0.01, seed=42, values="binary")
+    W, sim, ties = _check(X, cols=np.arange(0, 5000, 11), topK=200, shrink=100, normalize=True, similarity="cosine")
+    assert sim.binary_path
+
+
+def test_row_weights():
+    X = synth_urm(400, 150, 0.06, seed=9, values="ratings")
+    w = np.random.default_rng(0).random(400).astype(np.float32) + 0.5
+    _check(X, topK=15, shrink=3, similarity="cosine", row_weights=w)
+    with pytest.raises(ValueError):
+        _gpu_cls()(X, topK=5, row_weights=w[:-1])
+
+
+def test_topk_larger_than_candidates_and_empty_columns():
+    X = synth_urm(200, 120, 0.02, seed=2, values="continuous").tolil()
+    X[:, 5] = 0
+    X[:, 77] = 0
+    X = sps.csr_matrix(X.tocsr(), dtype=np.float32)
+    X.eliminate_zeros()
+    W, sim, _ = _check(X, topK=500, shrink=0, similarity="cosine")
+    assert sim.K == 120
+    assert W[:, 5].nnz == 0 and W[5, :].nnz == 0
+
+
+def test_signed_zeros_outrank_negatives():
+    """Compute_Similarity_Python.py:335-345 semantics on centred data with few positives per column."""
+    X = synth_urm(3000, 400, 0.004, seed=11, values="ratings")
+    for kind in ("adjusted", "pearson"):
+        W, sim, _ = _check(X, topK=50, shrink=0, similarity=kind)
+        assert sim.signed_data
+
+
+def test_negatives_emitted_when_zeros_run_out():
+    """Dense-ish signed data with K close to n_columns: negatives fill the slots zeros cannot."""
+    X = synth_urm(300, 40, 0.5, seed=4, values="ratings")
+    W, sim, _ = _check(X, topK=39, shrink=0, similarity="pearson")
+    assert (W.data < 0).any()
+
+
+def test_column_range_and_unknown_similarity():
+    X = synth_urm(500, 300, 0.03, seed=6, values="continuous")
+    cls = _gpu_cls()
+    sim = cls(X, topK=10, shrink=2, similarity="cosine")
+    Wfull = sim.compute_similarity()
+    Wpart = sim.compute_similarity(start_col=100, end_col=180)
+    assert abs(Wpart[:, 100:180] - Wfull[:, 100:180]).max() < 1e-7
+    assert Wpart[:, :100].nnz == 0 and Wpart[:, 180:].nnz == 0
+    with pytest.raises(ValueError):
+        cls(X, similarity="cosin")
+
+
+def test_windowed_accumulator_matches_single_window(monkeypatch):
+    """More columns than one shared-memory window holds: the multi-window path (C5 layout)."""
+    X = synth_urm(20_000, 120_000, 0.0004, seed=8, values="continuous")
+    W, sim, ties = _check(X, cols=np.arange(0, 120_000, 997), topK=50, shrink=10, similarity="cosine")
+    assert sim.n_windows >= 2
+    Xb = synth_urm(20_000, 120_000, 0.0004, seed=8, values="binary")
+    W, sim, ties = _check(Xb, cols=np.arange(0, 120_000, 1499), topK=50, shrink=10, similarity="cosine")
+    assert sim.n_windows >= 2 and sim.binary_path
+
+
+def test_popular_item_long_column():
+    """Zipf popularity: a few columns far longer than the staging chunk, heavy load imbalance."""
+    X = synth_urm(30_000, 2_000, 0.01, seed=13, values="ratings", popularity=1.1)
+    assert np.diff(X.tocsc().indptr).max() > 4096
+    _check(X, cols=np.arange(0, 2000, 13), topK=100, shrink=10, similarity="cosine")
+
+
+def test_dense_control_recipe_xtx():
+    """Recipe of Base/Similarity/Compute_similarity_test.py:31-56: normalize=False, shrink=0, topK=n => X^T X
+    with a zero diagonal."""
+    rng = np.random.default_rng(0)
+    D = (rng.random((60, 25)) * (rng.random((60, 25)) < 0.4)).astype(np.float32)
+    X = sps.csr_matrix(D)
+    W = _gpu_cls()(X, topK=25, shrink=0, normalize=False, similarity="cosine").compute_similarity().toarray()
+    G = D.astype(np.float64).T @ D.astype(np.float64)
+    np.fill_diagonal(G, 0)
+    assert np.allclose(W, G, rtol=1e-4, atol=1e-6)
