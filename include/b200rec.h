@@ -88,6 +88,15 @@ int b200_topk_table_to_csr_fill(int n_cols, int K, const int32_t* d_idx, const f
                                 const int32_t* d_cnt, int64_t nnz, int32_t* h_indptr, int32_t* h_indices,
                                 float* h_data, void* stream);
 
+/* TEST HOOK: shrink the logical capacity of the candidate buffer (K < cap <= allocated) so that small inputs
+ * exercise the overflow / rescan path of the selection. */
+int b200_sim_debug_set_cap(b200_sim_t h, int cap);
+
+/* TEST/BENCH HOOK: per-phase SM-cycle counters of the top-K kernel, summed over CTAs (thread 0's clock):
+ * [0] stage  [1] accumulate  [2] bootstrap histogram  [3] scan+clear  [4] evaluate+compact  [5] select
+ * [6] emit.  enable!=0 turns counting on for later launches; out8 (nullable) receives and resets the counters. */
+int b200_sim_debug_phase_cycles(b200_sim_t h, int enable, uint64_t* out8);
+
 /* duration in milliseconds of the last top-K kernel launched through this handle, measured with CUDA
  * events on the launching stream (bench.py roofline leg) */
 int b200_sim_last_kernel_ms(b200_sim_t h, float* ms);

@@ -3,19 +3,28 @@
 // Replaces Base/Similarity/Cython/Compute_Similarity_Cython.pyx:327-408 (computeItemSimilarities, the
 // Gustavson row-gather into an n_columns accumulator) and :467-568 (normalise, top-K, emit).
 //
-// Design (DESIGN.md "K1"): one persistent CTA per SM pulls target columns from an atomic counter.  For a
-// target column i the CTA stages i's CSC entries (user, x_ui * w_u) in shared memory, then -- one window
-// of the neighbour axis at a time -- every warp streams whole CSR row segments of those users with
-// coalesced vector loads and scatter-adds x_ui*x_uj into a shared-memory accumulator that covers the
-// window (fp32 CAS-add, or a native integer ATOMS add when every stored value is 1).  Rows are sorted, so
-// the segment of a row that falls in window w is a contiguous range whose bounds are precomputed
-// (`split`).  The window is then scanned: a dot-product histogram bootstraps a lower bound of the K-th
-// similarity, an upper bound of each cell's similarity (using the extreme column norms) prunes cells that
-// cannot qualify before their norm is gathered, survivors go to a candidate buffer of 64-bit keys
-// (similarity bits << 32 | ~index => ties resolve to the ascending index), and an 8-bit MSB radix select
-// keeps the K best.  Bytes per gathered entry: 8 (index + value) or 4 (binary path).
+// Design (DESIGN.md "K1").  At create time the columns are RENUMBERED by ascending norm term B_j (ties by
+// original index), the CSR rows re-sorted in the new numbering and the CSC built from them.  One persistent
+// CTA per SM pulls target columns from an atomic counter.  For a target column i the CTA stages i's CSC
+// entries (user, x_ui * w_u) in shared memory, then -- one window of the neighbour axis at a time -- every
+// warp streams whole CSR row segments of those users with coalesced loads and scatter-adds x_ui*x_uj into a
+// shared-memory accumulator covering the window (fp32 CAS-add, or a native integer ATOMS add when every
+// stored value is 1).  Rows are sorted, so the part of a row inside window w is a contiguous range whose
+// bounds are precomputed (`split`).  Selection per window:
+//   bootstrap  (first window only) a histogram of per-cell similarity LOWER bounds gives a floor `thr` of
+//              the K-th best similarity;
+//   scan       cells whose dot product is below a per-tile threshold (the analytic inverse of the
+//              similarity formula at `thr`, using the norm range of the 4096-cell tile -- tight because
+//              norms are monotone in the new numbering) are zeroed unread; the rest are appended as
+//              provisional (dot, j) records;
+//   evaluate   all records gather (B_j, original index) together, become exact 64-bit keys
+//              (similarity bits << 32 | ~original index, so ties resolve to the ascending index) or drop out;
+//   select     a range-normalised 2048-bin radix select keeps the K best whenever the buffer runs half full
+//              and after the last window.
+// Bytes per gathered entry: 8 (index + value) or 4 (binary path).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
 #include <vector>
@@ -29,46 +38,102 @@ typedef unsigned long long u64;
 
 constexpr int THREADS = 1024;
 constexpr int NWARPS = THREADS / 32;
-constexpr int COLCHUNK = 1024;  // users of the target column staged per chunk
+constexpr int STAGE_INTS = 3072; // staging area: per staged user one value + sp_stride row-segment bounds
+constexpr int SPMAX = 5;        // staged split columns per user (all windows at once when n_win + 1 <= SPMAX)
 constexpr int HBINS = 4096;     // bootstrap histogram bins (aliases the candidate buffer)
-constexpr int UB = 4;           // row segments in flight per warp
+constexpr int SBINS = 2048;     // select histogram bins (aliases the staging area)
+constexpr int SELT = 128;       // threads that run the select (one warp per scheduler)
+constexpr int UB = 2;           // 128-bit loads in flight per lane
+constexpr int TILE = THREADS * 4;
+constexpr int MAXTILES = 16;
 
 enum Formula { F_PROD = 0, F_NONORM = 1, F_JACCARD = 2, F_DICE = 3, F_TVERSKY = 4 };
 
 struct KParams {
-  int n_cols, K, n_win, win, cap;
-  int formula;
+  int n_cols, K, n_win, win, cap, cap_alloc;  // cap <= cap_alloc (a smaller logical cap is a test hook)
+  int acc_cells;     // accumulator cells allocated: max(win, SBINS), the cleared window doubles as select scratch
+  int lpu_log2;      // lanes that share one row segment in the accumulate phase (2^lpu_log2, 2..32)
   float se;          // shrink + 1e-6
   float shrink_div;  // shrink if != 0 else 1
   float ta, tb;
   const int* __restrict__ csr_ptr;
-  const int2* __restrict__ csr_ent;
-  const int* __restrict__ csr_idx;
+  const int2* __restrict__ csr_ent;  // (new column index, value bits), rows sorted by new index
+  const int* __restrict__ csr_idx;   // binary path: new column indices only
   const int* __restrict__ split;
-  const int* __restrict__ csc_ptr;
+  const int* __restrict__ csc_ptr;   // by new column index
   const int2* __restrict__ csc_ent;
   const int* __restrict__ csc_idx;
-  const float* __restrict__ A;
-  const float* __restrict__ B;
-  float B_min, B_max;
-  int col_begin, n_range;
-  const int* __restrict__ order;  // processing order of local columns (descending work), or nullptr
+  const float* __restrict__ A;       // by new column index
+  const int2* __restrict__ BN;       // by new column index: (B_j bits, original index); B ascending
+  const float* __restrict__ tileB;   // [n_win][MAXTILES + 1]: B at the tile boundaries of every window
+  const int* __restrict__ old2new;
+  int col_begin, n_range;            // original numbering
+  const int* __restrict__ order;     // processing order of local columns (descending work), or nullptr
   int* counter;
   int* out_idx;
   float* out_val;
   int* out_cnt;
   int signed_data;
+  unsigned long long* prof;  // optional [8] per-phase cycle counters (thread 0 of every CTA), test/bench hook
 };
 
+template <int F>
 __device__ __forceinline__ float sim_value(const KParams& p, float d, float a, float b) {
-  switch (p.formula) {
-    case F_PROD: return d / (a * b + p.se);
-    case F_NONORM: return d / p.shrink_div;
-    case F_JACCARD: return d / (a + b - d + p.se);
-    case F_DICE: return d / (a + b + p.se);
-    default: return d / (d + (a - d) * p.ta + (b - d) * p.tb + p.se);
-  }
+  if (F == F_PROD) return d / (a * b + p.se);
+  if (F == F_NONORM) return d / p.shrink_div;
+  if (F == F_JACCARD) return d / (a + b - d + p.se);
+  if (F == F_DICE) return d / (a + b + p.se);
+  return d / (d + (a - d) * p.ta + (b - d) * p.tb + p.se);
 }
+
+// Smallest positive dot product whose similarity can reach `t` (>0) for ANY neighbour norm term in
+// [b_lo, b_hi]: the analytic inverse of sim_value in d at both ends, widened by 1e-5 so that fp32 rounding
+// never excludes a qualifying cell.
+template <int F>
+__device__ __forceinline__ float dot_threshold(const KParams& p, float t, float a, float b_lo, float b_hi) {
+  float r = 3.4e38f;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const float b = e ? b_hi : b_lo;
+    float v;
+    if (F == F_PROD) v = t * (a * b + p.se);
+    else if (F == F_NONORM) v = t * p.shrink_div;
+    else if (F == F_JACCARD) v = t * (a + b + p.se) / (1.f + t);
+    else if (F == F_DICE) v = t * (a + b + p.se);
+    else {
+      const float den = 1.f - t * (1.f - p.ta - p.tb);
+      v = den > 1e-6f ? t * (a * p.ta + b * p.tb + p.se) / den : 0.f;
+    }
+    r = fminf(r, v);
+  }
+  return r > 0.f ? r * (1.f - 1e-5f) : 0.f;
+}
+
+// s such that sim_value(d, a, b) >= d * s for every positive d the data can produce and every b in
+// [b_lo, b_hi] (a cheap per-tile lower bound for the bootstrap histogram); 0 when no useful bound exists.
+template <int F>
+__device__ __forceinline__ float lower_bound_scale(const KParams& p, float a, float b_lo, float b_hi) {
+  const float b = fmaxf(b_lo, b_hi);
+  float den;
+  if (F == F_PROD) den = a * b + p.se;
+  else if (F == F_NONORM) den = p.shrink_div;
+  else if (F == F_JACCARD || F == F_DICE) den = a + b + p.se;  // jaccard: the "- d" only raises the value
+  else {
+    // tversky on set data: d <= a, so d*(1-ta-tb) <= a*max(0, 1-ta-tb)
+    if (p.ta < 0.f || p.tb < 0.f) return 0.f;
+    den = a * fmaxf(0.f, 1.f - p.ta - p.tb) + a * p.ta + b * p.tb + p.se;
+  }
+  return den > 0.f ? (1.f - 1e-5f) / den : 0.f;
+}
+
+#define PROF_MARK(ph)                                                        \
+  do {                                                                      \
+    if (p.prof && threadIdx.x == 0) {                                       \
+      const long long _t = clock64();                                       \
+      atomicAdd(p.prof + (ph), (unsigned long long)(_t - prof_t));          \
+      prof_t = _t;                                                          \
+    }                                                                       \
+  } while (0)
 
 template <bool NEG>
 __device__ __forceinline__ unsigned key32_of(float v) {
@@ -83,9 +148,14 @@ struct Shared {
   int digit, need, bincnt;
   int b0;
   int cnt;
+  unsigned kmin, kmax;
+  u64 sel_thr;
   int warp_tot[NWARPS];
-  int dig[256];
+  float dthr[MAXTILES];
+  float lbs[MAXTILES];
 };
+
+__device__ __forceinline__ void bar_sel() { asm volatile("bar.sync 1, %0;" ::"n"(SELT) : "memory"); }
 
 // exclusive suffix sum over the block: returns sum of v over all threads with a larger thread index
 __device__ __forceinline__ int block_suffix_excl(int v, int* warp_tot) {
@@ -104,239 +174,329 @@ __device__ __forceinline__ int block_suffix_excl(int v, int* warp_tot) {
   return above + incl - v;
 }
 
-// Keeps the `K` largest of buf[0..n) (n > K, distinct keys) in buf[0..K) and returns a threshold t such that
-// exactly those keys are >= t.  MSB-first radix select, 8 bits per pass, early exit when a bin is taken whole.
-// If lo<hi, entries whose index field (0xFFFFFFFF - low32) lies in [lo,hi) are dropped after the selection
-// (used by the overflow path); *n_out receives the surviving count.
-__device__ u64 block_select(u64* buf, int n, int K, Shared* sh, int drop_lo, int drop_hi, int* n_out) {
-  const int tid = threadIdx.x;
-  u64 prefix = 0, mask = 0;
-  int need = K;
-  for (int shift = 56; shift >= 0; shift -= 8) {
-    if (tid < 256) sh->dig[tid] = 0;
-    __syncthreads();
-    for (int q = tid; q < n; q += THREADS) {
-      u64 k = buf[q];
-      if ((k & mask) == prefix) atomicAdd(&sh->dig[(int)((k >> shift) & 255ull)], 1);
+// Called by threads 0..SELT-1 only (named barrier 1).  buf[0..n) holds distinct keys, some of them 0 (dead
+// slots).  Keeps the K largest non-zero keys (all of them if there are at most K) compacted at the front of
+// buf, writes the surviving count to sh->cnt and a threshold to sh->sel_thr such that exactly the survivors
+// are >= it (0 when nothing was cut).  Radix select over the occupied key range: every level maps the
+// still-undecided keys linearly onto SBINS bins (they spread out instead of piling onto one counter), finds
+// the bin holding the K-th key and narrows to it; stops as soon as a bin is taken whole.
+__device__ void select_group(u64* buf, int n, int K, Shared* sh, int* hist) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int SW = SELT / 32;
+  for (int i = tid; i < SBINS; i += SELT) hist[i] = 0;
+  if (tid == 0) { sh->kmin = 0xFFFFFFFFu; sh->kmax = 0u; sh->cnt = 0; }
+  bar_sel();
+  {
+    unsigned mn = 0xFFFFFFFFu, mx = 0u;
+    int valid = 0;
+    for (int q = tid; q < n; q += SELT) {
+      const u64 k = buf[q];
+      if (k) {
+        const unsigned h = (unsigned)(k >> 32);
+        mn = min(mn, h);
+        mx = max(mx, h);
+        ++valid;
+      }
     }
-    __syncthreads();
-    if (tid < 32) {
-      int c[8], local = 0;
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if (lane == 0) { atomicMin(&sh->kmin, mn); atomicMax(&sh->kmax, mx); atomicAdd(&sh->cnt, valid); }
+  }
+  bar_sel();
+  const int valid = sh->cnt;
+  u64 thr = 0;
+  if (valid > K) {
+    u64 base = ((u64)sh->kmin) << 32;
+    const u64 top = (((u64)sh->kmax) << 32) | 0xFFFFFFFFull;
+    int width = 64 - __clzll((long long)(top - base));  // live keys lie in [base, base + 2^width)
+    int need = K;
+    while (true) {
+      const int shift = max(0, width - 11);
+      for (int q = tid; q < n; q += SELT) {
+        const u64 k = buf[q];
+        const u64 off = k - base;
+        if (k >= base && k != 0ull && (width >= 64 || (off >> width) == 0ull)) atomicAdd(&hist[(int)(off >> shift)], 1);
+      }
+      bar_sel();
+      // SBINS / SELT = 16 bins per thread, highest bins in the highest threads
+      int c[SBINS / SELT], local = 0;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) { c[b] = sh->dig[tid * 8 + b]; local += c[b]; }
+      for (int b = 0; b < SBINS / SELT; ++b) {
+        c[b] = hist[tid * (SBINS / SELT) + b];
+        hist[tid * (SBINS / SELT) + b] = 0;
+        local += c[b];
+      }
       int incl = local;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
-        int t = __shfl_down_sync(0xffffffffu, incl, off);
-        if (tid + off < 32) incl += t;
+        const int t = __shfl_down_sync(0xffffffffu, incl, off);
+        if (lane + off < 32) incl += t;
       }
-      int cum = incl - local;  // keys in higher bins
+      if (lane == 0) sh->warp_tot[warp] = incl;
+      bar_sel();
+      int cum = incl - local;
+      for (int w = warp + 1; w < SW; ++w) cum += sh->warp_tot[w];
 #pragma unroll
-      for (int b = 7; b >= 0; --b) {
-        if (cum < need && cum + c[b] >= need) { sh->digit = tid * 8 + b; sh->need = need - cum; sh->bincnt = c[b]; }
+      for (int b = SBINS / SELT - 1; b >= 0; --b) {
+        if (cum < need && cum + c[b] >= need) { sh->digit = tid * (SBINS / SELT) + b; sh->need = need - cum; sh->bincnt = c[b]; }
         cum += c[b];
       }
+      bar_sel();
+      base += ((u64)sh->digit) << shift;
+      need = sh->need;
+      const int bincnt = sh->bincnt;
+      width = shift;
+      bar_sel();
+      if (bincnt == need || shift == 0) break;
     }
-    __syncthreads();
-    prefix |= ((u64)sh->digit) << shift;
-    mask |= 255ull << shift;
-    need = sh->need;
-    const int bincnt = sh->bincnt;
-    __syncthreads();
-    if (bincnt == need) break;
+    thr = base;
   }
-  // compaction through registers (cap <= 8 * THREADS)
-  u64 keep[8];
+  // compaction: survivors are gathered into registers (n <= 64 * SELT), then rewritten from the front
   if (tid == 0) sh->cnt = 0;
+  u64 keep[16];
+  const int rounds = (n + SELT - 1) / SELT;
+  for (int r0 = 0; r0 < rounds; r0 += 16) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    int i = q * THREADS + tid;
-    u64 k = (i < n) ? buf[i] : 0ull;
-    bool ok = (i < n) && (k >= prefix);
-    if (ok && drop_lo < drop_hi) {
-      int idx = (int)(0xFFFFFFFFu - (unsigned)k);
-      if (idx >= drop_lo && idx < drop_hi) ok = false;
+    for (int q = 0; q < 16; ++q) {
+      const int i = (r0 + q) * SELT + tid;
+      const u64 k = (r0 + q < rounds && i < n) ? buf[i] : 0ull;
+      keep[q] = (k != 0ull && k >= thr) ? k : 0ull;
     }
-    keep[q] = ok ? k : 0ull;
-  }
-  __syncthreads();
+    bar_sel();
+    // positions written are always < positions still unread (count of survivors so far <= entries consumed)
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    if (keep[q]) buf[atomicAdd(&sh->cnt, 1)] = keep[q];
+    for (int q = 0; q < 16; ++q)
+      if (keep[q]) buf[atomicAdd(&sh->cnt, 1)] = keep[q];
+    bar_sel();
   }
-  __syncthreads();
-  *n_out = sh->cnt;
-  __syncthreads();
-  return prefix;
+  if (tid == 0) sh->sel_thr = thr;
 }
 
-template <bool BINARY, bool NEG>
+// block-wide wrapper: threads >= SELT wait
+__device__ __forceinline__ u64 block_select(u64* buf, int n, int K, Shared* sh, int* hist, int* n_out) {
+  __syncthreads();
+  if (threadIdx.x < SELT) select_group(buf, n, K, sh, hist);
+  __syncthreads();
+  *n_out = sh->cnt;
+  return sh->sel_thr;
+}
+
+template <int F, bool BINARY, bool NEG>
 __device__ void process_column(const KParams& p, int col, int target, int out_base, unsigned char* smem_raw,
-                               Shared* sh, int* n_emitted) {
+                               Shared* sh, const float* s_tileB, int* n_emitted) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* accf = reinterpret_cast<float*>(smem_raw);
   int* acci = reinterpret_cast<int*>(smem_raw);
-  u64* buf = reinterpret_cast<u64*>(smem_raw + (size_t)p.win * 4);
+  u64* buf = reinterpret_cast<u64*>(smem_raw + (size_t)p.acc_cells * 4);
   int* hist = reinterpret_cast<int*>(buf);
-  float* sm_x = reinterpret_cast<float*>(buf + p.cap);
-  int* sm_s = reinterpret_cast<int*>(sm_x + COLCHUNK);
-  int* sm_e = sm_s + COLCHUNK;
+  int* stage = reinterpret_cast<int*>(buf + p.cap_alloc);
+  int* shist_stage = stage;  // select scratch while the window still holds cells (SBINS <= STAGE_INTS)
+  bool staged_valid = false;
 
   const int cs = p.csc_ptr[col], ce = p.csc_ptr[col + 1];
   const float Ai = p.A[col];
+  long long prof_t = p.prof ? clock64() : 0;
   u64 thr = 0;
   int nbuf = 0;
   if (tid == 0) { sh->nbuf = 0; if (!NEG) { sh->npos = 0; sh->nneg = 0; } }
+
+  // all window bounds of a user are staged at once when they fit (one trip to memory per column instead of
+  // one per window); columns longer than a chunk, or many windows, restage per (window, chunk)
+  const bool all_splits = (p.n_win + 1 <= SPMAX) && (ce - cs <= STAGE_INTS / (p.n_win + 2));
+  const int sp_stride = all_splits ? (p.n_win + 1) : 2;
+  const int colchunk = STAGE_INTS / (1 + sp_stride);  // users staged per chunk
+  float* sm_x = reinterpret_cast<float*>(stage);
+  int* sm_sp = stage + colchunk;
+  const int lpu = 1 << p.lpu_log2, upw = 32 >> p.lpu_log2;  // lanes per user, users per warp slot
+  const int sub = lane & (lpu - 1), uslot = lane >> p.lpu_log2;
   __syncthreads();
 
   for (int w = 0; w < p.n_win; ++w) {
     const int win_lo = w * p.win;
     const int win_n = min(p.win, p.n_cols - win_lo);
     const int win4 = (win_n + 3) >> 2;
+    const int ntiles = (win4 + THREADS - 1) / THREADS;
+    const float* tB = s_tileB + w * (MAXTILES + 1);
+    int* accw_i = acci - win_lo;
+    float* accw_f = accf - win_lo;
 
     // ---------------- accumulate: acc[j - win_lo] += x_ui * x_uj over users u of column `col`
-    for (int k0 = cs; k0 < ce; k0 += COLCHUNK) {
-      const int n = min(COLCHUNK, ce - k0);
-      __syncthreads();
-      for (int t = tid; t < n; t += THREADS) {
-        int u;
-        float x;
-        if (BINARY) {
-          u = p.csc_idx[k0 + t];
-          x = 1.0f;
-        } else {
-          int2 e = p.csc_ent[k0 + t];
-          u = e.x;
-          x = __int_as_float(e.y);
+    for (int k0 = cs; k0 < ce; k0 += colchunk) {
+      const int n = min(colchunk, ce - k0);
+      if (!all_splits || !staged_valid) {
+        staged_valid = true;
+        __syncthreads();
+        for (int t = tid; t < n; t += THREADS) {
+          int u;
+          if (BINARY) {
+            u = p.csc_idx[k0 + t];
+          } else {
+            const int2 e = p.csc_ent[k0 + t];
+            u = e.x;
+            sm_x[t] = __int_as_float(e.y);
+          }
+          if (p.n_win == 1) {
+            sm_sp[t * 2] = p.csr_ptr[u];
+            sm_sp[t * 2 + 1] = p.csr_ptr[u + 1];
+          } else if (all_splits) {
+            const int* sp = p.split + (size_t)u * (p.n_win + 1);
+            for (int q = 0; q <= p.n_win; ++q) sm_sp[t * sp_stride + q] = sp[q];
+          } else {
+            const int* sp = p.split + (size_t)u * (p.n_win + 1) + w;
+            sm_sp[t * 2] = sp[0];
+            sm_sp[t * 2 + 1] = sp[1];
+          }
         }
-        int s, e_;
-        if (p.n_win == 1) {
-          s = p.csr_ptr[u];
-          e_ = p.csr_ptr[u + 1];
-        } else {
-          const int* sp = p.split + (size_t)u * (p.n_win + 1) + w;
-          s = sp[0];
-          e_ = sp[1];
-        }
-        sm_x[t] = x;
-        sm_s[t] = s;
-        sm_e[t] = e_;
+        __syncthreads();
       }
-      __syncthreads();
-      for (int t0 = warp; t0 < n; t0 += NWARPS * UB) {
-        int s[UB], len[UB];
+      PROF_MARK(0);
+      const int spo = all_splits ? w : 0;
+      for (int t0 = warp * upw; t0 < n; t0 += NWARPS * upw * UB) {
+        int s[UB], e[UB], a0[UB];
         float x[UB];
-        int maxlen = 0;
+        int mych = 0;
 #pragma unroll
         for (int k = 0; k < UB; ++k) {
-          const int t = t0 + k * NWARPS;
+          const int t = t0 + k * NWARPS * upw + uslot;
           if (t < n) {
-            s[k] = sm_s[t];
-            len[k] = sm_e[t] - s[k];
-            x[k] = sm_x[t];
+            s[k] = sm_sp[t * sp_stride + spo];
+            e[k] = sm_sp[t * sp_stride + spo + 1];
+            x[k] = BINARY ? 1.f : sm_x[t];
           } else {
-            s[k] = 0; len[k] = 0; x[k] = 0.f;
+            s[k] = 0; e[k] = 0; x[k] = 0.f;
           }
-          maxlen = max(maxlen, len[k]);
+          // 16-byte chunks: 4 indices (binary) or 2 (index, value) pairs
+          a0[k] = BINARY ? (s[k] & ~3) : (s[k] & ~1);
+          mych = max(mych, BINARY ? ((e[k] - a0[k] + 3) >> 2) : ((e[k] - a0[k] + 1) >> 1));
         }
-        for (int r0 = 0; r0 < maxlen; r0 += 32) {
-          const int r = r0 + lane;
-          if (BINARY) {
-            int j[UB];
+        const int maxch = __reduce_max_sync(0xffffffffu, mych);
+        for (int c0 = 0; c0 < maxch; c0 += lpu) {
+          const int ch = c0 + sub;
+          int4 v[UB];
 #pragma unroll
-            for (int k = 0; k < UB; ++k) j[k] = (r < len[k]) ? __ldg(p.csr_idx + s[k] + r) : -1;
+          for (int k = 0; k < UB; ++k) {
+            const int g = a0[k] + ch * (BINARY ? 4 : 2);
+            v[k] = make_int4(-1, -1, -1, -1);
+            if (g < e[k]) v[k] = BINARY ? __ldg(reinterpret_cast<const int4*>(p.csr_idx + g))
+                                        : __ldg(reinterpret_cast<const int4*>(p.csr_ent + g));
+          }
 #pragma unroll
-            for (int k = 0; k < UB; ++k)
-              if (j[k] >= 0 && j[k] != col) atomicAdd(&acci[j[k] - win_lo], 1);
-          } else {
-            int2 e[UB];
+          for (int k = 0; k < UB; ++k) {
+            const int g = a0[k] + ch * (BINARY ? 4 : 2);
+            // the diagonal is accumulated like any other cell and zeroed after the loop
+            if (BINARY) {
+              const int jj[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+              if (g >= s[k] && g + 4 <= e[k]) {  // interior chunk: no bounds checks
 #pragma unroll
-            for (int k = 0; k < UB; ++k) e[k] = (r < len[k]) ? __ldg(p.csr_ent + s[k] + r) : make_int2(-1, 0);
+                for (int c = 0; c < 4; ++c) atomicAdd(&accw_i[jj[c]], 1);
+              } else {
 #pragma unroll
-            for (int k = 0; k < UB; ++k)
-              if (e[k].x >= 0 && e[k].x != col) atomicAdd(&accf[e[k].x - win_lo], x[k] * __int_as_float(e[k].y));
+                for (int c = 0; c < 4; ++c)
+                  if (g + c >= s[k] && g + c < e[k]) atomicAdd(&accw_i[jj[c]], 1);
+              }
+            } else {
+              if (g >= s[k] && g < e[k]) atomicAdd(&accw_f[v[k].x], x[k] * __int_as_float(v[k].y));
+              if (g + 1 >= s[k] && g + 1 < e[k]) atomicAdd(&accw_f[v[k].z], x[k] * __int_as_float(v[k].w));
+            }
           }
         }
       }
     }
     __syncthreads();
+    if (tid == 0 && col >= win_lo && col < win_lo + win_n) acci[col - win_lo] = 0;  // pyx:396
+    __syncthreads();
+    PROF_MARK(1);
 
-    // ---------------- bootstrap a lower bound of the target-th best similarity from the dot histogram
+    // ---------------- bootstrap: floor of the target-th best similarity from per-cell lower bounds
     nbuf = sh->nbuf;
     if (!NEG && thr == 0 && nbuf == 0 && win_n > 2 * target) {
       for (int i = tid; i < HBINS; i += THREADS) hist[i] = 0;
       if (tid == 0) sh->b0 = -1;
+      if (tid < ntiles) sh->lbs[tid] = lower_bound_scale<F>(p, Ai, tB[tid], tB[tid + 1]);
       __syncthreads();
       for (int i4 = tid; i4 < win4; i4 += THREADS) {
+        const float sc = sh->lbs[i4 / THREADS];
         float d[4];
         if (BINARY) {
-          int4 v = reinterpret_cast<const int4*>(acci)[i4];
+          const int4 v = reinterpret_cast<const int4*>(acci)[i4];
+          if ((v.x | v.y | v.z | v.w) == 0) continue;
           d[0] = (float)v.x; d[1] = (float)v.y; d[2] = (float)v.z; d[3] = (float)v.w;
         } else {
-          float4 v = reinterpret_cast<const float4*>(accf)[i4];
-          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (d[c] > 0.f) atomicAdd(&hist[min(__float_as_uint(d[c]) >> 19, (unsigned)(HBINS - 1))], 1);
-      }
-      __syncthreads();
-      int4 h = reinterpret_cast<const int4*>(hist)[tid];
-      const int local = h.x + h.y + h.z + h.w;
-      int cum = block_suffix_excl(local, sh->warp_tot);
-      const int hh[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-      for (int b = 3; b >= 0; --b) {
-        if (cum < target && cum + hh[b] >= target) sh->b0 = tid * 4 + b;
-        cum += hh[b];
-      }
-      __syncthreads();
-      const int b0 = sh->b0;
-      if (b0 > 0) {
-        const float d0 = __uint_as_float(((unsigned)b0) << 19);
-        const float lb = fminf(sim_value(p, d0, Ai, p.B_min), sim_value(p, d0, Ai, p.B_max));
-        if (lb > 0.f) thr = ((u64)__float_as_uint(lb)) << 32;
-      }
-      __syncthreads();  // hist (aliasing buf) fully consumed before candidates are pushed
-    }
-
-    // ---------------- scan: prune by upper bound, evaluate, push candidates; retry after an overflow
-    bool first = true;
-    while (true) {
-      if (tid == 0) sh->overflow = 0;
-      __syncthreads();
-      const unsigned thr32 = (unsigned)(thr >> 32);
-      int cpos = 0, cneg = 0;
-      for (int i4 = tid; i4 < win4; i4 += THREADS) {
-        float d[4];
-        if (BINARY) {
-          int4 v = reinterpret_cast<const int4*>(acci)[i4];
-          d[0] = (float)v.x; d[1] = (float)v.y; d[2] = (float)v.z; d[3] = (float)v.w;
-        } else {
-          float4 v = reinterpret_cast<const float4*>(accf)[i4];
+          const float4 v = reinterpret_cast<const float4*>(accf)[i4];
           d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float dd = d[c];
-          if (dd == 0.f) continue;
-          if (!NEG && first) { cpos += dd > 0.f; cneg += dd < 0.f; }
-          if (NEG ? (dd < 0.f) : (dd > 0.f)) {
-            const unsigned ub = max(key32_of<NEG>(sim_value(p, dd, Ai, p.B_min)),
-                                    key32_of<NEG>(sim_value(p, dd, Ai, p.B_max)));
-            if (ub >= thr32) {
-              const int j = win_lo + i4 * 4 + c;
-              const float sv = sim_value(p, dd, Ai, __ldg(p.B + j));
-              const u64 key = (((u64)key32_of<NEG>(sv)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)j);
-              if (key >= thr && (NEG ? (sv < 0.f) : (sv > 0.f))) {
-                const int pos = atomicAdd(&sh->nbuf, 1);
-                if (pos < p.cap) buf[pos] = key; else sh->overflow = 1;
-              }
+          const float lb = d[c] * sc;
+          if (lb > 0.f) atomicAdd(&hist[min(__float_as_uint(lb) >> 19, (unsigned)(HBINS - 1))], 1);
+        }
+      }
+      __syncthreads();
+      int hh[HBINS / THREADS], local = 0;
+#pragma unroll
+      for (int b = 0; b < HBINS / THREADS; ++b) { hh[b] = hist[tid * (HBINS / THREADS) + b]; local += hh[b]; }
+      int cum = block_suffix_excl(local, sh->warp_tot);
+#pragma unroll
+      for (int b = HBINS / THREADS - 1; b >= 0; --b) {
+        if (cum < target && cum + hh[b] >= target) sh->b0 = tid * (HBINS / THREADS) + b;
+        cum += hh[b];
+      }
+      __syncthreads();
+      const int b0 = sh->b0;
+      if (b0 > 0) thr = ((u64)(((unsigned)b0) << 19)) << 32;
+      __syncthreads();  // hist (aliasing buf) fully consumed before candidates are pushed
+    }
+    PROF_MARK(2);
+
+    // ---------------- scan + clear / evaluate, see the header comment.  A cell that finds the buffer full
+    // stays in place; the buffer is then pruned to the best `target` and the rescan picks the leftovers up.
+    bool first = true;
+    while (true) {
+      const int nbuf_old = sh->nbuf;
+      __syncthreads();
+      if (tid == 0) sh->overflow = 0;
+      if (tid < ntiles)
+        sh->dthr[tid] = (!NEG && thr) ? dot_threshold<F>(p, __uint_as_float((unsigned)(thr >> 32)), Ai, tB[tid], tB[tid + 1]) : 0.f;
+      int cpos = 0, cneg = 0;
+      const bool count_signs = !NEG && first && p.signed_data;
+      __syncthreads();
+      for (int i4 = tid; i4 < win4; i4 += THREADS) {
+        const float dthr = sh->dthr[i4 / THREADS];
+        float d[4];
+        if (BINARY) {
+          const int4 v = reinterpret_cast<const int4*>(acci)[i4];
+          if ((v.x | v.y | v.z | v.w) == 0) continue;
+          d[0] = (float)v.x; d[1] = (float)v.y; d[2] = (float)v.z; d[3] = (float)v.w;
+        } else {
+          const float4 v = reinterpret_cast<const float4*>(accf)[i4];
+          if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        if (count_signs) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { cpos += d[c] > 0.f; cneg += d[c] < 0.f; }
+        }
+        float keepv[4] = {0.f, 0.f, 0.f, 0.f};
+        const float dmax = NEG ? -fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) : fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3]));
+        if (dmax > 0.f && dmax >= dthr) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float dd = d[c];
+            if (NEG ? (dd < 0.f) : (dd > 0.f && dd >= dthr)) {
+              const int pos = atomicAdd(&sh->nbuf, 1);
+              if (pos < p.cap)
+                buf[pos] = (((u64)__float_as_uint(dd)) << 32) | (u64)(unsigned)(win_lo + i4 * 4 + c);
+              else { sh->overflow = 1; keepv[c] = dd; }
             }
           }
         }
+        if (BINARY)
+          reinterpret_cast<int4*>(acci)[i4] = make_int4((int)keepv[0], (int)keepv[1], (int)keepv[2], (int)keepv[3]);
+        else
+          reinterpret_cast<float4*>(accf)[i4] = make_float4(keepv[0], keepv[1], keepv[2], keepv[3]);
       }
-      if (!NEG && first && p.signed_data) {
+      if (count_signs) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
           cpos += __shfl_xor_sync(0xffffffffu, cpos, off);
@@ -346,30 +506,43 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
       }
       first = false;
       __syncthreads();
-      if (!sh->overflow) break;
-      // overflow: keep the best `target` of the full buffer, drop this window's entries (the rescan re-pushes
-      // the ones that still qualify), tighten the threshold, rescan.
+      PROF_MARK(3);
+      const int n_end = min(sh->nbuf, p.cap);
+      const bool overflow = sh->overflow != 0;
+      // evaluate in place: provisional (dot, j) -> exact key, or 0 (dead slot, dropped by the next select)
+      for (int e = nbuf_old + tid; e < n_end; e += THREADS) {
+        const u64 rec = buf[e];
+        const int j = (int)(unsigned)rec;
+        const float dd = __uint_as_float((unsigned)(rec >> 32));
+        const int2 bn = __ldg(p.BN + j);
+        const float sv = sim_value<F>(p, dd, Ai, __int_as_float(bn.x));
+        const u64 key = (((u64)key32_of<NEG>(sv)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)bn.y);
+        buf[e] = (key >= thr && (NEG ? (sv < 0.f) : (sv > 0.f))) ? key : 0ull;
+      }
+      nbuf = n_end;
+      __syncthreads();
+      if (tid == 0) sh->nbuf = nbuf;
+      PROF_MARK(4);
+      if (!overflow) break;
       int kept;
-      thr = max(thr, block_select(buf, p.cap, target, sh, win_lo, win_lo + win_n, &kept));
+      staged_valid = false;  // the staging area is the only scratch left while cells remain in the window
+      thr = max(thr, block_select(buf, nbuf, target, sh, shist_stage, &kept));
       if (tid == 0) sh->nbuf = kept;
       __syncthreads();
     }
+    __syncthreads();
     nbuf = sh->nbuf;
-    if (nbuf > target && (nbuf > p.cap / 2 || w == p.n_win - 1)) {
-      int kept;
-      thr = max(thr, block_select(buf, nbuf, target, sh, 0, 0, &kept));
+    if (nbuf > p.cap / 2 || w == p.n_win - 1) {
+      int kept;  // the window is all zero here and select leaves its scratch zeroed
+      thr = max(thr, block_select(buf, nbuf, target, sh, acci, &kept));
       if (tid == 0) sh->nbuf = kept;
       nbuf = kept;
+      __syncthreads();
     }
-    // ---------------- clear the window
-    {
-      int4 z = make_int4(0, 0, 0, 0);
-      for (int i4 = tid; i4 < win4; i4 += THREADS) reinterpret_cast<int4*>(acci)[i4] = z;
-    }
-    __syncthreads();
+    PROF_MARK(5);
   }
 
-  // ---------------- emit
+  // ---------------- emit (keys carry the ORIGINAL neighbour index; the last select left no dead slots)
   for (int t = tid; t < nbuf; t += THREADS) {
     const u64 k = buf[t];
     const unsigned hi = (unsigned)(k >> 32);
@@ -378,16 +551,21 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
   }
   *n_emitted = nbuf;
   __syncthreads();
+  PROF_MARK(6);
 }
 
-template <bool BINARY>
+template <int F, bool BINARY>
 __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Shared sh;
   const int tid = threadIdx.x;
+  // layout: [acc acc_cells*4][buf cap_alloc*8][stage STAGE_INTS*4][tileB n_win*(MAXTILES+1)*4]
+  float* s_tileB = reinterpret_cast<float*>(smem_raw + (size_t)p.acc_cells * 4 + (size_t)p.cap_alloc * 8 +
+                                            (size_t)STAGE_INTS * 4);
   {
-    int4 z = make_int4(0, 0, 0, 0);
-    for (int i4 = tid; i4 < (p.win >> 2); i4 += THREADS) reinterpret_cast<int4*>(smem_raw)[i4] = z;
+    const int4 z = make_int4(0, 0, 0, 0);
+    for (int i4 = tid; i4 < (p.acc_cells >> 2); i4 += THREADS) reinterpret_cast<int4*>(smem_raw)[i4] = z;
+    for (int i = tid; i < p.n_win * (MAXTILES + 1); i += THREADS) s_tileB[i] = p.tileB[i];
   }
   __syncthreads();
   while (true) {
@@ -396,10 +574,10 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     const int c = sh.col;
     if (c >= p.n_range) break;
     const int lc = p.order ? p.order[c] : c;
-    const int col = p.col_begin + lc;
+    const int col = p.old2new[p.col_begin + lc];  // new numbering
     const int out_base_row = lc;
     int n_out = 0;
-    process_column<BINARY, false>(p, col, p.K, out_base_row * p.K, smem_raw, &sh, &n_out);
+    process_column<F, BINARY, false>(p, col, p.K, out_base_row * p.K, smem_raw, &sh, s_tileB, &n_out);
     if (p.signed_data && n_out < p.K) {
       // zeros outrank negatives (Compute_Similarity_Python.py:335-345): negatives are only emitted when the
       // positives plus the implicit zeros (every column without a non-zero similarity, the diagonal
@@ -410,7 +588,7 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
       __syncthreads();
       if (m > 0 && nneg > 0) {
         int n_neg_out = 0;
-        process_column<BINARY, true>(p, col, m, out_base_row * p.K + n_out, smem_raw, &sh, &n_neg_out);
+        process_column<F, BINARY, true>(p, col, m, out_base_row * p.K + n_out, smem_raw, &sh, s_tileB, &n_neg_out);
         n_out += n_neg_out;
       }
     }
@@ -421,6 +599,16 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     if (tid == 0) p.out_cnt[out_base_row] = n_out;
     __syncthreads();
   }
+}
+
+// B at the tile boundaries of every window: tileB[w][t] = B[min(w*win + t*TILE, last column of window w)]
+__global__ void tile_bounds_kernel(const int2* __restrict__ BN, int n_cols, int n_win, int win, float* tileB) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_win * (MAXTILES + 1)) return;
+  const int w = g / (MAXTILES + 1), t = g % (MAXTILES + 1);
+  const int win_lo = w * win, win_n = min(win, n_cols - win_lo);
+  const int j = min(win_lo + t * TILE, win_lo + win_n - 1);
+  tileB[g] = __int_as_float(BN[j].x);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -477,20 +665,44 @@ __global__ void col_center_kernel(const int* __restrict__ idx, float* data, long
   }
 }
 
-__global__ void norms_kernel(const double* __restrict__ colsq, int n_cols, int mode, float alpha, float* A, float* B) {
+// per ORIGINAL column: A (target-side term) and B (neighbour-side term) of the similarity formula
+__global__ void norms_kernel(const double* __restrict__ colsq, int n_cols, int mode, float alpha, float* A, float* B,
+                             unsigned* Bkey, int* iota) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_cols) return;
   const double sq = colsq[j];
+  float a, b;
   if (mode == 0) {  // set kinds: plain sum of squares (pyx:170-174)
-    A[j] = (float)sq; B[j] = (float)sq;
+    a = b = (float)sq;
   } else if (mode == 1) {  // cosine family
-    const float n = (float)sqrt(sq);
-    A[j] = n; B[j] = n;
+    a = b = (float)sqrt(sq);
   } else {  // asymmetric (pyx:176-180)
     const double n = sqrt(sq) + 1e-6;
-    A[j] = (float)pow(n, 2.0 * (double)alpha);
-    B[j] = (float)pow(n, 2.0 * (1.0 - (double)alpha));
+    a = (float)pow(n, 2.0 * (double)alpha);
+    b = (float)pow(n, 2.0 * (1.0 - (double)alpha));
   }
+  A[j] = a;
+  B[j] = b;
+  Bkey[j] = __float_as_uint(b);  // b >= 0: the bit pattern orders like the value
+  iota[j] = j;
+}
+
+// new numbering: new2old = columns sorted by (B asc, original index asc)
+__global__ void renumber_kernel(const int* __restrict__ new2old, const float* __restrict__ A_old,
+                                const float* __restrict__ B_old, const int* __restrict__ cnt_old, int n_cols,
+                                int* old2new, float* A_new, int2* BN, int* cnt_new) {
+  const int jn = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jn >= n_cols) return;
+  const int jo = new2old[jn];
+  old2new[jo] = jn;
+  A_new[jn] = A_old[jo];
+  BN[jn] = make_int2(__float_as_int(B_old[jo]), jo);
+  cnt_new[jn] = cnt_old[jo];
+}
+
+__global__ void relabel_kernel(const int* __restrict__ idx_old, const int* __restrict__ old2new, long long nnz, int* idx_new) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x)
+    idx_new[i] = old2new[idx_old[i]];
 }
 
 __global__ void rowid_iota_kernel(const int* __restrict__ ptr, int n_rows, int* rowid, int* iota) {
@@ -540,7 +752,7 @@ __global__ void split_kernel(const int* __restrict__ ptr, const int* __restrict_
   split[g] = lo;
 }
 
-// work[c] = sum over users u of column c of len_u  (the gathered-entry count of SURVEY 8(d))
+// work[c] = sum over users u of (new) column c of len_u  (the gathered-entry count of SURVEY 8(d))
 __global__ void col_work_kernel(const int* __restrict__ csc_ptr, const int* __restrict__ csc_idx,
                                 const int2* __restrict__ csc_ent, const int* __restrict__ csr_ptr, int n_cols,
                                 unsigned long long* work) {
@@ -569,16 +781,19 @@ struct b200_sim_s {
   float shrink = 0.f, asym_alpha = 0.5f, ta = 1.f, tb = 1.f;
   int formula = F_PROD;
   bool binary = false, signed_data = false;
-  int n_win = 1, win = 0, cap = 2048;
+  int n_win = 1, win = 0, cap = 2048, cap_alloc = 2048;
   size_t smem_bytes = 0;
   int n_sm = 0;
-  DevBuf<int> csr_ptr, csr_idx, csc_ptr, csc_idx, split;
-  DevBuf<int2> csr_ent, csc_ent;
-  DevBuf<float> A, B;
-  DevBuf<unsigned long long> work;
-  std::vector<unsigned long long> h_work;
-  float B_min = 0.f, B_max = 0.f;
+  DevBuf<int> csr_ptr, csr_idx, csc_ptr, csc_idx, split, old2new;
+  DevBuf<int2> csr_ent, csc_ent, BN;
+  DevBuf<float> A, tileB;
+  int lpu_log2 = 3;
+  std::vector<unsigned long long> h_work;  // by ORIGINAL column index
   DevBuf<int> counter, order;
+  std::vector<int> h_order;  // cached LPT order for [order_lo, order_hi)
+  int order_lo = -1, order_hi = -1;
+  DevBuf<unsigned long long> prof;
+  bool prof_on = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 };
@@ -587,20 +802,38 @@ namespace {
 
 constexpr int GRID1D = 148 * 8;
 
+typedef void (*sim_kernel_t)(const KParams);
+sim_kernel_t kernel_for(int formula, bool binary) {
+  switch (formula) {
+    case F_PROD: return binary ? sim_topk_kernel<F_PROD, true> : sim_topk_kernel<F_PROD, false>;
+    case F_NONORM: return binary ? sim_topk_kernel<F_NONORM, true> : sim_topk_kernel<F_NONORM, false>;
+    case F_JACCARD: return binary ? sim_topk_kernel<F_JACCARD, true> : sim_topk_kernel<F_JACCARD, false>;
+    case F_DICE: return binary ? sim_topk_kernel<F_DICE, true> : sim_topk_kernel<F_DICE, false>;
+    default: return binary ? sim_topk_kernel<F_TVERSKY, true> : sim_topk_kernel<F_TVERSKY, false>;
+  }
+}
+
+int bits_for(long long n) {
+  int b = 1;
+  while ((1ll << b) < n) ++b;
+  return b;
+}
+
 void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, const float* h_data,
            const float* h_row_weights, cudaStream_t st) {
   const int n_rows = h->n_rows, n_cols = h->n_cols;
   const long long nnz = h->nnz;
+  const size_t nnz1 = (size_t)std::max<long long>(nnz, 1);
   h->n_sm = sm_count();
   B200_CUDA(cudaEventCreate(&h->ev0));
   B200_CUDA(cudaEventCreate(&h->ev1));
 
   h->csr_ptr.alloc((size_t)n_rows + 1);
-  h->csr_idx.alloc((size_t)std::max<long long>(nnz, 1));
-  DevBuf<float> data((size_t)std::max<long long>(nnz, 1));
+  DevBuf<int> idx_old(nnz1);
+  DevBuf<float> data(nnz1);
   B200_CUDA(cudaMemcpyAsync(h->csr_ptr.get(), h_indptr, sizeof(int) * ((size_t)n_rows + 1), cudaMemcpyHostToDevice, st));
   if (nnz) {
-    B200_CUDA(cudaMemcpyAsync(h->csr_idx.get(), h_indices, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(idx_old.get(), h_indices, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(data.get(), h_data, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice, st));
   }
   DevBuf<float> row_w;
@@ -622,8 +855,8 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
     } else if (h->kind == B200_SIM_ADJUSTED) {
       row_center_kernel<<<div_up((long long)n_rows * 32, 256), 256, 0, st>>>(h->csr_ptr.get(), data.get(), n_rows); count_launch();
     } else if (h->kind == B200_SIM_PEARSON) {
-      col_accum_kernel<<<GRID1D, 256, 0, st>>>(h->csr_idx.get(), data.get(), nnz, colsum.get(), nullptr, colcnt.get()); count_launch();
-      col_center_kernel<<<GRID1D, 256, 0, st>>>(h->csr_idx.get(), data.get(), nnz, colsum.get(), colcnt.get()); count_launch();
+      col_accum_kernel<<<GRID1D, 256, 0, st>>>(idx_old.get(), data.get(), nnz, colsum.get(), nullptr, colcnt.get()); count_launch();
+      col_center_kernel<<<GRID1D, 256, 0, st>>>(idx_old.get(), data.get(), nnz, colsum.get(), colcnt.get()); count_launch();
       B200_CUDA(cudaMemsetAsync(colcnt.get(), 0, sizeof(int) * (size_t)n_cols, st));
     }
   }
@@ -633,75 +866,90 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   if (nnz) { flags_kernel<<<GRID1D, 256, 0, st>>>(data.get(), nnz, flags.get()); count_launch(); }
   int hflags = 0;
   B200_CUDA(cudaMemcpyAsync(&hflags, flags.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
-  // ---- column sums of squares (before the row weights, pyx:169-194) and counts
-  if (nnz) { col_accum_kernel<<<GRID1D, 256, 0, st>>>(h->csr_idx.get(), data.get(), nnz, nullptr, colsq.get(), colcnt.get()); count_launch(); }
-  h->A.alloc((size_t)n_cols);
-  h->B.alloc((size_t)n_cols);
+  // ---- column sums of squares (before the row weights, pyx:169-194), counts, formula terms
+  if (nnz) { col_accum_kernel<<<GRID1D, 256, 0, st>>>(idx_old.get(), data.get(), nnz, nullptr, colsq.get(), colcnt.get()); count_launch(); }
+  DevBuf<float> A_old((size_t)n_cols), B_old((size_t)n_cols);
+  DevBuf<unsigned> Bkey((size_t)n_cols), Bkey_sorted((size_t)n_cols);
+  DevBuf<int> col_iota((size_t)n_cols), new2old((size_t)n_cols), cnt_new((size_t)n_cols);
   const int norm_mode = set_kind ? 0 : (h->kind == B200_SIM_ASYMMETRIC ? 2 : 1);
-  norms_kernel<<<div_up(n_cols, 256), 256, 0, st>>>(colsq.get(), n_cols, norm_mode, h->asym_alpha, h->A.get(), h->B.get()); count_launch();
+  norms_kernel<<<div_up(n_cols, 256), 256, 0, st>>>(colsq.get(), n_cols, norm_mode, h->asym_alpha, A_old.get(), B_old.get(),
+                                                    Bkey.get(), col_iota.get());
+  count_launch();
 
-  // ---- CSC: exclusive scan of the column counts, stable sort of (column, position) pairs
-  h->csc_ptr.alloc((size_t)n_cols + 1);
-  B200_CUDA(cudaMemsetAsync(h->csc_ptr.get(), 0, sizeof(int) * ((size_t)n_cols + 1), st));
+  // ---- renumber the columns by (B asc, original index asc): stable radix sort on the float bit pattern
   {
-    size_t tmp_bytes = 0;
-    B200_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, colcnt.get(), h->csc_ptr.get() + 1, n_cols, st));
-    DevBuf<unsigned char> tmp(tmp_bytes + 16);
-    B200_CUDA(cub::DeviceScan::InclusiveSum(tmp.get(), tmp_bytes, colcnt.get(), h->csc_ptr.get() + 1, n_cols, st));
-    count_launch(2);
+    size_t tb = 0;
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, Bkey.get(), Bkey_sorted.get(), col_iota.get(), new2old.get(), n_cols, 0, 32, st));
+    DevBuf<unsigned char> tmp(tb + 16);
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), tb, Bkey.get(), Bkey_sorted.get(), col_iota.get(), new2old.get(), n_cols, 0, 32, st));
+    count_launch(4);
     B200_CUDA(cudaStreamSynchronize(st));
   }
+  h->old2new.alloc((size_t)n_cols);
+  h->A.alloc((size_t)n_cols);
+  h->BN.alloc((size_t)n_cols);
+  renumber_kernel<<<div_up(n_cols, 256), 256, 0, st>>>(new2old.get(), A_old.get(), B_old.get(), colcnt.get(), n_cols,
+                                                       h->old2new.get(), h->A.get(), h->BN.get(), cnt_new.get());
+  count_launch();
   B200_CUDA(cudaStreamSynchronize(st));
   h->signed_data = (hflags & 2) != 0;
   h->binary = ((hflags & 1) == 0) && !h_row_weights;
 
-  DevBuf<int> rowid((size_t)std::max<long long>(nnz, 1)), iota((size_t)std::max<long long>(nnz, 1));
-  DevBuf<int> keys_out((size_t)std::max<long long>(nnz, 1)), perm((size_t)std::max<long long>(nnz, 1));
+  // ---- CSR in the new numbering: relabel, then sort every row segment by the new index
+  h->csr_idx.alloc(nnz1 + 8);
+  DevBuf<float> data_sorted(nnz1);
   if (nnz) {
+    DevBuf<int> idx_new(nnz1);
+    relabel_kernel<<<GRID1D, 256, 0, st>>>(idx_old.get(), h->old2new.get(), nnz, idx_new.get()); count_launch();
+    size_t tb = 0;
+    B200_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, tb, idx_new.get(), h->csr_idx.get(), data.get(), data_sorted.get(),
+                                                  (long long)nnz, (long long)n_rows, h->csr_ptr.get(), h->csr_ptr.get() + 1, st));
+    DevBuf<unsigned char> tmp(tb + 16);
+    B200_CUDA(cub::DeviceSegmentedSort::SortPairs(tmp.get(), tb, idx_new.get(), h->csr_idx.get(), data.get(), data_sorted.get(),
+                                                  (long long)nnz, (long long)n_rows, h->csr_ptr.get(), h->csr_ptr.get() + 1, st));
+    count_launch(3);
+    B200_CUDA(cudaStreamSynchronize(st));
+  }
+  idx_old.release();
+  data.release();
+
+  // ---- CSC (new numbering): exclusive scan of the column counts, stable sort of (column, position) pairs
+  h->csc_ptr.alloc((size_t)n_cols + 1);
+  B200_CUDA(cudaMemsetAsync(h->csc_ptr.get(), 0, sizeof(int) * ((size_t)n_cols + 1), st));
+  {
+    size_t tb = 0;
+    B200_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, cnt_new.get(), h->csc_ptr.get() + 1, n_cols, st));
+    DevBuf<unsigned char> tmp(tb + 16);
+    B200_CUDA(cub::DeviceScan::InclusiveSum(tmp.get(), tb, cnt_new.get(), h->csc_ptr.get() + 1, n_cols, st));
+    count_launch(2);
+    B200_CUDA(cudaStreamSynchronize(st));
+  }
+  if (nnz) {
+    DevBuf<int> rowid(nnz1), iota(nnz1), keys_out(nnz1), perm(nnz1);
     rowid_iota_kernel<<<div_up((long long)n_rows * 32, 256), 256, 0, st>>>(h->csr_ptr.get(), n_rows, rowid.get(), iota.get()); count_launch();
-    int end_bit = 1;
-    while ((1ll << end_bit) < (long long)n_cols) ++end_bit;
-    size_t tmp_bytes = 0;
-    B200_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->csr_idx.get(), keys_out.get(), iota.get(), perm.get(),
-                                              (int)nnz, 0, end_bit, st));
-    DevBuf<unsigned char> tmp(tmp_bytes + 16);
-    B200_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), tmp_bytes, h->csr_idx.get(), keys_out.get(), iota.get(), perm.get(),
-                                              (int)nnz, 0, end_bit, st));
+    size_t tb = 0;
+    const int end_bit = bits_for(n_cols);
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, h->csr_idx.get(), keys_out.get(), iota.get(), perm.get(), (int)nnz, 0, end_bit, st));
+    DevBuf<unsigned char> tmp(tb + 16);
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(), tb, h->csr_idx.get(), keys_out.get(), iota.get(), perm.get(), (int)nnz, 0, end_bit, st));
     count_launch(4);
     if (h->binary) {
       h->csc_idx.alloc((size_t)nnz);
-      build_csc_kernel<<<GRID1D, 256, 0, st>>>(perm.get(), rowid.get(), data.get(), nullptr, nnz, nullptr, h->csc_idx.get());
+      build_csc_kernel<<<GRID1D, 256, 0, st>>>(perm.get(), rowid.get(), data_sorted.get(), nullptr, nnz, nullptr, h->csc_idx.get());
     } else {
       h->csc_ent.alloc((size_t)nnz);
-      h->csr_ent.alloc((size_t)nnz);
-      build_csc_kernel<<<GRID1D, 256, 0, st>>>(perm.get(), rowid.get(), data.get(), row_w.get(), nnz, h->csc_ent.get(), nullptr);
-      build_csr_ent_kernel<<<GRID1D, 256, 0, st>>>(h->csr_idx.get(), data.get(), nnz, h->csr_ent.get()); count_launch();
+      h->csr_ent.alloc((size_t)nnz + 8);
+      build_csc_kernel<<<GRID1D, 256, 0, st>>>(perm.get(), rowid.get(), data_sorted.get(), row_w.get(), nnz, h->csc_ent.get(), nullptr);
+      build_csr_ent_kernel<<<GRID1D, 256, 0, st>>>(h->csr_idx.get(), data_sorted.get(), nnz, h->csr_ent.get()); count_launch();
     }
     count_launch();
     B200_CUDA(cudaStreamSynchronize(st));
   }
 
-  // ---- formula and norm extremes (over columns that hold entries)
   if (set_kind) {
     h->formula = h->kind == B200_SIM_JACCARD ? F_JACCARD : (h->kind == B200_SIM_DICE ? F_DICE : F_TVERSKY);
   } else {
     h->formula = h->normalize ? F_PROD : F_NONORM;
-  }
-  {
-    std::vector<float> hB((size_t)n_cols);
-    std::vector<int> hcnt((size_t)n_cols);
-    B200_CUDA(cudaMemcpy(hB.data(), h->B.get(), sizeof(float) * (size_t)n_cols, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(hcnt.data(), colcnt.get(), sizeof(int) * (size_t)n_cols, cudaMemcpyDeviceToHost));
-    float mn = 0.f, mx = 0.f;
-    bool any = false;
-    for (int j = 0; j < n_cols; ++j) {
-      if (hcnt[j] == 0) continue;
-      if (!any) { mn = mx = hB[j]; any = true; }
-      mn = std::min(mn, hB[j]);
-      mx = std::max(mx, hB[j]);
-    }
-    h->B_min = mn;
-    h->B_max = mx;
   }
 
   // ---- window geometry: the accumulator covers `win` neighbour columns; n_win passes per target column
@@ -710,34 +958,56 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   B200_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   int cap = 2048;
   while (cap < 4 * h->K) cap <<= 1;
-  B200_REQUIRE(cap <= 8 * THREADS, "topK=%d too large for the top-K kernel (max %d); use the dense path", h->K, 2 * THREADS);
+  B200_REQUIRE(cap <= 8192, "topK=%d too large for the top-K kernel (max 2048); use the dense path", h->K);
   h->cap = cap;
-  const size_t fixed = (size_t)cap * 8 + (size_t)COLCHUNK * 12 + sizeof(Shared) + 1024;
-  const long long max_cells = ((long long)max_smem - (long long)fixed) / 4;
-  B200_REQUIRE(max_cells >= 4096, "not enough shared memory (%d bytes) for the similarity kernel", max_smem);
-  int n_win = (int)((n_cols + max_cells - 1) / max_cells);
-  if (n_win < 1) n_win = 1;
+  h->cap_alloc = cap;
+  const size_t staging = (size_t)STAGE_INTS * 4;
+  int n_win = 1;
+  long long max_cells = 0;
+  for (;; ++n_win) {  // the tile-bound table grows with the window count
+    const size_t fixed = (size_t)cap * 8 + staging + (size_t)n_win * (MAXTILES + 1) * 4 + sizeof(Shared) + 1024;
+    max_cells = ((long long)max_smem - (long long)fixed) / 4;
+    max_cells = std::min<long long>(max_cells, (long long)MAXTILES * TILE);
+    B200_REQUIRE(max_cells >= 4096, "not enough shared memory (%d bytes) for the similarity kernel", max_smem);
+    if ((long long)n_win * max_cells >= n_cols) break;
+  }
   int win = (n_cols + n_win - 1) / n_win;
   win = (win + 3) & ~3;
   if (win < 4) win = 4;
   h->n_win = n_win;
   h->win = win;
-  h->smem_bytes = (size_t)win * 4 + (size_t)cap * 8 + (size_t)COLCHUNK * 12;
-  B200_CUDA(cudaFuncSetAttribute(sim_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  B200_CUDA(cudaFuncSetAttribute(sim_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  h->smem_bytes = (size_t)std::max(win, SBINS) * 4 + (size_t)cap * 8 + staging + (size_t)n_win * (MAXTILES + 1) * 4;
+  B200_CUDA(cudaFuncSetAttribute(kernel_for(h->formula, h->binary), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  h->tileB.alloc((size_t)n_win * (MAXTILES + 1));
+  tile_bounds_kernel<<<div_up((long long)n_win * (MAXTILES + 1), 128), 128, 0, st>>>(h->BN.get(), n_cols, n_win, win, h->tileB.get());
+  count_launch();
+  {
+    // lanes per row segment in the accumulate phase: enough 16-byte chunks for the average segment
+    const double avg_seg = nnz > 0 ? (double)nnz / (double)n_rows / (double)n_win : 1.0;
+    const double chunks = avg_seg / (h->binary ? 4.0 : 2.0) + 1.0;
+    int l2 = 1;
+    while (l2 < 5 && (1 << l2) < chunks) ++l2;
+    h->lpu_log2 = l2;
+  }
   if (n_win > 1) {
     h->split.alloc((size_t)n_rows * (n_win + 1));
     const long long total = (long long)n_rows * (n_win + 1);
     split_kernel<<<div_up(total, 256), 256, 0, st>>>(h->csr_ptr.get(), h->csr_idx.get(), n_rows, n_win, win, h->split.get()); count_launch();
   }
-  // ---- per-column work (for LPT ordering and the bytes model)
-  h->work.alloc((size_t)n_cols);
-  col_work_kernel<<<div_up((long long)n_cols * 32, 256), 256, 0, st>>>(h->csc_ptr.get(), h->binary ? h->csc_idx.get() : nullptr,
-                                                                      h->binary ? nullptr : h->csc_ent.get(), h->csr_ptr.get(), n_cols, h->work.get());
-  count_launch();
-  h->h_work.resize((size_t)n_cols);
-  B200_CUDA(cudaMemcpyAsync(h->h_work.data(), h->work.get(), sizeof(unsigned long long) * (size_t)n_cols, cudaMemcpyDeviceToHost, st));
-  B200_CUDA(cudaStreamSynchronize(st));
+  // ---- per-column work (for LPT ordering and the bytes model), reported by ORIGINAL column index
+  {
+    DevBuf<unsigned long long> work((size_t)n_cols);
+    col_work_kernel<<<div_up((long long)n_cols * 32, 256), 256, 0, st>>>(h->csc_ptr.get(), h->binary ? h->csc_idx.get() : nullptr,
+                                                                        h->binary ? nullptr : h->csc_ent.get(), h->csr_ptr.get(), n_cols, work.get());
+    count_launch();
+    std::vector<unsigned long long> w_new((size_t)n_cols);
+    std::vector<int> o2n((size_t)n_cols);
+    B200_CUDA(cudaMemcpyAsync(w_new.data(), work.get(), sizeof(unsigned long long) * (size_t)n_cols, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(o2n.data(), h->old2new.get(), sizeof(int) * (size_t)n_cols, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    h->h_work.resize((size_t)n_cols);
+    for (int c = 0; c < n_cols; ++c) h->h_work[(size_t)c] = w_new[(size_t)o2n[(size_t)c]];
+  }
   if (!h->binary) h->csr_idx.release();  // the AoS copy carries the indices
   h->counter.alloc(1);
   h->order.alloc((size_t)n_cols);
@@ -810,35 +1080,39 @@ int b200_sim_compute_device(b200_sim_t h, int start_col, int end_col, int32_t* d
     if (n_range == 0) return;
     B200_REQUIRE(d_idx && d_val && d_cnt, "b200_sim_compute: NULL output");
     cudaStream_t st = (cudaStream_t)stream;
-    // longest-processing-time-first order of the local columns
-    std::vector<int> order((size_t)n_range);
-    for (int i = 0; i < n_range; ++i) order[(size_t)i] = i;
-    const unsigned long long* w = h->h_work.data() + start_col;
-    std::stable_sort(order.begin(), order.end(), [w](int a, int b) { return w[a] > w[b]; });
-    B200_CUDA(cudaMemcpyAsync(h->order.get(), order.data(), sizeof(int) * (size_t)n_range, cudaMemcpyHostToDevice, st));
+    // longest-processing-time-first order of the local columns (cached per range)
+    if (h->order_lo != start_col || h->order_hi != end_col) {
+      h->h_order.resize((size_t)n_range);
+      for (int i = 0; i < n_range; ++i) h->h_order[(size_t)i] = i;
+      const unsigned long long* w = h->h_work.data() + start_col;
+      std::stable_sort(h->h_order.begin(), h->h_order.end(), [w](int a, int b) { return w[a] > w[b]; });
+      B200_CUDA(cudaMemcpyAsync(h->order.get(), h->h_order.data(), sizeof(int) * (size_t)n_range, cudaMemcpyHostToDevice, st));
+      B200_CUDA(cudaStreamSynchronize(st));
+      h->order_lo = start_col;
+      h->order_hi = end_col;
+    }
     B200_CUDA(cudaMemsetAsync(h->counter.get(), 0, sizeof(int), st));
     KParams p;
-    p.n_cols = h->n_cols; p.K = h->K; p.n_win = h->n_win; p.win = h->win; p.cap = h->cap;
-    p.formula = h->formula;
+    p.n_cols = h->n_cols; p.K = h->K; p.n_win = h->n_win; p.win = h->win; p.cap = h->cap; p.cap_alloc = h->cap_alloc;
+    p.acc_cells = std::max(h->win, SBINS);
+    p.lpu_log2 = h->lpu_log2;
+    p.tileB = h->tileB.get();
     p.se = h->shrink + 1e-6f;
     p.shrink_div = h->shrink != 0.f ? h->shrink : 1.f;
     p.ta = h->ta; p.tb = h->tb;
     p.csr_ptr = h->csr_ptr.get(); p.csr_ent = h->csr_ent.get(); p.csr_idx = h->csr_idx.get();
     p.split = h->split.get();
     p.csc_ptr = h->csc_ptr.get(); p.csc_ent = h->csc_ent.get(); p.csc_idx = h->csc_idx.get();
-    p.A = h->A.get(); p.B = h->B.get(); p.B_min = h->B_min; p.B_max = h->B_max;
+    p.A = h->A.get(); p.BN = h->BN.get(); p.old2new = h->old2new.get();
     p.col_begin = start_col; p.n_range = n_range;
     p.order = h->order.get();
     p.counter = h->counter.get();
     p.out_idx = d_idx; p.out_val = d_val; p.out_cnt = d_cnt;
     p.signed_data = h->signed_data ? 1 : 0;
+    p.prof = h->prof_on ? h->prof.get() : nullptr;
     const int grid = std::min(n_range, h->n_sm);
-    B200_CUDA(cudaStreamSynchronize(st));  // `order` is a host vector about to go out of scope
     B200_CUDA(cudaEventRecord(h->ev0, st));
-    if (h->binary)
-      sim_topk_kernel<true><<<grid, THREADS, h->smem_bytes, st>>>(p);
-    else
-      sim_topk_kernel<false><<<grid, THREADS, h->smem_bytes, st>>>(p);
+    kernel_for(h->formula, h->binary)<<<grid, THREADS, h->smem_bytes, st>>>(p);
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaEventRecord(h->ev1, st));
     h->timed = true;
@@ -860,6 +1134,30 @@ int b200_sim_compute(b200_sim_t h, int start_col, int end_col, int32_t* h_idx, f
     B200_CUDA(cudaMemcpy(h_idx, d_idx.get(), sizeof(int) * n_range * h->K, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(h_val, d_val.get(), sizeof(float) * n_range * h->K, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(h_cnt, d_cnt.get(), sizeof(int) * n_range, cudaMemcpyDeviceToHost));
+  });
+}
+
+int b200_sim_debug_set_cap(b200_sim_t h, int cap) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr, "b200_sim_debug_set_cap: NULL handle");
+    B200_REQUIRE(cap > h->K && cap <= h->cap_alloc, "b200_sim_debug_set_cap: cap must be in (K, %d]", h->cap_alloc);
+    h->cap = cap;
+  });
+}
+
+int b200_sim_debug_phase_cycles(b200_sim_t h, int enable, uint64_t* out8) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr, "b200_sim_debug_phase_cycles: NULL handle");
+    if (h->prof.n == 0) {
+      h->prof.alloc(8);
+      B200_CUDA(cudaMemset(h->prof.get(), 0, 8 * sizeof(unsigned long long)));
+    }
+    if (out8) {
+      B200_CUDA(cudaDeviceSynchronize());
+      B200_CUDA(cudaMemcpy(out8, h->prof.get(), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      B200_CUDA(cudaMemset(h->prof.get(), 0, 8 * sizeof(unsigned long long)));
+    }
+    h->prof_on = enable != 0;
   });
 }
 

@@ -19,8 +19,11 @@ def _gpu_cls():
     return Compute_Similarity_Cython
 
 
-def _check(X, cols=None, **kw):
+def _check(X, cols=None, debug_cap=None, **kw):
     sim = _gpu_cls()(X, **kw)
+    if debug_cap is not None:
+        from recsys2019_deeplearning_evaluation_b200 import _lib
+        _lib.check(_lib.load().b200_sim_debug_set_cap(sim._h, debug_cap))
     W = sim.compute_similarity()
     assert sps.isspmatrix_csr(W) and W.dtype == np.float32 and W.shape == (X.shape[1], X.shape[1])
     assert W.has_sorted_indices or (W.sorted_indices().indices == W.indices).all()
@@ -134,3 +137,16 @@ def test_dense_control_recipe_xtx():
     G = D.astype(np.float64).T @ D.astype(np.float64)
     np.fill_diagonal(G, 0)
     assert np.allclose(W, G, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("values", ["binary", "continuous", "ratings"])
+def test_candidate_buffer_overflow_path(values):
+    """A tiny logical candidate buffer forces the prune-and-rescan path on every column."""
+    X = synth_urm(3000, 1500, 0.03, seed=21, values=values)
+    _check(X, cols=np.arange(0, 1500, 5), debug_cap=40, topK=30, shrink=5, similarity="cosine")
+    _check(X, cols=np.arange(0, 1500, 7), debug_cap=33, topK=30, shrink=0, similarity="jaccard")
+
+
+def test_overflow_path_multiwindow_signed():
+    X = synth_urm(8000, 110_000, 0.0008, seed=22, values="ratings")
+    _check(X, cols=np.arange(0, 110_000, 1999), debug_cap=64, topK=20, shrink=1, similarity="pearson")

@@ -20,4 +20,14 @@ for r in range(reps):
     t = time.time(); tab = sim.compute_topk_device(0, X.shape[1]); torch.cuda.synchronize(); dt = time.time() - t
     ms = sim.last_kernel_ms()
     print("rep %d: wall %.3fs kernel %.3f ms  %.3e cols/s  alg %.2f GB -> %.1f GB/s" % (r, dt, ms, X.shape[1] / (ms * 1e-3), alg / 1e9, alg / 1e9 / (ms * 1e-3)), flush=True)
+import ctypes
+from recsys2019_deeplearning_evaluation_b200 import _lib
+L = _lib.load()
+_lib.check(L.b200_sim_debug_phase_cycles(sim._h, 1, None))
+tab = sim.compute_topk_device(0, X.shape[1]); torch.cuda.synchronize()
+out = (ctypes.c_uint64 * 8)()
+_lib.check(L.b200_sim_debug_phase_cycles(sim._h, 0, out))
+cyc = np.array(list(out), dtype=np.float64)
+names = ["stage", "mac", "bootstrap", "scan", "eval", "select", "emit", "-"]
+print("phase cycles per column: " + "  ".join("%s=%.0f" % (n, c / X.shape[1]) for n, c in zip(names, cyc)) + "  total=%.0f (kernel %.3f ms)" % (cyc.sum() / X.shape[1], sim.last_kernel_ms()), flush=True)
 t = time.time(); W = sim.table_to_csr(tab); print("to_csr %.3fs nnz=%d" % (time.time() - t, W.nnz), flush=True)
