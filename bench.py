@@ -1,0 +1,411 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path BASELINE.json names: ItemKNN cosine top-K rows/sec (and BPR samples/sec as a
+secondary figure) on a synthetic CSR URM.
+
+    python bench.py --gpus N --steps K --warmup W [--impl b200|reference] [--workload C5]
+
+One JSON line on stdout (rank 0).  A "step" is one full pass of the similarity hot path over the workload
+(all n_items columns: accumulate + normalise + top-K, plus the all-gather when N > 1) with the URM already
+resident in HBM.  `e2e` is the same metric through the reference-facing Python call
+(Compute_Similarity_Cython(URM, ...).compute_similarity() -> scipy CSR) with HOST buffers: H2D of the CSR,
+device-side constructor work, kernel, CSR assembly and D2H all inside the timed region.
+
+`--impl reference` times the reference's own Cython (oracle/_ref, compiled unmodified) on the host cores,
+column-sharded over worker processes with the reference's own start_col/end_col hook.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ItemKNN cosine top-K rows/sec"
+SIM_KW = dict(topK=200, shrink=100, normalize=True, similarity="cosine")  # SURVEY.md 8(d) hyper-parameters
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch(workload):
+    """dram bytes per launch of the top-K kernel from the committed ncu summary of this workload, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: the unmodified reference Cython class on host cores (oracle/_ref), or the numpy port when
+    the compiled reference is absent.  Rank 0 only."""
+    if rank != 0:
+        return
+    from recsys2019_deeplearning_evaluation_b200.synth import synth_config, CONFIGS
+    from oracle import ref_loader
+    t0 = time.time()
+    X = synth_config(args.workload, values=args.values)
+    n_items = X.shape[1]
+    log("[reference] URM %s nnz=%d generated in %.1fs" % (X.shape, X.nnz, time.time() - t0))
+    mod = ref_loader.load("Compute_Similarity_Cython")
+    kind = "reference" if mod is not None else "port"
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, args.ref_workers))
+    slice_cols = args.ref_slice
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    conns, procs = [], []
+    for w in range(workers):
+        a, b = ctx.Pipe()
+        pr = ctx.Process(target=_ref_worker, args=(b, X, kind, w), daemon=True)
+        pr.start()
+        conns.append(a)
+        procs.append(pr)
+    ctor_s = max(c.recv() for c in conns)  # constructors run concurrently; the slowest one
+    log("[reference] %d workers constructed (%s) in %.1fs" % (workers, kind, ctor_s))
+    rng = np.random.default_rng(0)
+
+    def one_step():
+        starts = rng.integers(1, max(2, n_items - slice_cols - 1), size=workers)
+        t = time.perf_counter()
+        for c, s in zip(conns, starts):
+            c.send((int(s), int(s) + slice_cols))
+        for c in conns:
+            c.recv()
+        return time.perf_counter() - t
+
+    for _ in range(args.warmup):
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
+    for c in conns:
+        c.send(None)
+    total = sum(times)
+    cols = workers * slice_cols * args.steps
+    rate = cols / total
+    e2e_rate = n_items / (ctor_s + n_items / rate)
+    nu, ni, dens = CONFIGS[args.workload]
+    sample = "%d workers x %d-column slices via start_col/end_col, %d steps; constructor %.1fs excluded from value, included in e2e (projected full fit)" % (
+        workers, slice_cols, args.steps, ctor_s)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s ItemKNN cosine topK=200 shrink=100 on %dx%d density %.4g %s URM" % (
+            args.workload, nu, ni, dens, args.values), "timing": "bounded sample of the column axis per step"},
+        "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": workers, "kind": kind, "sample": sample},
+        "e2e": {"value": e2e_rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores": cores,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def _ref_worker(conn, X, kind, w):
+    from oracle import ref_loader
+    t = time.perf_counter()
+    if kind == "reference":
+        import io, contextlib
+        cls = ref_loader.load("Compute_Similarity_Cython").Compute_Similarity_Cython
+        obj = cls(X, **SIM_KW)
+    else:
+        from oracle.similarity_oracle import SimilarityOracle
+        obj = SimilarityOracle(X, **SIM_KW)
+    conn.send(time.perf_counter() - t)
+    devnull = open(os.devnull, "w")
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            return
+        so = os.dup(1)
+        os.dup2(devnull.fileno(), 1)  # the reference prints a progress line per call
+        try:
+            obj.compute_similarity(start_col=msg[0], end_col=msg[1])
+        finally:
+            sys.stdout.flush()
+            os.dup2(so, 1)
+            os.close(so)
+        conn.send(1)
+
+
+def cpu_baseline_leg(X, budget_cols):
+    """Reference Cython (1 thread, as shipped) on a bounded slice of the same URM, for the b200 arm's JSON."""
+    from oracle import ref_loader
+    mod = ref_loader.load("Compute_Similarity_Cython")
+    kind = "reference" if mod is not None else "port"
+    t = time.perf_counter()
+    if mod is not None:
+        obj = mod.Compute_Similarity_Cython(X, **SIM_KW)
+    else:
+        from oracle.similarity_oracle import SimilarityOracle
+        obj = SimilarityOracle(X, **SIM_KW)
+    ctor = time.perf_counter() - t
+    n = X.shape[1]
+    lo = max(1, n // 3)
+    hi = min(n - 1, lo + budget_cols)
+    so = os.dup(1)
+    devnull = open(os.devnull, "w")
+    os.dup2(devnull.fileno(), 1)
+    try:
+        t = time.perf_counter()
+        obj.compute_similarity(start_col=lo, end_col=hi)
+        dt = time.perf_counter() - t
+    finally:
+        sys.stdout.flush()
+        os.dup2(so, 1)
+        os.close(so)
+    return {"value": (hi - lo) / dt, "unit": "rows/s", "cores": 1, "kind": kind,
+            "sample": "columns [%d,%d) of the same URM in %.1fs, 1 thread (the reference is single-threaded); constructor %.1fs not counted" % (lo, hi, dt, ctor)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+def pinned_csr(X):
+    """scipy CSR whose three arrays live in pinned host memory (so the e2e H2D runs at PCIe speed)."""
+    import torch
+    import scipy.sparse as sps
+    bufs = []
+    for a in (X.data.astype(np.float32, copy=False), X.indices.astype(np.int32, copy=False),
+              X.indptr.astype(np.int32, copy=False)):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        bufs.append(t)
+    M = sps.csr_matrix((bufs[0].numpy(), bufs[1].numpy(), bufs[2].numpy()), shape=X.shape, copy=False)
+    M.has_sorted_indices = True
+    M._pinned = bufs
+    return M
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from recsys2019_deeplearning_evaluation_b200.synth import synth_config, CONFIGS
+    from recsys2019_deeplearning_evaluation_b200.similarity import Compute_Similarity_Cython, topk_table_to_csr
+    from recsys2019_deeplearning_evaluation_b200 import _lib
+    from recsys2019_deeplearning_evaluation_b200.dist import balanced_ranges, allgather_topk_tables
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs CUDA (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    t0 = time.time()
+    X = synth_config(args.workload, values=args.values)
+    n_users, n_items = X.shape
+    log("[rank %d] URM %s nnz=%d generated in %.1fs" % (rank, X.shape, X.nnz, time.time() - t0))
+    Xp = pinned_csr(X)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- resident-input arm: handle built once, a step = kernel (+ all-gather)
+    sim = Compute_Similarity_Cython(Xp, **SIM_KW)
+    bounds = balanced_ranges(sim.column_work(), world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+
+    def step():
+        tab = sim.compute_topk_device(lo, hi)
+        if world > 1:
+            return allgather_topk_tables(tab.idx, tab.val, tab.cnt, bounds)
+        return tab.idx, tab.val, tab.cnt
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step()
+        kernel_ms.append(None)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = n_items * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- kernel-only roofline leg (CUDA events around the kernel on its launching stream, inside the library)
+    kms = []
+    for _ in range(args.steps):
+        sim.compute_topk_device(lo, hi)
+        kms.append(sim.last_kernel_ms())
+    kernel_avg_ms = float(np.mean(kms))
+    ent = sim.gathered_entries(lo, hi)
+    bpe = 4 if sim.binary_path else 8
+    share = (hi - lo) / float(n_items)
+    # bytes = bpe * sum_u len_u^2 (row gathers) + CSR + CSC read once + 8*K*n_items written
+    alg_bytes = bpe * ent + 2 * bpe * X.nnz * share + 8 * sim.K * (hi - lo)
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / 1e9 / (kernel_avg_ms * 1e-3)
+    traffic = ncu_traffic_per_launch(args.workload) if world == 1 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "sim_topk_kernel", "kernel_ms": kernel_avg_ms,
+                "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "bytes_model": "%d B x %d gathered row entries + CSR/CSC once + 8 B x K x columns" % (bpe, ent)}
+
+    # ---- e2e arm: host scipy CSR in -> scipy CSR out through the reference-facing class
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h2d = X.data.nbytes + X.indices.nbytes + X.indptr.nbytes
+    d2h = 0
+    e2e_times = []
+    for it in range(e2e_steps + 1):  # first pass is a warm-up
+        barrier()
+        t = time.perf_counter()
+        s2 = Compute_Similarity_Cython(Xp, **SIM_KW)
+        tab = s2.compute_topk_device(lo, hi)
+        if world > 1:
+            gi, gv, gc = allgather_topk_tables(tab.idx, tab.val, tab.cnt, bounds)
+        else:
+            gi, gv, gc = tab.idx, tab.val, tab.cnt
+        if rank == 0:
+            W = topk_table_to_csr(n_items, s2.K, gi.contiguous(), gv.contiguous(), gc.contiguous())
+            d2h = W.data.nbytes + W.indices.nbytes + W.indptr.nbytes
+        barrier()
+        dt = time.perf_counter() - t
+        s2._dealloc()
+        if it > 0:
+            e2e_times.append(dt)
+    e2e_s = float(np.mean(e2e_times))
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline_leg(X, args.cpu_cols)
+        except Exception as ex:  # the GPU numbers stand without it
+            cpu = {"value": None, "unit": "rows/s", "cores": 1, "kind": "unavailable", "sample": repr(ex)}
+    nu, ni, dens = CONFIGS[args.workload]
+    name, sms, mem = _lib.device_info()
+    out = {
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "i32 counts + f32" if sim.binary_path else "f32", "data": "synthetic",
+        "config": {"workload": "%s ItemKNN cosine topK=200 shrink=100 on %dx%d density %.4g %s URM" % (
+            args.workload, nu, ni, dens, args.values),
+            "windows": sim.n_windows, "binary_path": sim.binary_path,
+            "parallelism": "item-sharded x%d + NCCL all-gather of [n_items/N, K] idx/val" % world if world > 1 else "1 GPU",
+            "timing": "inputs (CSR+CSC %.2f GB) larger than the 126 MB L2; no explicit flush" % (2 * bpe * X.nnz / 1e9)},
+        "clocks": clocks,
+        "e2e": {"value": n_items / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "seconds_per_fit": e2e_s, "steps": e2e_steps,
+                "what": "Compute_Similarity_Cython(host scipy CSR in pinned memory).compute_similarity() -> scipy CSR"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "device": name,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C5", help="C1..C5 (synth.CONFIGS); the metric is quoted on C5")
+    ap.add_argument("--values", default="binary", choices=["binary", "ratings", "continuous"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-cols", type=int, default=2000, help="columns in the CPU-baseline slice")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-workers", type=int, default=16)
+    ap.add_argument("--ref-slice", type=int, default=250)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,8 @@ int b200_sim_debug_phase_cycles(b200_sim_t h, int enable, uint64_t* out8);
 int b200_sim_last_kernel_ms(b200_sim_t h, float* ms);
 /* sum over columns [start,end) of the gathered-entry count  sum_{u in col} len_u  (SURVEY 8(d) bytes model) */
 int b200_sim_work(b200_sim_t h, int start_col, int end_col, int64_t* gathered_entries);
+/* the same quantity per (original) column, n_cols int64 values: the weights of the multi-GPU column partition */
+int b200_sim_col_work(b200_sim_t h, int64_t* out_n_cols);
 
 #ifdef __cplusplus
 }

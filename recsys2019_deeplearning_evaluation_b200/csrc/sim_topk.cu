@@ -1170,6 +1170,13 @@ int b200_sim_last_kernel_ms(b200_sim_t h, float* ms) {
   });
 }
 
+int b200_sim_col_work(b200_sim_t h, int64_t* out_n_cols) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr && out_n_cols != nullptr, "b200_sim_col_work: NULL argument");
+    for (int c = 0; c < h->n_cols; ++c) out_n_cols[c] = (int64_t)h->h_work[(size_t)c];
+  });
+}
+
 int b200_sim_work(b200_sim_t h, int start_col, int end_col, int64_t* gathered_entries) {
   return guarded([&] {
     B200_REQUIRE(h != nullptr && gathered_entries != nullptr, "b200_sim_work: NULL argument");

@@ -1,0 +1,73 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
+
+K1 shards the item axis: the URM is replicated, rank r computes the top-K rows of a contiguous
+column range chosen so that the ranges carry equal gathered-entry work, and one all-gather of the fixed-shape
+[cols_per_rank_max, K] idx/val slabs (+ counts) gives every rank the full table.  The reference has no
+distributed path; its hook is compute_similarity(start_col, end_col) (Compute_Similarity_Cython.pyx:413,450-454).
+"""
+import numpy as np
+
+
+def balanced_ranges(work, world_size):
+    """Contiguous ranges [lo_r, hi_r) covering [0, len(work)) with (nearly) equal sums of `work`.
+    Returns an int64 array of world_size + 1 boundaries.  Pure host logic (tested on CPU)."""
+    work = np.asarray(work, dtype=np.float64)
+    n = len(work)
+    bounds = np.zeros(world_size + 1, np.int64)
+    bounds[-1] = n
+    if n == 0 or world_size == 1:
+        return bounds
+    csum = np.cumsum(work + 1e-9)  # strictly increasing so that empty columns still get spread
+    total = csum[-1]
+    for r in range(1, world_size):
+        bounds[r] = int(np.searchsorted(csum, total * r / world_size, side="left")) + 1
+    bounds[1:-1] = np.clip(bounds[1:-1], 0, n)
+    bounds = np.maximum.accumulate(bounds)
+    return bounds
+
+
+def allgather_topk_tables(idx, val, cnt, bounds, group=None):
+    """idx/val: [n_local, K] torch tensors of this rank's range, cnt: [n_local].  Every rank contributes a slab
+    padded to the largest range; returns the full [n_cols, K] idx/val and [n_cols] cnt on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = (bounds[1:] - bounds[:-1]).astype(np.int64)
+    m = int(sizes.max())
+    K = idx.shape[1]
+    n_local = int(sizes[rank])
+
+    def pad(t, fill):
+        out = torch.full((m,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+        if n_local:
+            out[:n_local] = t[:n_local]
+        return out
+
+    send_idx, send_val, send_cnt = pad(idx, -1), pad(val, 0), pad(cnt, 0)
+    g_idx = torch.empty((world * m, K), dtype=idx.dtype, device=idx.device)
+    g_val = torch.empty((world * m, K), dtype=val.dtype, device=val.device)
+    g_cnt = torch.empty((world * m,), dtype=cnt.dtype, device=cnt.device)
+    dist.all_gather_into_tensor(g_idx, send_idx, group=group)
+    dist.all_gather_into_tensor(g_val, send_val, group=group)
+    dist.all_gather_into_tensor(g_cnt, send_cnt, group=group)
+    if all(int(s) == m for s in sizes):
+        return g_idx, g_val, g_cnt
+    keep = torch.cat([torch.arange(r * m, r * m + int(sizes[r]), device=idx.device) for r in range(world)])
+    return g_idx[keep], g_val[keep], g_cnt[keep]
+
+
+def compute_similarity_sharded(sim, group=None, assemble=True):
+    """Item-sharded compute_similarity: every rank holds the same `sim` (Compute_Similarity_Cython built from the
+    replicated URM).  Returns the scipy CSR W (on every rank) or, with assemble=False, the gathered device table."""
+    import torch.distributed as dist
+    from .similarity import topk_table_to_csr
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    bounds = balanced_ranges(sim.column_work(), world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    tab = sim.compute_topk_device(lo, hi)
+    g_idx, g_val, g_cnt = allgather_topk_tables(tab.idx, tab.val, tab.cnt, bounds, group)
+    if not assemble:
+        return g_idx, g_val, g_cnt
+    return topk_table_to_csr(sim.n_columns, sim.K, g_idx.contiguous(), g_val.contiguous(), g_cnt.contiguous())

@@ -145,6 +145,12 @@ class Compute_Similarity_Cython:
         _lib.check(self._lib.b200_sim_work(self._h, lo, hi, ctypes.byref(out)))
         return int(out.value)
 
+    def column_work(self):
+        """Per-column gathered-entry counts (int64[n_columns]) -- weights for the multi-GPU partition."""
+        out = np.empty(self.n_columns, np.int64)
+        _lib.check(self._lib.b200_sim_col_work(self._h, _lib.ptr(out)))
+        return out
+
     def _dealloc(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.b200_sim_destroy(self._h)

@@ -1,0 +1,80 @@
+"""CPU: host-side logic -- synthetic generator, column partition, the multi-rank gather (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from recsys2019_deeplearning_evaluation_b200.dist import balanced_ranges
+from recsys2019_deeplearning_evaluation_b200.synth import synth_urm, CONFIGS
+
+
+def test_synth_deterministic_sorted_binary():
+    A = synth_urm(300, 100, 0.05, seed=3)
+    B = synth_urm(300, 100, 0.05, seed=3)
+    assert (A.indices == B.indices).all() and (A.indptr == B.indptr).all()
+    assert A.dtype == np.float32 and (A.data == 1).all()
+    for r in range(300):
+        row = A.indices[A.indptr[r]:A.indptr[r + 1]]
+        assert (np.diff(row) > 0).all()
+    Z = synth_urm(2000, 300, 0.02, seed=1, values="ratings", popularity=1.0)
+    cnt = np.bincount(Z.indices, minlength=300)
+    assert cnt[:10].sum() > 5 * cnt[-10:].sum()
+    assert set(CONFIGS) == {"C1", "C2", "C3", "C4", "C5"}
+
+
+def test_balanced_ranges_properties():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        w = rng.integers(0, 1000, 997)
+        b = balanced_ranges(w, world)
+        assert b[0] == 0 and b[-1] == 997 and (np.diff(b) >= 0).all()
+        sums = [w[b[i]:b[i + 1]].sum() for i in range(world)]
+        assert max(sums) - min(sums) <= 2 * w.max()
+    assert balanced_ranges(np.zeros(10), 4)[-1] == 10
+    assert list(balanced_ranges([5], 3))[-1] == 1
+    assert list(balanced_ranges([], 2)) == [0, 0, 0]
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gather_worker(rank, world, port, sizes, K, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from recsys2019_deeplearning_evaluation_b200.dist import allgather_topk_tables
+    bounds = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(sizes[rank])
+    base = int(bounds[rank])
+    idx = (torch.arange(n * K, dtype=torch.int32).reshape(n, K) + base * K)
+    val = idx.to(torch.float32) * 0.5
+    cnt = torch.full((n,), rank + 1, dtype=torch.int32)
+    g_idx, g_val, g_cnt = allgather_topk_tables(idx, val, cnt, bounds)
+    q.put((rank, g_idx.numpy().copy(), g_val.numpy().copy(), g_cnt.numpy().copy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sizes", [[5, 5], [7, 3], [0, 4]])
+def test_allgather_topk_tables_gloo_world2(sizes):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    K = 4
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, sizes, K, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = sum(sizes)
+    want_idx = np.arange(n * K, dtype=np.int32).reshape(n, K)
+    want_cnt = np.concatenate([np.full(sizes[0], 1), np.full(sizes[1], 2)]).astype(np.int32)
+    for rank, gi, gv, gc in res:
+        assert gi.shape == (n, K) and (gi == want_idx).all()
+        assert np.allclose(gv, want_idx * 0.5) and (gc == want_cnt).all()
