@@ -105,6 +105,46 @@ int b200_sim_work(b200_sim_t h, int start_col, int end_col, int64_t* gathered_en
 /* the same quantity per (original) column, n_cols int64 values: the weights of the multi-GPU column partition */
 int b200_sim_col_work(b200_sim_t h, int64_t* out_n_cols);
 
+/* ------------------------------------------------------------------------------------------------
+ * K2: matrix-factorisation SGD epochs, BPR-MF and FunkSVD  (hot path ii)
+ * replaces  MatrixFactorization/Cython/MatrixFactorization_Cython_Epoch.pyx:51-987
+ *           (ctor :96-151, epochIteration_Cython :276-286, BPR :583-678, FunkSVD :289-390,
+ *            apply :773-832, adaptive_gradient :838-876, samplers :881-987, getters :688-705)
+ * AsySVD (:396-578) is out of scope.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200_mf_s* b200_mf_t;
+
+enum b200_mf_algorithm { B200_MF_BPR = 0, B200_MF_FUNK_SVD = 1 };
+enum b200_sgd_mode { B200_SGD = 0, B200_ADAGRAD = 1, B200_RMSPROP = 2, B200_ADAM = 3 };
+enum b200_sampler { B200_SAMPLER_GLIBC = 0, /* host replay of srand(seed)/rand(), the reference's stream */
+                    B200_SAMPLER_PHILOX = 1 /* Philox4x32-10 on the device, same acceptance rules */ };
+
+/* URM: CSR, sorted indices (pyx:118-119).  h_user_factors / h_item_factors: the initial factors, row-major
+ * [n_users x f] / [n_items x f] doubles -- the caller draws them exactly as pyx:177-178 does (numpy legacy RNG)
+ * so that parity runs start from the reference's own initial point.  has_seed == 0 mirrors random_seed=None.
+ * hogwild != 0: no mini-batch barrier, every sample updates at once (batch_size is then only used for the
+ * per-epoch sample count, pyx:586 / :292). */
+int b200_mf_create(b200_mf_t* out, int64_t n_users, int64_t n_items, int64_t nnz, const int32_t* h_indptr,
+                   const int32_t* h_indices, const float* h_data, int n_factors, int algorithm, int batch_size,
+                   float negative_interactions_quota, float learning_rate, int use_bias, float user_reg,
+                   float item_reg, float bias_reg, float positive_reg, float negative_reg, int sgd_mode,
+                   float gamma, float beta_1, float beta_2, const double* h_user_factors,
+                   const double* h_item_factors, int has_seed, uint32_t random_seed, int sampler, int hogwild);
+int b200_mf_destroy(b200_mf_t h);
+/* epochIteration_Cython() (pyx:276-286): (n_users or nnz)/batch_size + 1 mini-batches */
+int b200_mf_epoch(b200_mf_t h, void* stream);
+int b200_mf_samples_last_epoch(b200_mf_t h, int64_t* n);
+/* the (user, item, neg item | rating) stream the last epoch consumed (for replaying it through the oracle) */
+int b200_mf_get_samples(b200_mf_t h, int32_t* u, int32_t* i, int32_t* j, float* r);
+/* get_USER_factors / get_ITEM_factors / get_USER_bias / get_ITEM_bias / get_GLOBAL_bias (pyx:688-705);
+ * any pointer may be NULL; doubles like the reference's arrays */
+int b200_mf_get_factors(b200_mf_t h, double* user_factors, double* item_factors, double* user_bias,
+                        double* item_bias, double* global_bias);
+/* device pointers of the fp32 factor matrices (scoring without a host round trip) */
+int b200_mf_device_factors(b200_mf_t h, float** d_user_factors, float** d_item_factors);
+/* device time of the last epoch (sampling kernel + epoch kernel), CUDA events on the launching stream */
+int b200_mf_last_epoch_ms(b200_mf_t h, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,18 @@ SIGNATURES = {
     "b200_sim_last_kernel_ms": (ctypes.c_int, [c_void, c_float_p]),
     "b200_sim_col_work": (ctypes.c_int, [c_void, c_void]),
     "b200_sim_work": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, c_i64_p]),
+    "b200_mf_create": (ctypes.c_int, [ctypes.POINTER(c_void), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void, c_void, c_void,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                      ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                      ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void, c_void, ctypes.c_int, ctypes.c_uint32,
+                                      ctypes.c_int, ctypes.c_int]),
+    "b200_mf_destroy": (ctypes.c_int, [c_void]),
+    "b200_mf_epoch": (ctypes.c_int, [c_void, c_void]),
+    "b200_mf_samples_last_epoch": (ctypes.c_int, [c_void, c_i64_p]),
+    "b200_mf_get_samples": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_void]),
+    "b200_mf_get_factors": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_void, c_void]),
+    "b200_mf_device_factors": (ctypes.c_int, [c_void, ctypes.POINTER(c_void), ctypes.POINTER(c_void)]),
+    "b200_mf_last_epoch_ms": (ctypes.c_int, [c_void, c_float_p]),
 }
 
 _lib = None

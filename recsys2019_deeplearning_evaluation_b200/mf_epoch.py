@@ -1,0 +1,146 @@
+"""Host-side mirror of MatrixFactorization/Cython/MatrixFactorization_Cython_Epoch.pyx:51-987 (BPR-MF and FunkSVD)
+backed by libb200rec.so.  Same constructor signature, `epochIteration_Cython()` and getters (pyx:688-705).
+
+Extra keyword arguments (not in the reference):
+    sampler = "glibc"   sample stream replayed with glibc's srand(seed)/rand(): the reference's own stream
+              "philox"  Philox4x32-10 drawn on the device (same acceptance rules, different numbers)
+    hogwild = False     True drops the mini-batch barrier (every sample updates at once)
+
+Declared differences (DESIGN.md "K2"): parameters and optimiser state are fp32 on the device (fp64 in pyx:78,
+:177-178); AsySVD is not provided; `random_seed=None` starts glibc's default stream (seed 1) per object instead of
+continuing the process-wide libc state.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sps
+
+from . import _lib
+
+_ALGO = {"MF_BPR": 0, "FUNK_SVD": 1}
+_MODE = {"sgd": 0, "adagrad": 1, "rmsprop": 2, "adam": 3}
+_SAMPLER = {"glibc": 0, "philox": 1}
+
+
+class MatrixFactorization_Cython_Epoch:
+    SGD_MODE_VALUES = ["sgd", "adam", "adagrad", "rmsprop"]
+    ALGORITHM_NAME_VALUES = ["FUNK_SVD", "ASY_SVD", "MF_BPR"]
+
+    def __init__(self, URM_train, n_factors=1, algorithm_name=None, batch_size=1, negative_interactions_quota=0.5,
+                 learning_rate=1e-3, use_bias=False, user_reg=0.0, item_reg=0.0, bias_reg=0.0, positive_reg=0.0,
+                 negative_reg=0.0, verbose=False, print_step_seconds=300, random_seed=None, init_mean=0.0,
+                 init_std_dev=0.1, sgd_mode="sgd", gamma=0.995, beta_1=0.9, beta_2=0.999,
+                 sampler="glibc", hogwild=False):
+        self._h = ctypes.c_void_p()
+        self._lib = _lib.load()
+        if sgd_mode not in self.SGD_MODE_VALUES:  # pyx:108-109
+            raise ValueError("Value for 'sgd_mode' not recognized. Acceptable values are {}, provided was '{}'".format(
+                self.SGD_MODE_VALUES, sgd_mode))
+        if algorithm_name not in self.ALGORITHM_NAME_VALUES:  # pyx:111-112
+            raise ValueError("Value for 'algorithm_name' not recognized. Acceptable values are {}, provided was '{}'".format(
+                self.ALGORITHM_NAME_VALUES, algorithm_name))
+        if algorithm_name == "ASY_SVD":
+            raise NotImplementedError("ASY_SVD (pyx:396-578) is not on the CUDA path")
+        if sampler not in _SAMPLER:
+            raise ValueError("sampler must be 'glibc' or 'philox'")
+        X = sps.csr_matrix(URM_train, dtype=np.float32)  # check_matrix(URM_train, 'csr') + sorted_indices, pyx:116-117
+        if not X.has_sorted_indices:
+            X = X.sorted_indices()
+        self.n_users, self.n_items = X.shape
+        self.n_factors = int(n_factors)
+        self.batch_size = int(batch_size)
+        self.algorithm_name = algorithm_name
+        if random_seed is not None:  # pyx:145-147
+            np.random.seed(seed=random_seed)
+        # pyx:177-178: user factors first, then item factors, from numpy's legacy global RNG
+        U0 = np.random.normal(init_mean, init_std_dev, (self.n_users, self.n_factors)).astype(np.float64)
+        V0 = np.random.normal(init_mean, init_std_dev, (self.n_items, self.n_factors)).astype(np.float64)
+        indptr = np.ascontiguousarray(X.indptr, np.int32)
+        indices = np.ascontiguousarray(X.indices, np.int32)
+        data = np.ascontiguousarray(X.data, np.float32)
+        _lib.check(self._lib.b200_mf_create(
+            ctypes.byref(self._h), self.n_users, self.n_items, X.nnz, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data),
+            self.n_factors, _ALGO[algorithm_name], self.batch_size, float(negative_interactions_quota), float(learning_rate),
+            int(bool(use_bias)), float(user_reg), float(item_reg), float(bias_reg), float(positive_reg), float(negative_reg),
+            _MODE[sgd_mode], float(gamma), float(beta_1), float(beta_2), _lib.ptr(U0), _lib.ptr(V0),
+            int(random_seed is not None), int(random_seed) & 0xFFFFFFFF if random_seed is not None else 0,
+            _SAMPLER[sampler], int(bool(hogwild))))
+        self.use_bias = bool(use_bias)
+
+    def epochIteration_Cython(self):
+        import torch
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(self._lib.b200_mf_epoch(self._h, st))
+
+    def samples_last_epoch(self):
+        n = ctypes.c_int64()
+        _lib.check(self._lib.b200_mf_samples_last_epoch(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def last_epoch_ms(self):
+        ms = ctypes.c_float()
+        _lib.check(self._lib.b200_mf_last_epoch_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def get_samples(self):
+        """(u, i, j) for MF_BPR or (u, i, rating) for FUNK_SVD of the last epoch."""
+        n = self.samples_last_epoch()
+        u = np.empty(n, np.int32); i = np.empty(n, np.int32)
+        if self.algorithm_name == "MF_BPR":
+            j = np.empty(n, np.int32)
+            _lib.check(self._lib.b200_mf_get_samples(self._h, _lib.ptr(u), _lib.ptr(i), _lib.ptr(j), None))
+            return u, i, j
+        r = np.empty(n, np.float32)
+        _lib.check(self._lib.b200_mf_get_samples(self._h, _lib.ptr(u), _lib.ptr(i), None, _lib.ptr(r)))
+        return u, i, r
+
+    def _get(self, which):
+        U = np.empty((self.n_users, self.n_factors), np.float64) if which == 0 else None
+        V = np.empty((self.n_items, self.n_factors), np.float64) if which == 1 else None
+        bu = np.empty(self.n_users, np.float64) if which == 2 else None
+        bi = np.empty(self.n_items, np.float64) if which == 3 else None
+        mu = np.empty(1, np.float64) if which == 4 else None
+        _lib.check(self._lib.b200_mf_get_factors(self._h, _lib.ptr(U), _lib.ptr(V), _lib.ptr(bu), _lib.ptr(bi), _lib.ptr(mu)))
+        return (U, V, bu, bi, mu)[which]
+
+    def get_USER_factors(self):
+        return self._get(0)
+
+    def get_ITEM_factors(self):
+        return self._get(1)
+
+    def get_USER_bias(self):
+        return self._get(2)
+
+    def get_ITEM_bias(self):
+        return self._get(3)
+
+    def get_GLOBAL_bias(self):
+        return np.array(self._get(4)[0])
+
+    def _dealloc(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.b200_mf_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self._dealloc()
+        except Exception:
+            pass
+
+
+def smoke():
+    """One BPR-MF epoch on cuda:0 against the C oracle (same replayed sample stream)."""
+    from .synth import synth_urm
+    from oracle.sgd_oracle import MFOracle  # test infrastructure; smoke() is one of its permitted callers
+    X = synth_urm(500, 200, 0.05, seed=2)
+    kw = dict(n_factors=32, algorithm_name="MF_BPR", batch_size=64, learning_rate=0.05, random_seed=11, sgd_mode="adagrad",
+              user_reg=1e-3, positive_reg=1e-3, negative_reg=1e-3)
+    g = MatrixFactorization_Cython_Epoch(X, **kw)
+    o = MFOracle(X, **kw)
+    for _ in range(2):
+        g.epochIteration_Cython()
+        o.epochIteration_Cython()
+    for a, b in ((g.get_USER_factors(), o.get_USER_factors()), (g.get_ITEM_factors(), o.get_ITEM_factors())):
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-6), float(np.abs(a - b).max())

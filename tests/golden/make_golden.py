@@ -71,3 +71,30 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_sgd_golden():
+    """tests/golden/sgd_golden.npz: factors / S after 3 epochs of the compiled reference trainers."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_sgd import MF_CASES, SLIM_CASES, _urm
+    out = {}
+    MF = ref_loader.load("MatrixFactorization_Cython_Epoch").MatrixFactorization_Cython_Epoch
+    SL = ref_loader.load("SLIM_BPR_Cython_Epoch").SLIM_BPR_Cython_Epoch
+    for n, (algo, kw) in enumerate(MF_CASES):
+        m = MF(_urm(), n_factors=16, algorithm_name=algo, learning_rate=0.05, random_seed=42, **kw)
+        for _ in range(3):
+            m.epochIteration_Cython()
+        out["mf%d_U" % n], out["mf%d_V" % n] = m.get_USER_factors(), m.get_ITEM_factors()
+    for n, (sym, mode) in enumerate(SLIM_CASES):
+        r = SL(_urm(), train_with_sparse_weights=False, learning_rate=0.05, li_reg=1e-3, lj_reg=2e-3, topK=120, symmetric=sym,
+               random_seed=7, sgd_mode=mode)
+        for _ in range(3):
+            r.epochIteration_Cython()
+        S = r.get_S()
+        out["slim%d_S" % n] = np.asarray(S.toarray() if hasattr(S, "toarray") else S, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "sgd_golden.npz"), **out)
+    print("wrote sgd_golden.npz")
+
+
+if __name__ == "__main__":
+    make_sgd_golden()
