@@ -344,6 +344,13 @@ def run_b200(args, rank, world, local_rank):
 
     if rank != 0:
         return
+    sim._dealloc()
+    secondary = None
+    if world == 1 and not args.no_bpr:
+        try:
+            secondary = bpr_leg(args, X)
+        except Exception as ex:
+            secondary = {"metric": "BPR-MF samples/sec", "error": repr(ex)}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -369,9 +376,63 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "secondary": secondary,
         "device": name,
     }
     print(json.dumps(out), flush=True)
+
+
+def bpr_leg(args, X):
+    """Second half of BASELINE.json's metric: BPR-MF samples/sec (MatrixFactorization_Cython_Epoch,
+    algorithm_name='MF_BPR', 128 factors, the wrapper's default batch_size=1000, sgd) on the same URM, 1 GPU.
+    A step is one epochIteration_Cython(); device time by CUDA events on the launching stream, wall time around the
+    call (the glibc sampler runs on the host inside it)."""
+    import torch
+    from recsys2019_deeplearning_evaluation_b200.mf_epoch import MatrixFactorization_Cython_Epoch
+    f = 128
+    peak, peak_src = measured_peaks()
+    res = {"metric": "BPR-MF samples/sec", "unit": "samples/s",
+           "config": {"workload": "%s MF_BPR n_factors=%d sgd lr=1e-3" % (args.workload, f),
+                      "bytes_per_sample": 6 * f * 4, "timing": "factor tables (%.2f GB) larger than L2" % ((X.shape[0] + X.shape[1]) * f * 4 / 1e9)},
+           "modes": {}}
+    for label, kw in (("minibatch_bs1000_glibc_stream", dict(batch_size=1000, sampler="glibc")),
+                      ("minibatch_bs1000_philox", dict(batch_size=1000, sampler="philox")),
+                      ("hogwild_philox", dict(batch_size=1000, sampler="philox", hogwild=True))):
+        m = MatrixFactorization_Cython_Epoch(X, n_factors=f, algorithm_name="MF_BPR", learning_rate=1e-3, random_seed=42,
+                                             sgd_mode="sgd", **kw)
+        for _ in range(3):
+            m.epochIteration_Cython()
+        torch.cuda.synchronize()
+        walls, devs = [], []
+        for _ in range(max(3, args.steps)):
+            t = time.perf_counter()
+            m.epochIteration_Cython()
+            torch.cuda.synchronize()
+            walls.append(time.perf_counter() - t)
+            devs.append(m.last_epoch_ms() * 1e-3)
+        n = m.samples_last_epoch()
+        dev = float(np.mean(devs))
+        res["modes"][label] = {"value": n / dev, "e2e_value": n / float(np.mean(walls)), "samples_per_epoch": n,
+                               "device_ms_per_epoch": 1e3 * dev,
+                               "roofline": {"bound": "hbm", "achieved": n * 6 * f * 4 / 1e9 / dev, "peak": peak, "unit": "GB/s",
+                                            "frac": n * 6 * f * 4 / 1e9 / dev / peak, "peak_source": peak_src}}
+        m._dealloc()
+    res["value"] = res["modes"]["hogwild_philox"]["value"]
+    res["reference_semantics_value"] = res["modes"]["minibatch_bs1000_philox"]["value"]
+    if not args.no_cpu_baseline:
+        from oracle import ref_loader
+        mod = ref_loader.load("MatrixFactorization_Cython_Epoch")
+        if mod is not None:
+            ref_loader.numpy_alias_shim()
+            r = mod.MatrixFactorization_Cython_Epoch(X, n_factors=f, algorithm_name="MF_BPR", batch_size=1000, learning_rate=1e-3,
+                                                     random_seed=42, sgd_mode="sgd")
+            t = time.perf_counter()
+            r.epochIteration_Cython()
+            dt = time.perf_counter() - t
+            n = (X.shape[0] // 1000 + 1) * 1000
+            res["cpu_baseline"] = {"value": n / dt, "unit": "samples/s", "cores": 1, "kind": "reference",
+                                   "sample": "one epochIteration_Cython (%d samples) in %.1fs, 1 thread" % (n, dt)}
+    return res
 
 
 def main():
@@ -385,6 +446,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-cols", type=int, default=2000, help="columns in the CPU-baseline slice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bpr", action="store_true", help="skip the BPR-MF samples/sec leg")
     ap.add_argument("--ref-workers", type=int, default=16)
     ap.add_argument("--ref-slice", type=int, default=250)
     args = ap.parse_args()

@@ -145,6 +145,40 @@ int b200_mf_device_factors(b200_mf_t h, float** d_user_factors, float** d_item_f
 /* device time of the last epoch (sampling kernel + epoch kernel), CUDA events on the launching stream */
 int b200_mf_last_epoch_ms(b200_mf_t h, float* ms);
 
+/* ------------------------------------------------------------------------------------------------
+ * K3: SLIM-BPR epochs on a dense / symmetric item-item matrix  (hot path ii)
+ * replaces  SLIM_BPR/Cython/SLIM_BPR_Cython_Epoch.pyx:60-480  (ctor :88-134, epochIteration_Cython :211-335,
+ *           sampleBPR_Cython :436-480, adaptive_gradient :395-433, get_S :340-388, Triangular_Matrix :1223-1415)
+ * The tree-sparse training mode (Sparse_Matrix_Tree_CSR, :509-1031) is out of scope.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200_slim_s* b200_slim_t;
+
+/* URM_mask: CSR, sorted indices (pyx:100-119).  S starts at zero.  hogwild == 0: the batch-1 recursion in stream
+ * order on one CTA (the reference's semantics); hogwild != 0: all SMs, atomics, no ordering between samples. */
+int b200_slim_create(b200_slim_t* out, int64_t n_users, int64_t n_items, int64_t nnz, const int32_t* h_indptr,
+                     const int32_t* h_indices, float learning_rate, float li_reg, float lj_reg, int symmetric,
+                     int sgd_mode, float gamma, float beta_1, float beta_2, int has_seed, uint32_t random_seed,
+                     int sampler, int hogwild);
+int b200_slim_destroy(b200_slim_t h);
+/* epochIteration_Cython() (pyx:211-335): n_users samples */
+int b200_slim_epoch(b200_slim_t h, void* stream);
+int b200_slim_get_samples(b200_slim_t h, int32_t* u, int32_t* i, int32_t* j);
+/* the full n_items x n_items view get_S() starts from (diagonal zeroed pyx:345-355, symmetric mode mirrored
+ * pyx:1363-1372), row-major fp32, to a host buffer and/or a device buffer (either may be NULL) */
+int b200_slim_get_S_dense(b200_slim_t h, float* h_out, float* d_out);
+int b200_slim_last_epoch_ms(b200_slim_t h, float* ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1b: top-K along the rows / columns of a dense fp32 n x n matrix on the device
+ * replaces  Base/Recommender_utils.py:55-122 similarityMatrixTopK            (along_columns=1, mode 0)
+ *           SLIM_BPR_Cython_Epoch.pyx:1335-1415 / :371,386 row top-K of get_S (along_columns=0, mode 1 / 0)
+ * mode 0: the K largest of the non-zero values; mode 1: the K largest over all cells, zeros then dropped.
+ * Output table [n, K] like b200_sim_compute_device (line = row or column, idx = position along it).
+ * ------------------------------------------------------------------------------------------------ */
+enum b200_topk_mode { B200_TOPK_NONZERO = 0, B200_TOPK_ZEROS_OUTRANK = 1 };
+int b200_dense_topk_device(const float* d_matrix, int n, int K, int along_columns, int mode, int32_t* d_idx,
+                           float* d_val, int32_t* d_cnt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

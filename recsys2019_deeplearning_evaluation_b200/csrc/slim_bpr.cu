@@ -1,0 +1,395 @@
+// K3: SLIM-BPR epochs on a dense (optionally symmetric) item-item matrix S, sm_100a.
+//
+// Replaces SLIM_BPR/Cython/SLIM_BPR_Cython_Epoch.pyx: epochIteration_Cython :211-335, sampleBPR_Cython :436-480,
+// adaptive_gradient :395-433 (per-ITEM scalar state shared by the positive and negative roles), symmetric storage
+// Triangular_Matrix :1272-1330, get_S :340-388 (diagonal zeroed).  The tree-sparse training mode (:509-1031) is
+// not reproduced: S is dense fp32 in HBM (C2: 55 MB, L2-resident).
+//
+// Two execution modes (DESIGN.md "K3"):
+//   * sequential (the reference's semantics exactly): the recursion is batch-1 and every sample reads cells the
+//     previous one may have written, so ONE CTA walks the replayed sample stream in order; the 2*len_u cell reads,
+//     the x_uij reduction and the 2*len_u updates of a sample are spread over the CTA's threads.
+//   * hogwild: all SMs, one warp per sample, float atomics on S (Hogwild races), Philox or replayed stream.
+// Roofline: HBM/L2, 4*len_u*4 bytes per sample for S (two row gathers read + written) + 4*len_u for the profile.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+namespace slim {
+
+enum SgdMode { SGD = 0, ADAGRAD = 1, RMSPROP = 2, ADAM = 3 };
+
+struct Params {
+  int n_users, n_items, symmetric, sgd_mode;
+  float lr, li_reg, lj_reg, gamma, beta1, beta2;
+  double b1_pow, b2_pow;
+  const int* __restrict__ indptr;
+  const int* __restrict__ indices;
+  float* S;                // n_items x n_items row-major; symmetric mode uses the lower triangle (row >= col)
+  float *c, *m1, *m2;      // per-item adaptive state
+  const int* su; const int* si; const int* sj;
+  long long n_samples;
+  double* pow_out;
+};
+
+__device__ __forceinline__ size_t cell(const Params& p, int a, int b) {
+  if (p.symmetric && b > a) { const int t = a; a = b; b = t; }  // pyx:1287-1302, 1309-1330
+  return (size_t)a * p.n_items + b;
+}
+
+__device__ __forceinline__ float adapt_item(const Params& p, float g, int item, float inv1, float inv2) {  // pyx:395-433
+  if (p.sgd_mode == ADAGRAD) {
+    const float cc = p.c[item] + g * g;
+    p.c[item] = cc;
+    return g / (sqrtf(cc) + 1e-8f);
+  } else if (p.sgd_mode == RMSPROP) {
+    const float cc = p.c[item] * p.gamma + (1.f - p.gamma) * g * g;
+    p.c[item] = cc;
+    return g / (sqrtf(cc) + 1e-8f);
+  } else if (p.sgd_mode == ADAM) {
+    const float a = p.m1[item] * p.beta1 + (1.f - p.beta1) * g;
+    const float b = p.m2[item] * p.beta2 + (1.f - p.beta2) * g * g;
+    p.m1[item] = a;
+    p.m2[item] = b;
+    return (a * inv1) / (sqrtf(b * inv2) + 1e-8f);
+  }
+  return g;
+}
+
+constexpr int SEQ_THREADS = 512;
+
+// one CTA, samples strictly in order (pyx:231-312)
+__global__ void __launch_bounds__(SEQ_THREADS) slim_sequential_kernel(const Params p) {
+  __shared__ float red[SEQ_THREADS / 32];
+  __shared__ float s_gi, s_gj;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double b1p = p.b1_pow, b2p = p.b2_pow;
+  for (long long n = 0; n < p.n_samples; ++n) {
+    const int u = p.su[n], i = p.si[n], j = p.sj[n];
+    const int s = p.indptr[u], e = p.indptr[u + 1];
+    float x = 0.f;
+    for (int k = s + tid; k < e; k += SEQ_THREADS) {
+      const int sn = p.indices[k];
+      x += p.S[cell(p, i, sn)] - p.S[cell(p, j, sn)];  // pyx:242-255
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int w = 0; w < SEQ_THREADS / 32; ++w) t += red[w];
+      const float g = 1.f / (1.f + expf(t));  // pyx:258
+      const float inv1 = (float)(1.0 / (1.0 - b1p)), inv2 = (float)(1.0 / (1.0 - b2p));
+      s_gi = adapt_item(p, g, i, inv1, inv2);  // i first, then j (pyx:262-263)
+      s_gj = adapt_item(p, g, j, inv1, inv2);
+    }
+    __syncthreads();
+    const float gi = s_gi, gj = s_gj;
+    // pyx:266-304.  Within one sample the cells (i, s) are distinct from each other and from the cells (j, s')
+    // except in symmetric mode where (i, j) and (j, i) coincide when both i and j are in the profile -- j never is
+    // (it is a sampled negative), so the cell sets are disjoint and the order inside the sample is free.
+    for (int k = s + tid; k < e; k += SEQ_THREADS) {
+      const int sn = p.indices[k];
+      if (sn != i) { const size_t c = cell(p, i, sn); const float v = p.S[c]; p.S[c] = v + p.lr * (gi - p.li_reg * v); }
+      if (sn != j) { const size_t c = cell(p, j, sn); const float v = p.S[c]; p.S[c] = v - p.lr * (gj - p.lj_reg * v); }
+    }
+    if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:309-312
+    __syncthreads();
+  }
+  if (tid == 0) { p.pow_out[0] = b1p; p.pow_out[1] = b2p; }
+}
+
+// all SMs, one warp per sample, no ordering between samples
+__global__ void __launch_bounds__(256) slim_hogwild_kernel(const Params p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long n = warp; n < p.n_samples; n += n_warps) {
+    const int u = p.su[n], i = p.si[n], j = p.sj[n];
+    const int s = p.indptr[u], e = p.indptr[u + 1];
+    float x = 0.f;
+    for (int k = s + lane; k < e; k += 32) {
+      const int sn = p.indices[k];
+      x += p.S[cell(p, i, sn)] - p.S[cell(p, j, sn)];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    const float g = 1.f / (1.f + expf(x));
+    float gi = g, gj = g;
+    if (p.sgd_mode != SGD) {
+      float inv1 = 1.f, inv2 = 1.f;
+      if (p.sgd_mode == ADAM) {
+        inv1 = (float)(1.0 / (1.0 - p.b1_pow * pow((double)p.beta1, (double)n)));
+        inv2 = (float)(1.0 / (1.0 - p.b2_pow * pow((double)p.beta2, (double)n)));
+      }
+      if (lane == 0) { gi = adapt_item(p, g, i, inv1, inv2); gj = adapt_item(p, g, j, inv1, inv2); }
+      gi = __shfl_sync(0xffffffffu, gi, 0);
+      gj = __shfl_sync(0xffffffffu, gj, 0);
+    }
+    for (int k = s + lane; k < e; k += 32) {
+      const int sn = p.indices[k];
+      if (sn != i) { const size_t c = cell(p, i, sn); atomicAdd(p.S + c, p.lr * (gi - p.li_reg * p.S[c])); }
+      if (sn != j) { const size_t c = cell(p, j, sn); atomicAdd(p.S + c, -p.lr * (gj - p.lj_reg * p.S[c])); }
+    }
+  }
+}
+
+// expands the stored matrix into the full n x n view get_S returns before its top-K (diagonal zeroed, pyx:345-355;
+// symmetric mode mirrors the lower triangle, pyx:1363-1372)
+__global__ void slim_full_kernel(const float* __restrict__ S, int n, int symmetric, float* out) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)n * n) return;
+  const int r = (int)(g / n), c = (int)(g % n);
+  float v;
+  if (r == c) v = 0.f;
+  else if (symmetric && c > r) v = S[(size_t)c * n + r];
+  else v = S[g];
+  out[g] = v;
+}
+
+// device Philox sampler (same acceptance rules as sampleBPR_Cython, pyx:436-480)
+__device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0, unsigned k1) {
+  const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+}
+__device__ __forceinline__ uint4 philox(unsigned long long idx, unsigned blk, unsigned seed, unsigned epoch) {
+  unsigned c0 = (unsigned)idx, c1 = (unsigned)(idx >> 32), c2 = blk, c3 = 0x243F6A88u;
+  unsigned k0 = seed, k1 = epoch;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__global__ void slim_sample_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, int n_users, int n_items,
+                                   long long n_samples, unsigned seed, unsigned epoch, int* su, int* si, int* sj) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_samples) return;
+  unsigned blk = 0;
+  uint4 cur = philox((unsigned long long)g, blk++, seed, epoch);
+  int pos = 0;
+  auto next = [&]() {
+    if (pos == 4) { cur = philox((unsigned long long)g, blk++, seed, epoch); pos = 0; }
+    const unsigned v = pos == 0 ? cur.x : (pos == 1 ? cur.y : (pos == 2 ? cur.z : cur.w));
+    ++pos;
+    return v;
+  };
+  int u, s, n;
+  do {
+    u = (int)(next() % (unsigned)n_users);
+    s = indptr[u];
+    n = indptr[u + 1] - s;
+  } while (n == 0 || n == n_items);
+  const int item = indices[s + (int)(next() % (unsigned)n)];
+  int neg;
+  while (true) {
+    neg = (int)(next() % (unsigned)n_items);
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (indices[s + mid] < neg) lo = mid + 1; else hi = mid; }
+    if (lo == n || indices[s + lo] != neg) break;
+  }
+  su[g] = u; si[g] = item; sj[g] = neg;
+}
+
+struct GlibcRand {
+  int32_t r[31];
+  int f = 3, b = 0;
+  void seed(unsigned s) {
+    int32_t word = s == 0 ? 1 : (int32_t)s;
+    r[0] = word;
+    for (int i = 1; i < 31; ++i) {
+      const long hi = word / 127773, lo = word % 127773;
+      long w = 16807 * lo - 2836 * hi;
+      if (w < 0) w += 2147483647;
+      word = (int32_t)w;
+      r[i] = word;
+    }
+    f = 3; b = 0;
+    for (int i = 0; i < 310; ++i) raw();
+  }
+  uint32_t raw() {
+    const uint32_t v = (uint32_t)r[f] + (uint32_t)r[b];
+    r[f] = (int32_t)v;
+    f = (f + 1) % 31;
+    b = (b + 1) % 31;
+    return v;
+  }
+  int next() { return (int)(raw() >> 1); }
+};
+
+}  // namespace slim
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::slim;
+
+struct b200_slim_s {
+  Params p{};
+  int sampler = 0, hogwild = 0;
+  unsigned seed = 1, epoch = 0;
+  GlibcRand rng;
+  std::vector<int> h_indptr, h_indices, hs_u, hs_i, hs_j;
+  DevBuf<int> d_indptr, d_indices, su, si, sj;
+  DevBuf<float> S, c, m1, m2;
+  DevBuf<double> pow_out;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+};
+
+extern "C" {
+
+int b200_slim_create(b200_slim_t* out, int64_t n_users, int64_t n_items, int64_t nnz, const int32_t* h_indptr,
+                     const int32_t* h_indices, float learning_rate, float li_reg, float lj_reg, int symmetric, int sgd_mode,
+                     float gamma, float beta_1, float beta_2, int has_seed, uint32_t random_seed, int sampler, int hogwild) {
+  if (out) *out = nullptr;
+  b200_slim_s* h = nullptr;
+  int rc = guarded([&] {
+    B200_REQUIRE(out && h_indptr && (nnz == 0 || h_indices), "b200_slim_create: NULL argument");
+    B200_REQUIRE(n_users > 0 && n_items > 0 && nnz >= 0 && nnz < (1ll << 31) - 1, "b200_slim_create: bad shape");
+    B200_REQUIRE(sgd_mode >= SGD && sgd_mode <= ADAM, "b200_slim_create: unknown sgd_mode %d", sgd_mode);
+    B200_REQUIRE((double)n_items * (double)n_items * 4.0 < 1.6e11, "b200_slim_create: dense S does not fit one GPU");
+    h = new b200_slim_s();
+    Params& p = h->p;
+    p.n_users = (int)n_users; p.n_items = (int)n_items; p.symmetric = symmetric != 0; p.sgd_mode = sgd_mode;
+    p.lr = learning_rate; p.li_reg = li_reg; p.lj_reg = lj_reg; p.gamma = gamma; p.beta1 = beta_1; p.beta2 = beta_2;
+    p.b1_pow = beta_1; p.b2_pow = beta_2;  // pyx:157-158
+    h->sampler = sampler; h->hogwild = hogwild != 0;
+    h->seed = has_seed ? random_seed : 1u;
+    h->rng.seed(h->seed);
+    h->h_indptr.assign(h_indptr, h_indptr + n_users + 1);
+    h->h_indices.assign(h_indices, h_indices + nnz);
+    h->d_indptr.alloc((size_t)n_users + 1);
+    h->d_indices.alloc((size_t)std::max<int64_t>(nnz, 1));
+    B200_CUDA(cudaMemcpy(h->d_indptr.get(), h_indptr, sizeof(int) * ((size_t)n_users + 1), cudaMemcpyHostToDevice));
+    if (nnz) B200_CUDA(cudaMemcpy(h->d_indices.get(), h_indices, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
+    p.indptr = h->d_indptr.get(); p.indices = h->d_indices.get();
+    const size_t cells = (size_t)n_items * (size_t)n_items;
+    h->S.alloc(cells);
+    B200_CUDA(cudaMemset(h->S.get(), 0, cells * sizeof(float)));  // S starts at zero (pyx:122-125)
+    p.S = h->S.get();
+    if (sgd_mode == ADAGRAD || sgd_mode == RMSPROP) {
+      h->c.alloc((size_t)n_items); B200_CUDA(cudaMemset(h->c.get(), 0, sizeof(float) * (size_t)n_items)); p.c = h->c.get();
+    } else if (sgd_mode == ADAM) {
+      h->m1.alloc((size_t)n_items); h->m2.alloc((size_t)n_items);
+      B200_CUDA(cudaMemset(h->m1.get(), 0, sizeof(float) * (size_t)n_items));
+      B200_CUDA(cudaMemset(h->m2.get(), 0, sizeof(float) * (size_t)n_items));
+      p.m1 = h->m1.get(); p.m2 = h->m2.get();
+    }
+    h->su.alloc((size_t)n_users); h->si.alloc((size_t)n_users); h->sj.alloc((size_t)n_users);
+    p.su = h->su.get(); p.si = h->si.get(); p.sj = h->sj.get();
+    h->pow_out.alloc(2);
+    p.pow_out = h->pow_out.get();
+    B200_CUDA(cudaEventCreate(&h->ev0));
+    B200_CUDA(cudaEventCreate(&h->ev1));
+    *out = h;
+  });
+  if (rc != B200_OK && h) delete h;
+  return rc;
+}
+
+int b200_slim_destroy(b200_slim_t h) {
+  if (!h) return B200_OK;
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return B200_OK;
+}
+
+int b200_slim_epoch(b200_slim_t h, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr, "b200_slim_epoch: NULL handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    Params& p = h->p;
+    const long long n = p.n_users;  // pyx:231: n_users samples per epoch
+    p.n_samples = n;
+    if (h->sampler == 0) {
+      h->hs_u.resize((size_t)n); h->hs_i.resize((size_t)n); h->hs_j.resize((size_t)n);
+      const int* indptr = h->h_indptr.data();
+      const int* indices = h->h_indices.data();
+      for (long long g = 0; g < n; ++g) {  // sampleBPR_Cython pyx:436-480, draw for draw
+        long u = 0, start = 0, len = 0;
+        while (len == 0 || len == p.n_items) {
+          u = h->rng.next() % p.n_users;
+          start = indptr[u];
+          len = indptr[u + 1] - start;
+        }
+        const long item = indices[start + h->rng.next() % len];
+        long neg;
+        for (;;) {
+          neg = h->rng.next() % p.n_items;
+          const int* lo = std::lower_bound(indices + start, indices + start + len, (int)neg);
+          if (lo == indices + start + len || *lo != neg) break;
+        }
+        h->hs_u[(size_t)g] = (int)u; h->hs_i[(size_t)g] = (int)item; h->hs_j[(size_t)g] = (int)neg;
+      }
+      B200_CUDA(cudaMemcpyAsync(h->su.get(), h->hs_u.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+      B200_CUDA(cudaMemcpyAsync(h->si.get(), h->hs_i.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+      B200_CUDA(cudaMemcpyAsync(h->sj.get(), h->hs_j.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    B200_CUDA(cudaEventRecord(h->ev0, st));
+    if (h->sampler != 0) {
+      slim_sample_kernel<<<div_up(n, 256), 256, 0, st>>>(p.indptr, p.indices, p.n_users, p.n_items, n, h->seed, h->epoch,
+                                                        h->su.get(), h->si.get(), h->sj.get());
+      count_launch();
+    }
+    if (h->hogwild) {
+      slim_hogwild_kernel<<<sm_count() * 8, 256, 0, st>>>(p);
+      if (p.sgd_mode == ADAM) { p.b1_pow *= pow((double)p.beta1, (double)n); p.b2_pow *= pow((double)p.beta2, (double)n); }
+    } else {
+      slim_sequential_kernel<<<1, SEQ_THREADS, 0, st>>>(p);
+    }
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+    B200_CUDA(cudaEventRecord(h->ev1, st));
+    h->timed = true;
+    if (!h->hogwild && p.sgd_mode == ADAM) {
+      double pw[2];
+      B200_CUDA(cudaMemcpyAsync(pw, h->pow_out.get(), sizeof(pw), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaStreamSynchronize(st));
+      p.b1_pow = pw[0]; p.b2_pow = pw[1];
+    } else if (h->sampler == 0) {
+      B200_CUDA(cudaStreamSynchronize(st));
+    }
+    h->epoch += 1;
+  });
+}
+
+int b200_slim_get_samples(b200_slim_t h, int32_t* u, int32_t* i, int32_t* j) {
+  return guarded([&] {
+    B200_REQUIRE(h && u && i && j, "b200_slim_get_samples: NULL argument");
+    B200_CUDA(cudaDeviceSynchronize());
+    const size_t n = (size_t)h->p.n_users;
+    B200_CUDA(cudaMemcpy(u, h->su.get(), sizeof(int) * n, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(i, h->si.get(), sizeof(int) * n, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(j, h->sj.get(), sizeof(int) * n, cudaMemcpyDeviceToHost));
+  });
+}
+
+int b200_slim_get_S_dense(b200_slim_t h, float* h_out, float* d_out) {
+  return guarded([&] {
+    B200_REQUIRE(h && (h_out || d_out), "b200_slim_get_S_dense: NULL argument");
+    const int n = h->p.n_items;
+    const size_t cells = (size_t)n * n;
+    DevBuf<float> tmp;
+    float* dst = d_out;
+    if (!dst) { tmp.alloc(cells); dst = tmp.get(); }
+    slim_full_kernel<<<div_up((long long)cells, 256), 256>>>(h->p.S, n, h->p.symmetric, dst);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+    if (h_out) B200_CUDA(cudaMemcpy(h_out, dst, cells * sizeof(float), cudaMemcpyDeviceToHost));
+    else B200_CUDA(cudaDeviceSynchronize());
+  });
+}
+
+int b200_slim_last_epoch_ms(b200_slim_t h, float* ms) {
+  return guarded([&] {
+    B200_REQUIRE(h && ms && h->timed, "b200_slim_last_epoch_ms: no epoch run yet");
+    B200_CUDA(cudaEventSynchronize(h->ev1));
+    B200_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  });
+}
+
+}  // extern "C"

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "b200rec.h")
 def header_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(b200_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
