@@ -66,6 +66,15 @@ int b200_sim_create(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz
                     const float* h_row_weights, void* stream);
 int b200_sim_destroy(b200_sim_t h);
 
+/* P3alpha / RP3beta product (GraphBased/P3alphaRecommender.py:54-117, GraphBased/RP3betaRecommender.py:54-104):
+ * for target item i and neighbour j,  value = A[i] * B[j] * sum over users u of item i of data[u, j], with
+ * data = (r_uj / rowsum_u)^alpha (Pui), A[i] = (1/deg_i)^alpha (the constant row of Piu), B[j] = deg_j^-beta
+ * (RP3beta; all ones for P3alpha).  The same accumulate/top-K kernel as the similarities (formula "scale");
+ * b200_sim_compute* then returns per TARGET item i its topK (j, value) -- row i of the reference's W_sparse. */
+int b200_sim_create_scaled(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* h_indptr,
+                           const int32_t* h_indices, const float* h_data, const float* h_A, const float* h_B,
+                           int topK, void* stream);
+
 /* effective K (min(topK, n_cols)), window geometry and path chosen at create time */
 int b200_sim_info(b200_sim_t h, int* K, int* n_windows, int* window_cells, int* binary_path, int* signed_data);
 
@@ -178,6 +187,10 @@ int b200_slim_last_epoch_ms(b200_slim_t h, float* ms);
 enum b200_topk_mode { B200_TOPK_NONZERO = 0, B200_TOPK_ZEROS_OUTRANK = 1 };
 int b200_dense_topk_device(const float* d_matrix, int n, int K, int along_columns, int mode, int32_t* d_idx,
                            float* d_val, int32_t* d_cnt, void* stream);
+/* the same selection over the lines of a compressed sparse n x n matrix on the device (CSC columns or CSR rows):
+ * line l holds entries d_ptr[l]..d_ptr[l+1] with positions d_line_idx[] and values d_vals[] */
+int b200_sparse_topk_device(int n, const int32_t* d_ptr, const int32_t* d_line_idx, const float* d_vals, int K,
+                            int mode, int32_t* d_idx, float* d_val, int32_t* d_cnt, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,14 +26,21 @@ __device__ __forceinline__ float from_orderable(unsigned o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
 }
 
-__global__ void __launch_bounds__(THREADS) dense_topk_kernel(const float* __restrict__ M, int n_lines, int n_inner,
+// SPARSE: line l is the segment [ptr[l], ptr[l+1]) of (sidx, M); its cells are the stored entries and the implicit
+// zeros of a length-n_inner line.
+template <bool SPARSE>
+__global__ void __launch_bounds__(THREADS) topk_lines_kernel(const float* __restrict__ M, const int* __restrict__ ptr,
+                                                             const int* __restrict__ sidx, int n_lines, int n_inner_dense,
                                                              long long stride_line, long long stride_inner, int K, int mode,
                                                              int* out_idx, float* out_val, int* out_cnt) {
   __shared__ int hist[BINS];
   __shared__ int s_digit, s_need, s_cnt, s_npos, s_nneg;
   const int tid = threadIdx.x, lane = tid & 31;
   for (int line = blockIdx.x; line < n_lines; line += gridDim.x) {
-    const float* L = M + (long long)line * stride_line;
+    const float* L = SPARSE ? M + ptr[line] : M + (long long)line * stride_line;
+    const int* LI = SPARSE ? sidx + ptr[line] : nullptr;
+    const int n_inner = SPARSE ? ptr[line + 1] - ptr[line] : n_inner_dense;
+    if (SPARSE) stride_inner = 1;
     if (tid == 0) { s_npos = 0; s_nneg = 0; s_cnt = 0; }
     __syncthreads();
     int npos = 0, nneg = 0;
@@ -47,7 +54,7 @@ __global__ void __launch_bounds__(THREADS) dense_topk_kernel(const float* __rest
     if (lane == 0) { atomicAdd(&s_npos, npos); atomicAdd(&s_nneg, nneg); }
     __syncthreads();
     npos = s_npos; nneg = s_nneg;
-    const int nzero = n_inner - npos - nneg;
+    const int nzero = n_inner_dense - npos - nneg;
     int keep;  // how many non-zero cells survive
     if (mode == 0) keep = min(K, npos + nneg);                                   // similarityMatrixTopK
     else keep = min(K, npos) + min(nneg, max(0, K - npos - nzero));               // zeros outrank negatives
@@ -63,7 +70,7 @@ __global__ void __launch_bounds__(THREADS) dense_topk_kernel(const float* __rest
         for (int q = tid; q < n_inner; q += THREADS) {
           const float v = L[(long long)q * stride_inner];
           if (v != 0.f) {
-            const u64 key = (((u64)orderable(v)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)q);
+            const u64 key = (((u64)orderable(v)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)(SPARSE ? LI[q] : q));
             if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> sh) & ((1u << nb) - 1))], 1);
           }
         }
@@ -99,10 +106,11 @@ __global__ void __launch_bounds__(THREADS) dense_topk_kernel(const float* __rest
       for (int q = tid; q < n_inner; q += THREADS) {
         const float v = L[(long long)q * stride_inner];
         if (v != 0.f) {
-          const u64 key = (((u64)orderable(v)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)q);
+          const int qi = SPARSE ? LI[q] : q;
+          const u64 key = (((u64)orderable(v)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)qi);
           if (key >= thr) {
             const int pos = atomicAdd(&s_cnt, 1);
-            out_idx[(size_t)line * K + pos] = q;
+            out_idx[(size_t)line * K + pos] = qi;
             out_val[(size_t)line * K + pos] = v;
           }
         }
@@ -131,7 +139,21 @@ int b200_dense_topk_device(const float* d_matrix, int n, int K, int along_column
     B200_REQUIRE(mode == 0 || mode == 1, "b200_dense_topk: unknown mode %d", mode);
     cudaStream_t st = (cudaStream_t)stream;
     const long long sl = along_columns ? 1 : n, si = along_columns ? n : 1;
-    dtk::dense_topk_kernel<<<std::min(n, sm_count() * 8), dtk::THREADS, 0, st>>>(d_matrix, n, n, sl, si, K, mode, d_idx, d_val, d_cnt);
+    dtk::topk_lines_kernel<false><<<std::min(n, sm_count() * 8), dtk::THREADS, 0, st>>>(d_matrix, nullptr, nullptr, n, n, sl, si, K, mode, d_idx, d_val, d_cnt);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+  });
+}
+
+int b200_sparse_topk_device(int n, const int32_t* d_ptr, const int32_t* d_line_idx, const float* d_vals, int K, int mode,
+                            int32_t* d_idx, float* d_val, int32_t* d_cnt, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(d_ptr && d_idx && d_val && d_cnt, "b200_sparse_topk: NULL argument");
+    B200_REQUIRE(n > 0 && K > 0 && K <= n, "b200_sparse_topk: need 0 < K <= n (got K=%d n=%d)", K, n);
+    B200_REQUIRE(mode == 0 || mode == 1, "b200_sparse_topk: unknown mode %d", mode);
+    cudaStream_t st = (cudaStream_t)stream;
+    dtk::topk_lines_kernel<true><<<std::min(n, sm_count() * 8), dtk::THREADS, 0, st>>>(d_vals, d_ptr, d_line_idx, n, n, 0, 1, K, mode,
+                                                                                       d_idx, d_val, d_cnt);
     B200_CUDA(cudaGetLastError());
     count_launch();
   });

@@ -262,7 +262,31 @@ __global__ void __launch_bounds__(256) mf_hogwild_kernel(const Params p, long lo
     const int u = p.su[g], i = p.si[g];
     float* Uu = p.U + (size_t)u * f;
     float* Vi = p.V + (size_t)i * f;
-    if (p.algorithm == MF_BPR) {
+    if (p.algorithm == MF_BPR && p.sgd_mode == SGD && (f & 3) == 0) {
+      // plain-SGD BPR, rows as float4: one 16-byte load and store per lane and row for f = 128
+      const int j = p.sj[g];
+      float* Vj = p.V + (size_t)j * f;
+      float x = 0.f;
+      for (int q = lane * 4; q < f; q += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(Uu + q), b = *reinterpret_cast<const float4*>(Vi + q),
+                     c = *reinterpret_cast<const float4*>(Vj + q);
+        x += a.x * (b.x - c.x) + a.y * (b.y - c.y) + a.z * (b.z - c.z) + a.w * (b.w - c.w);
+      }
+      x = warp_sum(x);
+      const float sig = 1.f / (1.f + expf(x));
+      const float lr = p.lr;
+      for (int q = lane * 4; q < f; q += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(Uu + q), b = *reinterpret_cast<const float4*>(Vi + q),
+                     c = *reinterpret_cast<const float4*>(Vj + q);
+        // deltas go through RED.ADD so that concurrent samples sharing a row add up instead of overwriting each other
+        red_add4(Vi + q, make_float4(lr * (sig * a.x - p.positive_reg * b.x), lr * (sig * a.y - p.positive_reg * b.y),
+                                     lr * (sig * a.z - p.positive_reg * b.z), lr * (sig * a.w - p.positive_reg * b.w)));
+        red_add4(Vj + q, make_float4(lr * (-sig * a.x - p.negative_reg * c.x), lr * (-sig * a.y - p.negative_reg * c.y),
+                                     lr * (-sig * a.z - p.negative_reg * c.z), lr * (-sig * a.w - p.negative_reg * c.w)));
+        red_add4(Uu + q, make_float4(lr * (sig * (b.x - c.x) - p.user_reg * a.x), lr * (sig * (b.y - c.y) - p.user_reg * a.y),
+                                     lr * (sig * (b.z - c.z) - p.user_reg * a.z), lr * (sig * (b.w - c.w) - p.user_reg * a.w)));
+      }
+    } else if (p.algorithm == MF_BPR) {
       const int j = p.sj[g];
       float* Vj = p.V + (size_t)j * f;
       float x = 0.f;
@@ -273,9 +297,9 @@ __global__ void __launch_bounds__(256) mf_hogwild_kernel(const Params p, long lo
         const float a = Uu[q], b = Vi[q], c = Vj[q];
         const size_t oi = (size_t)i * f + q, oj = (size_t)j * f + q, ou = (size_t)u * f + q;
         // items first, then the user, as pyx:792-832 orders the apply
-        Vi[q] = b + p.lr * adapt(ad, sig * a - p.positive_reg * b, p.cV ? p.cV + oi : nullptr, p.m1V ? p.m1V + oi : nullptr, p.m2V ? p.m2V + oi : nullptr);
-        Vj[q] = c + p.lr * adapt(ad, -sig * a - p.negative_reg * c, p.cV ? p.cV + oj : nullptr, p.m1V ? p.m1V + oj : nullptr, p.m2V ? p.m2V + oj : nullptr);
-        Uu[q] = a + p.lr * adapt(ad, sig * (b - c) - p.user_reg * a, p.cU ? p.cU + ou : nullptr, p.m1U ? p.m1U + ou : nullptr, p.m2U ? p.m2U + ou : nullptr);
+        atomicAdd(Vi + q, p.lr * adapt(ad, sig * a - p.positive_reg * b, p.cV ? p.cV + oi : nullptr, p.m1V ? p.m1V + oi : nullptr, p.m2V ? p.m2V + oi : nullptr));
+        atomicAdd(Vj + q, p.lr * adapt(ad, -sig * a - p.negative_reg * c, p.cV ? p.cV + oj : nullptr, p.m1V ? p.m1V + oj : nullptr, p.m2V ? p.m2V + oj : nullptr));
+        atomicAdd(Uu + q, p.lr * adapt(ad, sig * (b - c) - p.user_reg * a, p.cU ? p.cU + ou : nullptr, p.m1U ? p.m1U + ou : nullptr, p.m2U ? p.m2U + ou : nullptr));
       }
     } else {
       float x = 0.f;
@@ -291,8 +315,8 @@ __global__ void __launch_bounds__(256) mf_hogwild_kernel(const Params p, long lo
       for (int q = lane; q < f; q += 32) {
         const float a = Uu[q], b = Vi[q];
         const size_t oi = (size_t)i * f + q, ou = (size_t)u * f + q;
-        Vi[q] = b + p.lr * adapt(ad, err * a - p.positive_reg * b, p.cV ? p.cV + oi : nullptr, p.m1V ? p.m1V + oi : nullptr, p.m2V ? p.m2V + oi : nullptr);
-        Uu[q] = a + p.lr * adapt(ad, err * b - p.user_reg * a, p.cU ? p.cU + ou : nullptr, p.m1U ? p.m1U + ou : nullptr, p.m2U ? p.m2U + ou : nullptr);
+        atomicAdd(Vi + q, p.lr * adapt(ad, err * a - p.positive_reg * b, p.cV ? p.cV + oi : nullptr, p.m1V ? p.m1V + oi : nullptr, p.m2V ? p.m2V + oi : nullptr));
+        atomicAdd(Uu + q, p.lr * adapt(ad, err * b - p.user_reg * a, p.cU ? p.cU + ou : nullptr, p.m1U ? p.m1U + ou : nullptr, p.m2U ? p.m2U + ou : nullptr));
       }
     }
   }
@@ -594,7 +618,7 @@ int b200_mf_epoch(b200_mf_t h, void* stream) {
       count_launch();
     }
     if (p.hogwild) {
-      mf_hogwild_kernel<<<h->grid, 256, 0, st>>>(p, n);
+      mf_hogwild_kernel<<<sm_count() * 8, 256, 0, st>>>(p, n);
       B200_CUDA(cudaGetLastError());
       if (p.sgd_mode == ADAM) {  // powers advance once per size-1 batch
         p.b1_pow *= pow((double)p.beta1, (double)n);

@@ -47,7 +47,7 @@ constexpr int UB = 2;           // 128-bit loads in flight per lane
 constexpr int TILE = THREADS * 4;
 constexpr int MAXTILES = 16;
 
-enum Formula { F_PROD = 0, F_NONORM = 1, F_JACCARD = 2, F_DICE = 3, F_TVERSKY = 4 };
+enum Formula { F_PROD = 0, F_NONORM = 1, F_JACCARD = 2, F_DICE = 3, F_TVERSKY = 4, F_SCALE = 5 };
 
 struct KParams {
   int n_cols, K, n_win, win, cap, cap_alloc;  // cap <= cap_alloc (a smaller logical cap is a test hook)
@@ -83,6 +83,7 @@ __device__ __forceinline__ float sim_value(const KParams& p, float d, float a, f
   if (F == F_NONORM) return d / p.shrink_div;
   if (F == F_JACCARD) return d / (a + b - d + p.se);
   if (F == F_DICE) return d / (a + b + p.se);
+  if (F == F_SCALE) return d * a * b;  // P3alpha / RP3beta: dot * (1/deg_i)^alpha * deg_j^-beta
   return d / (d + (a - d) * p.ta + (b - d) * p.tb + p.se);
 }
 
@@ -100,6 +101,7 @@ __device__ __forceinline__ float dot_threshold(const KParams& p, float t, float 
     else if (F == F_NONORM) v = t * p.shrink_div;
     else if (F == F_JACCARD) v = t * (a + b + p.se) / (1.f + t);
     else if (F == F_DICE) v = t * (a + b + p.se);
+    else if (F == F_SCALE) v = (a * b > 0.f) ? t / (a * b) : 3.4e38f;
     else {
       const float den = 1.f - t * (1.f - p.ta - p.tb);
       v = den > 1e-6f ? t * (a * p.ta + b * p.tb + p.se) / den : 0.f;
@@ -115,6 +117,7 @@ template <int F>
 __device__ __forceinline__ float lower_bound_scale(const KParams& p, float a, float b_lo, float b_hi) {
   const float b = fmaxf(b_lo, b_hi);
   float den;
+  if (F == F_SCALE) return a * fminf(b_lo, b_hi) * (1.f - 1e-5f);
   if (F == F_PROD) den = a * b + p.se;
   else if (F == F_NONORM) den = p.shrink_div;
   else if (F == F_JACCARD || F == F_DICE) den = a + b + p.se;  // jaccard: the "- d" only raises the value
@@ -687,6 +690,13 @@ __global__ void norms_kernel(const double* __restrict__ colsq, int n_cols, int m
   iota[j] = j;
 }
 
+__global__ void scaled_keys_kernel(const float* __restrict__ B, int n_cols, unsigned* Bkey, int* iota) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_cols) return;
+  Bkey[j] = __float_as_uint(fmaxf(B[j], 0.f));
+  iota[j] = j;
+}
+
 // new numbering: new2old = columns sorted by (B asc, original index asc)
 __global__ void renumber_kernel(const int* __restrict__ new2old, const float* __restrict__ A_old,
                                 const float* __restrict__ B_old, const int* __restrict__ cnt_old, int n_cols,
@@ -727,7 +737,7 @@ __global__ void build_csc_kernel(const int* __restrict__ perm, const int* __rest
     if (idx_only) {
       idx_only[q] = u;
     } else {
-      float x = data[pp];
+      float x = data ? data[pp] : 1.0f;
       if (row_w) x *= row_w[u];
       ent[q] = make_int2(u, __float_as_int(x));
     }
@@ -781,6 +791,9 @@ struct b200_sim_s {
   float shrink = 0.f, asym_alpha = 0.5f, ta = 1.f, tb = 1.f;
   int formula = F_PROD;
   bool binary = false, signed_data = false;
+  bool scaled = false;             // P3alpha / RP3beta product: CSC values are 1, A and B come from the caller
+  const float* h_A = nullptr;
+  const float* h_B = nullptr;
   int n_win = 1, win = 0, cap = 2048, cap_alloc = 2048;
   size_t smem_bytes = 0;
   int n_sm = 0;
@@ -809,6 +822,7 @@ sim_kernel_t kernel_for(int formula, bool binary) {
     case F_NONORM: return binary ? sim_topk_kernel<F_NONORM, true> : sim_topk_kernel<F_NONORM, false>;
     case F_JACCARD: return binary ? sim_topk_kernel<F_JACCARD, true> : sim_topk_kernel<F_JACCARD, false>;
     case F_DICE: return binary ? sim_topk_kernel<F_DICE, true> : sim_topk_kernel<F_DICE, false>;
+    case F_SCALE: return sim_topk_kernel<F_SCALE, false>;
     default: return binary ? sim_topk_kernel<F_TVERSKY, true> : sim_topk_kernel<F_TVERSKY, false>;
   }
 }
@@ -843,13 +857,13 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   }
 
   // ---- per-kind data transform (pyx:160-165)
-  const bool set_kind = h->kind == B200_SIM_JACCARD || h->kind == B200_SIM_DICE || h->kind == B200_SIM_TVERSKY;
+  const bool set_kind = !h->scaled && (h->kind == B200_SIM_JACCARD || h->kind == B200_SIM_DICE || h->kind == B200_SIM_TVERSKY);
   DevBuf<double> colsum((size_t)n_cols), colsq((size_t)n_cols);
   DevBuf<int> colcnt((size_t)n_cols);
   B200_CUDA(cudaMemsetAsync(colsum.get(), 0, sizeof(double) * (size_t)n_cols, st));
   B200_CUDA(cudaMemsetAsync(colsq.get(), 0, sizeof(double) * (size_t)n_cols, st));
   B200_CUDA(cudaMemsetAsync(colcnt.get(), 0, sizeof(int) * (size_t)n_cols, st));
-  if (nnz) {
+  if (nnz && !h->scaled) {
     if (set_kind) {
       fill_ones_kernel<<<GRID1D, 256, 0, st>>>(data.get(), nnz); count_launch();
     } else if (h->kind == B200_SIM_ADJUSTED) {
@@ -871,9 +885,15 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   DevBuf<float> A_old((size_t)n_cols), B_old((size_t)n_cols);
   DevBuf<unsigned> Bkey((size_t)n_cols), Bkey_sorted((size_t)n_cols);
   DevBuf<int> col_iota((size_t)n_cols), new2old((size_t)n_cols), cnt_new((size_t)n_cols);
-  const int norm_mode = set_kind ? 0 : (h->kind == B200_SIM_ASYMMETRIC ? 2 : 1);
-  norms_kernel<<<div_up(n_cols, 256), 256, 0, st>>>(colsq.get(), n_cols, norm_mode, h->asym_alpha, A_old.get(), B_old.get(),
-                                                    Bkey.get(), col_iota.get());
+  if (h->scaled) {
+    B200_CUDA(cudaMemcpyAsync(A_old.get(), h->h_A, sizeof(float) * (size_t)n_cols, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(B_old.get(), h->h_B, sizeof(float) * (size_t)n_cols, cudaMemcpyHostToDevice, st));
+    scaled_keys_kernel<<<div_up(n_cols, 256), 256, 0, st>>>(B_old.get(), n_cols, Bkey.get(), col_iota.get());
+  } else {
+    const int norm_mode = set_kind ? 0 : (h->kind == B200_SIM_ASYMMETRIC ? 2 : 1);
+    norms_kernel<<<div_up(n_cols, 256), 256, 0, st>>>(colsq.get(), n_cols, norm_mode, h->asym_alpha, A_old.get(), B_old.get(),
+                                                      Bkey.get(), col_iota.get());
+  }
   count_launch();
 
   // ---- renumber the columns by (B asc, original index asc): stable radix sort on the float bit pattern
@@ -893,7 +913,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   count_launch();
   B200_CUDA(cudaStreamSynchronize(st));
   h->signed_data = (hflags & 2) != 0;
-  h->binary = ((hflags & 1) == 0) && !h_row_weights;
+  h->binary = ((hflags & 1) == 0) && !h_row_weights && !h->scaled;
 
   // ---- CSR in the new numbering: relabel, then sort every row segment by the new index
   h->csr_idx.alloc(nnz1 + 8);
@@ -939,14 +959,16 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
     } else {
       h->csc_ent.alloc((size_t)nnz);
       h->csr_ent.alloc((size_t)nnz + 8);
-      build_csc_kernel<<<GRID1D, 256, 0, st>>>(perm.get(), rowid.get(), data_sorted.get(), row_w.get(), nnz, h->csc_ent.get(), nullptr);
+      build_csc_kernel<<<GRID1D, 256, 0, st>>>(perm.get(), rowid.get(), h->scaled ? nullptr : data_sorted.get(), row_w.get(), nnz, h->csc_ent.get(), nullptr);
       build_csr_ent_kernel<<<GRID1D, 256, 0, st>>>(h->csr_idx.get(), data_sorted.get(), nnz, h->csr_ent.get()); count_launch();
     }
     count_launch();
     B200_CUDA(cudaStreamSynchronize(st));
   }
 
-  if (set_kind) {
+  if (h->scaled) {
+    h->formula = F_SCALE;
+  } else if (set_kind) {
     h->formula = h->kind == B200_SIM_JACCARD ? F_JACCARD : (h->kind == B200_SIM_DICE ? F_DICE : F_TVERSKY);
   } else {
     h->formula = h->normalize ? F_PROD : F_NONORM;
@@ -1045,6 +1067,29 @@ int b200_sim_create(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz
     h->ta = tversky_alpha;
     h->tb = tversky_beta;
     build(h, h_indptr, h_indices, h_data, h_row_weights, (cudaStream_t)stream);
+    *out = h;
+  });
+  if (rc != B200_OK && h) delete h;
+  return rc;
+}
+
+int b200_sim_create_scaled(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* h_indptr,
+                           const int32_t* h_indices, const float* h_data, const float* h_A, const float* h_B, int topK,
+                           void* stream) {
+  if (out) *out = nullptr;
+  b200_sim_s* h = nullptr;
+  int rc = guarded([&] {
+    B200_REQUIRE(out && h_indptr && h_A && h_B && (nnz == 0 || (h_indices && h_data)), "b200_sim_create_scaled: NULL argument");
+    B200_REQUIRE(n_rows > 0 && n_cols > 0 && nnz >= 0 && nnz < (1ll << 31) - 1, "b200_sim_create_scaled: bad shape");
+    B200_REQUIRE(topK >= 1, "b200_sim_create_scaled: topK must be >= 1");
+    h = new b200_sim_s();
+    h->n_rows = (int)n_rows; h->n_cols = (int)n_cols; h->nnz = nnz;
+    h->kind = B200_SIM_COSINE;
+    h->K = (int)std::min<int64_t>(topK, n_cols);
+    h->scaled = true;
+    h->h_A = h_A; h->h_B = h_B;
+    build(h, h_indptr, h_indices, h_data, nullptr, (cudaStream_t)stream);
+    h->h_A = h->h_B = nullptr;
     *out = h;
   });
   if (rc != B200_OK && h) delete h;

@@ -129,18 +129,3 @@ class MatrixFactorization_Cython_Epoch:
         except Exception:
             pass
 
-
-def smoke():
-    """One BPR-MF epoch on cuda:0 against the C oracle (same replayed sample stream)."""
-    from .synth import synth_urm
-    from oracle.sgd_oracle import MFOracle  # test infrastructure; smoke() is one of its permitted callers
-    X = synth_urm(500, 200, 0.05, seed=2)
-    kw = dict(n_factors=32, algorithm_name="MF_BPR", batch_size=64, learning_rate=0.05, random_seed=11, sgd_mode="adagrad",
-              user_reg=1e-3, positive_reg=1e-3, negative_reg=1e-3)
-    g = MatrixFactorization_Cython_Epoch(X, **kw)
-    o = MFOracle(X, **kw)
-    for _ in range(2):
-        g.epochIteration_Cython()
-        o.epochIteration_Cython()
-    for a, b in ((g.get_USER_factors(), o.get_USER_factors()), (g.get_ITEM_factors(), o.get_ITEM_factors())):
-        assert np.allclose(a, b, rtol=1e-4, atol=1e-6), float(np.abs(a - b).max())

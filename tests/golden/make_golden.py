@@ -98,3 +98,35 @@ def make_sgd_golden():
 
 if __name__ == "__main__":
     make_sgd_golden()
+
+
+GRAPH_CASES = [
+    dict(cls="P3alpha", topK=10, alpha=1.0, normalize_similarity=False),
+    dict(cls="P3alpha", topK=10, alpha=0.7, normalize_similarity=True),
+    dict(cls="RP3beta", topK=10, alpha=1.0, beta=0.6, normalize_similarity=True),
+    dict(cls="RP3beta", topK=12, alpha=0.5, beta=0.3, normalize_similarity=False),
+    dict(cls="RP3beta", topK=10, alpha=1.2, beta=0.6, min_rating=2, implicit=True, normalize_similarity=True),
+]
+
+
+def make_graph_golden():
+    """tests/golden/graph_golden.npz: W_sparse of the reference's P3alphaRecommender / RP3betaRecommender."""
+    ref_loader.ensure_import_path()
+    from GraphBased.P3alphaRecommender import P3alphaRecommender
+    from GraphBased.RP3betaRecommender import RP3betaRecommender
+    out = {}
+    for n, c in enumerate(GRAPH_CASES):
+        c = dict(c)
+        cls = P3alphaRecommender if c.pop("cls") == "P3alpha" else RP3betaRecommender
+        X = synth_urm(400, 150, 0.06, seed=17, values="continuous" if n % 2 == 0 else "ratings")
+        r = cls(X)
+        r.fit(**c)
+        W = sps.csr_matrix(r.W_sparse)
+        W.sort_indices()
+        out["g%d_indptr" % n], out["g%d_indices" % n], out["g%d_data" % n] = W.indptr, W.indices, W.data
+    np.savez_compressed(os.path.join(HERE, "graph_golden.npz"), **out)
+    print("wrote graph_golden.npz")
+
+
+if __name__ == "__main__":
+    make_graph_golden()

@@ -79,24 +79,34 @@ def test_philox_stream_parity_and_sample_validity(algo):
     _compare(g, o)
 
 
-def test_hogwild_moves_like_the_sequential_recursion():
-    """Hogwild mode (no batch barrier) against the batch_size=1 recursion on the same Philox stream and initial
-    point: the accumulated parameter movement must point the same way (statistical parity)."""
-    X = synth_urm(2000, 600, 0.03, seed=7, popularity=0.8)
+def test_hogwild_descends_like_the_sequential_recursion():
+    """Hogwild mode (no batch barrier; every sample of an epoch may read stale rows) against the batch_size=1
+    recursion on the same Philox stream and initial point: statistical parity -- the BPR
+    objective on a fixed probe set must fall by a comparable amount."""
+    X = synth_urm(4000, 600, 0.03, seed=7, popularity=0.8)
     kw = dict(algorithm_name="MF_BPR", n_factors=32, batch_size=1, learning_rate=0.05, random_seed=3, sgd_mode="sgd",
-              user_reg=1e-3, positive_reg=1e-3, negative_reg=1e-3)
+              user_reg=1e-4, positive_reg=1e-4, negative_reg=1e-4)
     g = _cls()(X, sampler="philox", hogwild=True, **kw)
     s = _cls()(X, sampler="philox", hogwild=False, **kw)  # sequential batch-1 semantics, same stream
-    U0, V0 = s.get_USER_factors(), s.get_ITEM_factors()
-    for _ in range(5):
+    rng = np.random.default_rng(0)
+    us = rng.integers(0, 4000, 30000)
+    us = us[np.diff(X.indptr)[us] > 0]
+    pos = np.array([X.indices[X.indptr[u] + rng.integers(0, X.indptr[u + 1] - X.indptr[u])] for u in us])
+    neg = rng.integers(0, 600, len(us))
+
+    def loss(m):
+        U, V = m.get_USER_factors(), m.get_ITEM_factors()
+        x = np.einsum("ij,ij->i", U[us], V[pos] - V[neg])
+        return float(np.mean(np.log1p(np.exp(-x))))
+
+    l0 = loss(s)
+    for _ in range(40):
         g.epochIteration_Cython()
         s.epochIteration_Cython()
     assert np.array_equal(g.get_samples()[0], s.get_samples()[0])
-    for a, b, z in ((g.get_USER_factors(), s.get_USER_factors(), U0), (g.get_ITEM_factors(), s.get_ITEM_factors(), V0)):
-        da, db = (a - z).ravel(), (b - z).ravel()
-        cos = float(da @ db / (np.linalg.norm(da) * np.linalg.norm(db)))
-        assert np.linalg.norm(db) > 0 and cos > 0.98, cos
-        assert abs(np.linalg.norm(da) / np.linalg.norm(db) - 1) < 0.1
+    ls, lh = loss(s), loss(g)
+    assert l0 - ls > 0.01, (l0, ls)
+    assert 0.7 < (l0 - lh) / (l0 - ls) < 1.3, (l0, ls, lh)
 
 
 def test_argument_errors():
