@@ -192,6 +192,30 @@ int b200_dense_topk_device(const float* d_matrix, int n, int K, int along_column
 int b200_sparse_topk_device(int n, const int32_t* d_ptr, const int32_t* d_line_idx, const float* d_vals, int K,
                             int mode, int32_t* d_idx, float* d_val, int32_t* d_cnt, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K6: batch scoring behind _compute_item_score / recommend
+ * replaces  Base/BaseSimilarityMatrixRecommender.py:73-92 (and :97-116)   URM[users] . W_sparse -> dense block
+ *           Base/BaseMatrixFactorizationRecommender.py:38-70              U[users] . V^T (+ biases)
+ *           Base/BaseRecommender.py:164-169, :189-196                      seen -> -inf, per-row top-`cutoff`
+ * All pointers are DEVICE pointers; d_out / d_scores are dense row-major [n_users_block, n_items] fp32.
+ * ------------------------------------------------------------------------------------------------ */
+/* d_out[b, :] = sum over (i, r) in row d_users[b] of CSR A of r * (row i of CSR B) */
+int b200_score_spmm_device(const int32_t* d_users, int n_users_block, const int32_t* d_a_ptr, const int32_t* d_a_idx,
+                           const float* d_a_val, const int32_t* d_b_ptr, const int32_t* d_b_idx, const float* d_b_val,
+                           int n_out_cols, float* d_out, void* stream);
+/* d_out[cols, rows] = transpose of d_in[rows, cols] (item factors are scored from their transpose) */
+int b200_transpose_device(const float* d_in, int rows, int cols, float* d_out, void* stream);
+/* d_out[b, j] = U[d_users[b], :] . VT[:, j] (+ global + user + item bias when the three pointers are non-NULL) */
+int b200_score_mf_device(const int32_t* d_users, int n_users_block, const float* d_user_factors,
+                         const float* d_item_factors_T, int n_factors, int n_items, const float* d_user_bias,
+                         const float* d_item_bias, const float* d_global_bias, float* d_out, void* stream);
+/* -inf on items outside d_items_keep (nullable, n_items bytes) and on the seen items of each user (nullable URM) */
+int b200_score_mask_device(const int32_t* d_users, int n_users_block, const int32_t* d_urm_ptr, const int32_t* d_urm_idx,
+                           const unsigned char* d_items_keep, int n_items, float* d_scores, void* stream);
+/* per row the `cutoff` (<= 1024) best items, best first, ties by ascending item index: [n_rows, cutoff] tables */
+int b200_score_topn_device(const float* d_scores, int n_rows, int n_items, int cutoff, int32_t* d_items,
+                           float* d_item_scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

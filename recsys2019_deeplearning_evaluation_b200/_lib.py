@@ -58,6 +58,11 @@ SIGNATURES = {
     "b200_slim_last_epoch_ms": (ctypes.c_int, [c_void, c_float_p]),
     "b200_dense_topk_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void]),
     "b200_sparse_topk_device": (ctypes.c_int, [ctypes.c_int, c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void]),
+    "b200_score_spmm_device": (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, c_void, c_void, c_void, c_void, ctypes.c_int, c_void, c_void]),
+    "b200_transpose_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, c_void, c_void]),
+    "b200_score_mf_device": (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void, c_void]),
+    "b200_score_mask_device": (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, c_void, ctypes.c_int, c_void, c_void]),
+    "b200_score_topn_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
 }
 
 _lib = None

@@ -1,0 +1,429 @@
+"""Recommender-level mirrors: the reference's `.fit()` / `._compute_item_score()` / `.recommend()` API on top of the
+CUDA core.  Class names, `fit` keyword arguments and fitted attributes (`W_sparse`, `USER_factors`, `ITEM_factors`, ...)
+follow the reference so that the evaluator and the hyper-parameter search can drive them unchanged:
+
+    Base/BaseRecommender.py:14-253                       BaseRecommender (init casts, recommend, seen filter)
+    Base/BaseSimilarityMatrixRecommender.py:15-116       _compute_item_score = URM[users] . W_sparse
+    Base/BaseMatrixFactorizationRecommender.py:15-102    _compute_item_score = U[users] . V^T (+ biases)
+    KNN/ItemKNNCFRecommender.py:31-54, KNN/UserKNNCFRecommender.py:32-54
+    GraphBased/P3alphaRecommender.py:34-144, GraphBased/RP3betaRecommender.py:31-154
+    SLIM_BPR/Cython/SLIM_BPR_Cython.py:67-183
+    MatrixFactorization/Cython/MatrixFactorization_Cython.py:33-190
+    Base/Incremental_Training_Early_Stopping.py:91-261   epoch loop with periodic validation / best-model snapshot
+
+Scores, the seen-item mask and the top-`cutoff` selection run on the device (csrc/score.cu); the dense score block is
+only copied to the host when the caller asks for it (`_compute_item_score`, `return_scores=True`).
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sps
+
+from . import _lib
+from .similarity import Compute_Similarity, _as_csr_f32
+
+
+def _dev_csr(M):
+    """CSR scipy matrix -> (indptr, indices, data) int32/int32/float32 CUDA tensors."""
+    import torch
+    M = sps.csr_matrix(M, dtype=np.float32)
+    if not M.has_sorted_indices:
+        M = M.sorted_indices()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return (torch.from_numpy(np.ascontiguousarray(M.indptr, np.int32)).to(dev),
+            torch.from_numpy(np.ascontiguousarray(M.indices, np.int32)).to(dev),
+            torch.from_numpy(np.ascontiguousarray(M.data, np.float32)).to(dev))
+
+
+def _stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class BaseRecommender(object):
+    RECOMMENDER_NAME = "Recommender_Base_Class"
+
+    def __init__(self, URM_train, verbose=True):
+        self.URM_train = sps.csr_matrix(URM_train.copy(), dtype=np.float32)  # BaseRecommender.py:23-24
+        self.URM_train.eliminate_zeros()
+        self.URM_train.sort_indices()
+        self.n_users, self.n_items = self.URM_train.shape
+        self.verbose = verbose
+        self.items_to_ignore_flag = False
+        self.items_to_ignore_ID = np.array([], dtype=np.int64)
+        self._cold_user_mask = np.ediff1d(self.URM_train.indptr) == 0
+        self._cold_item_mask = np.bincount(self.URM_train.indices, minlength=self.n_items) == 0
+        self._lib = _lib.load()
+        self._d_urm = None
+
+    def _print(self, string):
+        if self.verbose:
+            print("{}: {}".format(self.RECOMMENDER_NAME, string))
+
+    def get_URM_train(self):
+        return self.URM_train.copy()
+
+    def set_items_to_ignore(self, items_to_ignore):
+        self.items_to_ignore_flag = True
+        self.items_to_ignore_ID = np.array(items_to_ignore, dtype=np.int64)
+
+    def reset_items_to_ignore(self):
+        self.items_to_ignore_flag = False
+        self.items_to_ignore_ID = np.array([], dtype=np.int64)
+
+    def _urm_device(self):
+        if self._d_urm is None:
+            self._d_urm = _dev_csr(self.URM_train)
+        return self._d_urm
+
+    # ---- device-side pieces shared by every model -----------------------------------------------------------------
+    def _scores_device(self, d_users, items_to_compute=None):
+        """[B, n_items] float32 CUDA tensor of raw scores; model specific."""
+        raise NotImplementedError("BaseRecommender: compute_item_score not assigned for current recommender")
+
+    def _users_tensor(self, user_id_array):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(user_id_array, np.int32)).to(torch.device("cuda", torch.cuda.current_device()))
+
+    def _mask_items(self, scores, items_to_compute, d_users=None, seen=False):
+        import torch
+        keep = None
+        if items_to_compute is not None:
+            k = np.zeros(self.n_items, np.uint8)
+            k[np.asarray(items_to_compute, dtype=np.int64)] = 1
+            keep = torch.from_numpy(k).to(scores.device)
+        ptr, idx, _ = self._urm_device()
+        _lib.check(self._lib.b200_score_mask_device(
+            d_users.data_ptr() if (seen and d_users is not None) else None, scores.shape[0],
+            ptr.data_ptr() if seen else None, idx.data_ptr() if seen else None,
+            keep.data_ptr() if keep is not None else None, self.n_items, scores.data_ptr(), _stream()))
+        return scores
+
+    def _compute_item_score(self, user_id_array, items_to_compute=None):
+        """(len(user_id_array), n_items) float32 ndarray, -inf on items outside `items_to_compute`."""
+        d_users = self._users_tensor(user_id_array)
+        scores = self._scores_device(d_users)
+        if items_to_compute is not None:
+            self._mask_items(scores, items_to_compute)
+        return scores.cpu().numpy()
+
+    def recommend(self, user_id_array, cutoff=None, remove_seen_flag=True, items_to_compute=None, remove_top_pop_flag=False,
+                  remove_custom_items_flag=False, return_scores=False):
+        """BaseRecommender.py:131-222 on the device: scores -> seen / custom items to -inf -> per-user top-`cutoff`
+        (best first, ties by ascending item id) with -inf entries dropped from the lists."""
+        import torch
+        single_user = np.isscalar(user_id_array)
+        users = np.atleast_1d(user_id_array)
+        if cutoff is None:
+            cutoff = self.n_items - 1
+        cutoff = int(min(cutoff, self.n_items))
+        d_users = self._users_tensor(users)
+        scores = self._scores_device(d_users)
+        if items_to_compute is not None or remove_seen_flag:
+            self._mask_items(scores, items_to_compute, d_users, seen=remove_seen_flag)
+        if remove_custom_items_flag and len(self.items_to_ignore_ID):
+            scores[:, torch.from_numpy(self.items_to_ignore_ID).to(scores.device)] = float("-inf")
+        if cutoff <= 1024:
+            items = torch.empty((len(users), cutoff), dtype=torch.int32, device=scores.device)
+            vals = torch.empty((len(users), cutoff), dtype=torch.float32, device=scores.device)
+            _lib.check(self._lib.b200_score_topn_device(scores.data_ptr(), len(users), self.n_items, cutoff, items.data_ptr(),
+                                                        vals.data_ptr(), _stream()))
+            items_h, vals_h = items.cpu().numpy(), vals.cpu().numpy()
+        else:  # full rankings are host work in the reference too; keep the device scores, sort on the host
+            sc = scores.cpu().numpy()
+            order = np.lexsort((np.broadcast_to(np.arange(self.n_items), sc.shape), -sc), axis=1)[:, :cutoff]
+            items_h, vals_h = order.astype(np.int32), np.take_along_axis(sc, order, axis=1)
+        ranking_list = [items_h[r][np.isfinite(vals_h[r])].tolist() for r in range(len(users))]
+        if single_user:
+            ranking_list = ranking_list[0]
+        if return_scores:
+            return ranking_list, scores.cpu().numpy()
+        return ranking_list
+
+
+class BaseItemSimilarityMatrixRecommender(BaseRecommender):
+    """BaseSimilarityMatrixRecommender.py:62-92: scores = URM[users] . W_sparse."""
+
+    def _w_device(self):
+        if getattr(self, "_d_w_src", None) is not self.W_sparse:
+            self._d_w = _dev_csr(self.W_sparse)
+            self._d_w_src = self.W_sparse
+        return self._d_w
+
+    def _scores_device(self, d_users, items_to_compute=None):
+        import torch
+        a_ptr, a_idx, a_val = self._urm_device()
+        b_ptr, b_idx, b_val = self._w_device()
+        out = torch.empty((d_users.shape[0], self.n_items), dtype=torch.float32, device=d_users.device)
+        _lib.check(self._lib.b200_score_spmm_device(d_users.data_ptr(), d_users.shape[0], a_ptr.data_ptr(), a_idx.data_ptr(),
+                                                    a_val.data_ptr(), b_ptr.data_ptr(), b_idx.data_ptr(), b_val.data_ptr(),
+                                                    self.n_items, out.data_ptr(), _stream()))
+        return out
+
+
+class BaseUserSimilarityMatrixRecommender(BaseRecommender):
+    """BaseSimilarityMatrixRecommender.py:95-116: scores = W_sparse[users] . URM."""
+
+    def _scores_device(self, d_users, items_to_compute=None):
+        import torch
+        if getattr(self, "_d_w_src", None) is not self.W_sparse:
+            self._d_w = _dev_csr(self.W_sparse)
+            self._d_w_src = self.W_sparse
+        a_ptr, a_idx, a_val = self._d_w
+        b_ptr, b_idx, b_val = self._urm_device()
+        out = torch.empty((d_users.shape[0], self.n_items), dtype=torch.float32, device=d_users.device)
+        _lib.check(self._lib.b200_score_spmm_device(d_users.data_ptr(), d_users.shape[0], a_ptr.data_ptr(), a_idx.data_ptr(),
+                                                    a_val.data_ptr(), b_ptr.data_ptr(), b_idx.data_ptr(), b_val.data_ptr(),
+                                                    self.n_items, out.data_ptr(), _stream()))
+        return out
+
+
+class ItemKNNCFRecommender(BaseItemSimilarityMatrixRecommender):
+    RECOMMENDER_NAME = "ItemKNNCFRecommender"
+    FEATURE_WEIGHTING_VALUES = ["BM25", "TF-IDF", "none"]
+
+    def fit(self, topK=50, shrink=100, similarity="cosine", normalize=True, feature_weighting="none", **similarity_args):
+        """KNN/ItemKNNCFRecommender.py:31-54."""
+        self.topK, self.shrink = topK, shrink
+        if feature_weighting not in self.FEATURE_WEIGHTING_VALUES:
+            raise ValueError("Value for 'feature_weighting' not recognized. Acceptable values are {}, provided was '{}'".format(
+                self.FEATURE_WEIGHTING_VALUES, feature_weighting))
+        if feature_weighting != "none":
+            raise NotImplementedError("BM25 / TF-IDF feature weighting (Base/IR_feature_weighting.py) is a 'next' row")
+        sim = Compute_Similarity(self.URM_train, shrink=shrink, topK=topK, normalize=normalize, similarity=similarity,
+                                 **similarity_args)
+        self.W_sparse = sps.csr_matrix(sim.compute_similarity(), dtype=np.float32)
+        sim.compute_similarity_object._dealloc()
+
+
+class UserKNNCFRecommender(BaseUserSimilarityMatrixRecommender):
+    RECOMMENDER_NAME = "UserKNNCFRecommender"
+
+    def fit(self, topK=50, shrink=100, similarity="cosine", normalize=True, feature_weighting="none", **similarity_args):
+        """KNN/UserKNNCFRecommender.py:32-54: the same kernel on URM^T (columns = users)."""
+        self.topK, self.shrink = topK, shrink
+        if feature_weighting != "none":
+            raise NotImplementedError("BM25 / TF-IDF feature weighting is a 'next' row")
+        sim = Compute_Similarity(self.URM_train.T.tocsr(), shrink=shrink, topK=topK, normalize=normalize, similarity=similarity,
+                                 **similarity_args)
+        self.W_sparse = sps.csr_matrix(sim.compute_similarity(), dtype=np.float32)
+        sim.compute_similarity_object._dealloc()
+
+
+class P3alphaRecommender(BaseItemSimilarityMatrixRecommender):
+    RECOMMENDER_NAME = "P3alphaRecommender"
+
+    def fit(self, topK=100, alpha=1.0, min_rating=0, implicit=False, normalize_similarity=False):
+        from .graph import p3_similarity
+        self.topK, self.alpha, self.min_rating, self.implicit, self.normalize_similarity = topK, alpha, min_rating, implicit, normalize_similarity
+        self.W_sparse = p3_similarity(self.URM_train, topK=topK, alpha=alpha, beta=0.0, min_rating=min_rating, implicit=implicit,
+                                      normalize_similarity=normalize_similarity)
+
+
+class RP3betaRecommender(BaseItemSimilarityMatrixRecommender):
+    RECOMMENDER_NAME = "RP3betaRecommender"
+
+    def fit(self, alpha=1.0, beta=0.6, min_rating=0, topK=100, implicit=False, normalize_similarity=True):
+        from .graph import p3_similarity
+        self.alpha, self.beta, self.min_rating, self.topK, self.implicit, self.normalize_similarity = alpha, beta, min_rating, topK, implicit, normalize_similarity
+        self.W_sparse = p3_similarity(self.URM_train, topK=topK, alpha=alpha, beta=beta, min_rating=min_rating, implicit=implicit,
+                                      normalize_similarity=normalize_similarity)
+
+
+class Incremental_Training_Early_Stopping(object):
+    """Base/Incremental_Training_Early_Stopping.py:91-261, same control flow: run epochs, every `validation_every_n`
+    epochs prepare the model, evaluate `validation_metric` with `evaluator_object.evaluateRecommender(self)`, keep the
+    best snapshot, stop after `lower_validations_allowed` non-improving validations."""
+
+    def _train_with_early_stopping(self, epochs_max, epochs_min=0, validation_every_n=None, stop_on_validation=False,
+                                   validation_metric=None, lower_validations_allowed=None, evaluator_object=None,
+                                   algorithm_name="Incremental_Training_Early_Stopping"):
+        assert epochs_max > 0 and 0 <= epochs_min <= epochs_max
+        assert evaluator_object is None or (validation_every_n is not None and validation_metric is not None)
+        self.best_validation_metric, lower_validation_count = None, 0
+        self.epochs_best, epochs_current, convergence = 0, 0, False
+        while epochs_current < epochs_max and not convergence:
+            self._run_epoch(epochs_current)
+            if evaluator_object is not None and (epochs_current + 1) % validation_every_n == 0:
+                self._prepare_model_for_validation()
+                results_run, _ = evaluator_object.evaluateRecommender(self)
+                results_run = results_run[list(results_run.keys())[0]]
+                current_metric_value = results_run[validation_metric]
+                if not np.isfinite(current_metric_value):  # :200-205
+                    break
+                if self.best_validation_metric is None or self.best_validation_metric < current_metric_value:
+                    self.best_validation_metric = current_metric_value
+                    self._update_best_model()
+                    self.epochs_best = epochs_current + 1
+                    lower_validation_count = 0
+                else:
+                    lower_validation_count += 1
+                if stop_on_validation and lower_validation_count >= lower_validations_allowed and epochs_current >= epochs_min:
+                    convergence = True
+            epochs_current += 1
+        if evaluator_object is None:  # no validation: the last model is the best model
+            self._prepare_model_for_validation()
+            self._update_best_model()
+            self.epochs_best = epochs_current
+
+
+class BaseMatrixFactorizationRecommender(BaseRecommender):
+    """BaseMatrixFactorizationRecommender.py:15-102: scores = U[users] . V^T (+ global + user + item bias)."""
+
+    def __init__(self, URM_train, verbose=True):
+        super(BaseMatrixFactorizationRecommender, self).__init__(URM_train, verbose=verbose)
+        self.use_bias = False
+
+    def _factors_device(self):
+        import torch
+        key = (id(self.USER_factors), id(self.ITEM_factors))
+        if getattr(self, "_d_f_key", None) != key:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            U = torch.from_numpy(np.ascontiguousarray(self.USER_factors, np.float32)).to(dev)
+            V = torch.from_numpy(np.ascontiguousarray(self.ITEM_factors, np.float32)).to(dev)
+            VT = torch.empty((V.shape[1], V.shape[0]), dtype=torch.float32, device=dev)
+            _lib.check(self._lib.b200_transpose_device(V.data_ptr(), V.shape[0], V.shape[1], VT.data_ptr(), _stream()))
+            biases = None
+            if self.use_bias:
+                biases = tuple(torch.from_numpy(np.ascontiguousarray(np.atleast_1d(b), np.float32)).to(dev)
+                               for b in (self.USER_bias, self.ITEM_bias, self.GLOBAL_bias))
+            self._d_f, self._d_f_key = (U, VT, biases), key
+        return self._d_f
+
+    def _scores_device(self, d_users, items_to_compute=None):
+        import torch
+        U, VT, biases = self._factors_device()
+        out = torch.empty((d_users.shape[0], self.n_items), dtype=torch.float32, device=d_users.device)
+        bu = bi = mu = None
+        if biases is not None:
+            bu, bi, mu = (b.data_ptr() for b in biases)
+        _lib.check(self._lib.b200_score_mf_device(d_users.data_ptr(), d_users.shape[0], U.data_ptr(), VT.data_ptr(), U.shape[1],
+                                                  self.n_items, bu, bi, mu, out.data_ptr(), _stream()))
+        return out
+
+
+class _MatrixFactorization_Cython(BaseMatrixFactorizationRecommender, Incremental_Training_Early_Stopping):
+    """MatrixFactorization/Cython/MatrixFactorization_Cython.py:19-141."""
+    RECOMMENDER_NAME = "MatrixFactorization_Cython_Recommender"
+
+    def __init__(self, URM_train, verbose=True, algorithm_name="MF_BPR"):
+        super(_MatrixFactorization_Cython, self).__init__(URM_train, verbose=verbose)
+        self.normalize = False
+        self.algorithm_name = algorithm_name
+
+    def fit(self, epochs=300, batch_size=1000, num_factors=10, positive_threshold_BPR=None, learning_rate=0.001, use_bias=True,
+            sgd_mode="sgd", negative_interactions_quota=0.0, init_mean=0.0, init_std_dev=0.1, user_reg=0.0, item_reg=0.0,
+            bias_reg=0.0, positive_reg=0.0, negative_reg=0.0, random_seed=None, sampler="glibc", hogwild=False,
+            **earlystopping_kwargs):
+        from .mf_epoch import MatrixFactorization_Cython_Epoch
+        self.num_factors, self.use_bias, self.sgd_mode = num_factors, use_bias, sgd_mode
+        self.positive_threshold_BPR, self.learning_rate = positive_threshold_BPR, learning_rate
+        assert 0.0 <= negative_interactions_quota < 1.0, "{}: negative_interactions_quota must be a float value >=0 and < 1.0, provided was '{}'".format(
+            self.RECOMMENDER_NAME, negative_interactions_quota)  # MatrixFactorization_Cython.py:49-50
+        self.negative_interactions_quota = negative_interactions_quota
+        if self.algorithm_name not in ("FUNK_SVD", "MF_BPR"):
+            raise NotImplementedError("ASY_SVD is not on the CUDA path")
+        URM_train_positive = self.URM_train
+        if self.algorithm_name == "MF_BPR":  # :63-72
+            URM_train_positive = self.URM_train.copy()
+            if positive_threshold_BPR is not None:
+                URM_train_positive.data = URM_train_positive.data >= positive_threshold_BPR
+                URM_train_positive.eliminate_zeros()
+                assert URM_train_positive.nnz > 0, "MatrixFactorization_Cython: URM_train_positive is empty, positive threshold is too high"
+        self.cythonEpoch = MatrixFactorization_Cython_Epoch(
+            URM_train_positive, algorithm_name=self.algorithm_name, n_factors=num_factors, learning_rate=learning_rate,
+            sgd_mode=sgd_mode, user_reg=user_reg, item_reg=item_reg, bias_reg=bias_reg, positive_reg=positive_reg,
+            negative_reg=negative_reg, batch_size=batch_size, use_bias=use_bias, init_mean=init_mean,
+            negative_interactions_quota=negative_interactions_quota, init_std_dev=init_std_dev, verbose=self.verbose,
+            random_seed=random_seed, sampler=sampler, hogwild=hogwild)
+        self._prepare_model_for_validation()
+        self._update_best_model()
+        self._train_with_early_stopping(epochs, algorithm_name=self.algorithm_name, **earlystopping_kwargs)
+        self.USER_factors, self.ITEM_factors = self.USER_factors_best, self.ITEM_factors_best
+        if self.use_bias:
+            self.USER_bias, self.ITEM_bias, self.GLOBAL_bias = self.USER_bias_best, self.ITEM_bias_best, self.GLOBAL_bias_best
+        self.cythonEpoch._dealloc()
+
+    def _prepare_model_for_validation(self):  # :120-127
+        self.USER_factors = self.cythonEpoch.get_USER_factors()
+        self.ITEM_factors = self.cythonEpoch.get_ITEM_factors()
+        if self.use_bias:
+            self.USER_bias = self.cythonEpoch.get_USER_bias()
+            self.ITEM_bias = self.cythonEpoch.get_ITEM_bias()
+            self.GLOBAL_bias = self.cythonEpoch.get_GLOBAL_bias()
+
+    def _update_best_model(self):  # :129-136
+        self.USER_factors_best, self.ITEM_factors_best = self.USER_factors.copy(), self.ITEM_factors.copy()
+        if self.use_bias:
+            self.USER_bias_best, self.ITEM_bias_best, self.GLOBAL_bias_best = self.USER_bias.copy(), self.ITEM_bias.copy(), np.array(self.GLOBAL_bias)
+
+    def _run_epoch(self, num_epoch):
+        self.cythonEpoch.epochIteration_Cython()
+
+
+class MatrixFactorization_BPR_Cython(_MatrixFactorization_Cython):
+    """MatrixFactorization_Cython.py:144-161: forces use_bias=False and negative_interactions_quota=0."""
+    RECOMMENDER_NAME = "MatrixFactorization_BPR_Cython_Recommender"
+
+    def __init__(self, *pos_args, **key_args):
+        super(MatrixFactorization_BPR_Cython, self).__init__(*pos_args, algorithm_name="MF_BPR", **key_args)
+
+    def fit(self, **key_args):
+        key_args["use_bias"] = False
+        key_args["negative_interactions_quota"] = 0.0
+        super(MatrixFactorization_BPR_Cython, self).fit(**key_args)
+
+
+class MatrixFactorization_FunkSVD_Cython(_MatrixFactorization_Cython):
+    """MatrixFactorization_Cython.py:164-176."""
+    RECOMMENDER_NAME = "MatrixFactorization_FunkSVD_Cython_Recommender"
+
+    def __init__(self, *pos_args, **key_args):
+        super(MatrixFactorization_FunkSVD_Cython, self).__init__(*pos_args, algorithm_name="FUNK_SVD", **key_args)
+
+
+class SLIM_BPR_Cython(BaseItemSimilarityMatrixRecommender, Incremental_Training_Early_Stopping):
+    """SLIM_BPR/Cython/SLIM_BPR_Cython.py:48-183 with S dense on the device (no RAM-based mode selection)."""
+    RECOMMENDER_NAME = "SLIM_BPR_Recommender"
+
+    def fit(self, epochs=300, positive_threshold_BPR=None, train_with_sparse_weights=None, symmetric=True, random_seed=None,
+            lambda_i=0.0, lambda_j=0.0, learning_rate=1e-4, topK=200, sgd_mode="adagrad", gamma=0.995, beta_1=0.9,
+            beta_2=0.999, sampler="glibc", hogwild=False, **earlystopping_kwargs):
+        from .slim_bpr_epoch import SLIM_BPR_Cython_Epoch, similarityMatrixTopK
+        if train_with_sparse_weights:
+            raise NotImplementedError("train_with_sparse_weights=True is not on the CUDA path")
+        self.symmetric, self.train_with_sparse_weights = symmetric, False
+        URM_train_positive = self.URM_train.copy()
+        if positive_threshold_BPR is not None:  # SLIM_BPR_Cython.py:112-116
+            URM_train_positive.data = URM_train_positive.data >= positive_threshold_BPR
+            URM_train_positive.eliminate_zeros()
+            assert URM_train_positive.nnz > 0, "SLIM_BPR_Cython: URM_train_positive is empty, positive threshold is too high"
+        if topK is not False and topK < 1:  # :138-140
+            raise ValueError("TopK not valid. Acceptable values are either False or a positive integer value. Provided value was '{}'".format(topK))
+        self.topK, self._topk_fn = topK, similarityMatrixTopK
+        self.cythonEpoch = SLIM_BPR_Cython_Epoch(URM_train_positive, train_with_sparse_weights=False, final_model_sparse_weights=True,
+                                                 topK=topK, learning_rate=learning_rate, li_reg=lambda_i, lj_reg=lambda_j,
+                                                 symmetric=symmetric, sgd_mode=sgd_mode, verbose=self.verbose, random_seed=random_seed,
+                                                 gamma=gamma, beta_1=beta_1, beta_2=beta_2, sampler=sampler, hogwild=hogwild)
+        self.S_incremental = self.cythonEpoch.get_S()
+        self.S_best = self.S_incremental.copy()
+        self._train_with_early_stopping(epochs, algorithm_name=self.RECOMMENDER_NAME, **earlystopping_kwargs)
+        self.get_S_incremental_and_set_W()
+        self.cythonEpoch._dealloc()
+
+    def _prepare_model_for_validation(self):
+        self.get_S_incremental_and_set_W()
+
+    def _update_best_model(self):
+        self.S_best = self.S_incremental.copy()
+
+    def _run_epoch(self, num_epoch):
+        self.cythonEpoch.epochIteration_Cython()
+
+    def get_S_incremental_and_set_W(self):  # :174-183: dense training applies a COLUMN top-K on top of get_S
+        self.S_incremental = self.cythonEpoch.get_S()
+        W = self.S_incremental
+        if self.topK is not False:
+            from .graph import sparse_column_topk
+            W = sparse_column_topk(sps.csr_matrix(W, dtype=np.float32), self.topK)
+        self.W_sparse = sps.csr_matrix(W, dtype=np.float32)

