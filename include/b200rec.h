@@ -87,6 +87,10 @@ int b200_sim_info(b200_sim_t h, int* K, int* n_windows, int* window_cells, int* 
 int b200_sim_compute_device(b200_sim_t h, int start_col, int end_col, int32_t* d_idx, float* d_val,
                             int32_t* d_cnt, void* stream);
 int b200_sim_compute(b200_sim_t h, int start_col, int end_col, int32_t* h_idx, float* h_val, int32_t* h_cnt);
+/* Dense output (TopK == 0, pyx:510-513,597-599; and the full Gram EASE_R asks for with topK = n_items,
+ * EASE_R/EASE_R_Recommender.py:55-56): d_out is [end_col - start_col, n_cols] row-major fp32,
+ * d_out[target - start_col, neighbour] = W[neighbour, target]; zero where the columns share no row. */
+int b200_sim_compute_dense_device(b200_sim_t h, int start_col, int end_col, float* d_out, void* stream);
 
 /* Assemble the scipy-canonical CSR of W (n_cols x n_cols, row j = neighbour, column = target column, sorted
  * column indices per row, fp32 -- what pyx:603-611 returns) from a top-K table holding ALL columns
@@ -199,7 +203,8 @@ int b200_sparse_topk_device(int n, const int32_t* d_ptr, const int32_t* d_line_i
  *           Base/BaseRecommender.py:164-169, :189-196                      seen -> -inf, per-row top-`cutoff`
  * All pointers are DEVICE pointers; d_out / d_scores are dense row-major [n_users_block, n_items] fp32.
  * ------------------------------------------------------------------------------------------------ */
-/* d_out[b, :] = sum over (i, r) in row d_users[b] of CSR A of r * (row i of CSR B) */
+/* d_out[b, :] = sum over (i, r) in row d_users[b] of CSR A of r * (row i of B); B is CSR, or -- with d_b_ptr and
+ * d_b_idx NULL -- a dense row-major [*, n_out_cols] matrix in d_b_val (EASE_R's dense W, EASE_R_Recommender.py:87-106) */
 int b200_score_spmm_device(const int32_t* d_users, int n_users_block, const int32_t* d_a_ptr, const int32_t* d_a_idx,
                            const float* d_a_val, const int32_t* d_b_ptr, const int32_t* d_b_idx, const float* d_b_val,
                            int n_out_cols, float* d_out, void* stream);
@@ -215,6 +220,20 @@ int b200_score_mask_device(const int32_t* d_users, int n_users_block, const int3
 /* per row the `cutoff` (<= 1024) best items, best first, ties by ascending item index: [n_rows, cutoff] tables */
 int b200_score_topn_device(const float* d_scores, int n_rows, int n_items, int cutoff, int32_t* d_items,
                            float* d_item_scores, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5: EASE^R closed form  (hot path iii)
+ * replaces  EASE_R/EASE_R_Recommender.py:55-69
+ * ------------------------------------------------------------------------------------------------ */
+/* In-place inverse of a symmetric positive definite matrix on the device through a blocked Cholesky factorisation
+ * (replaces np.linalg.inv, EASE_R_Recommender.py:65).  d_A: [n_pad, n_pad] row-major fp32, n_pad a multiple of 128
+ * (pad with an identity block); d_work: 2 * n_pad * n_pad floats. */
+int b200_spd_inverse_device(float* d_A, int n_pad, float* d_work, void* stream);
+/* d_G: dense [n_items, n_items] Gram block X^T X (b200_sim_compute_dense_device with normalize=0, shrink=0); the
+ * diagonal is replaced by item popularity (stored-entry count per column of the URM, :62-63) + l2_norm, the matrix is
+ * inverted, and B[i, j] = P[i, j] / (-P[j, j]), B[j, j] = 0 is written to h_B (host) and/or d_B (device). */
+int b200_ease_from_gram_device(const float* d_G, int n_items, const int32_t* d_urm_indices, int64_t nnz, float l2_norm,
+                               float* h_B, float* d_B, void* stream);
 
 #ifdef __cplusplus
 }

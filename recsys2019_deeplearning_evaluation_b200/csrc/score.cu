@@ -33,7 +33,12 @@ __global__ void __launch_bounds__(512) spmm_rows_kernel(const int* __restrict__ 
     for (int k = s + warp; k < e; k += nwarps) {
       const int i = a_idx[k];
       const float r = a_val[k];
-      for (int q = b_ptr[i] + lane; q < b_ptr[i + 1]; q += 32) atomicAdd(o + b_idx[q], r * b_val[q]);
+      if (b_ptr) {
+        for (int q = b_ptr[i] + lane; q < b_ptr[i + 1]; q += 32) atomicAdd(o + b_idx[q], r * b_val[q]);
+      } else {  // dense B: row i is b_val[i * n_out_cols ..]
+        const float* brow = b_val + (size_t)i * n_out_cols;
+        for (int j = lane; j < n_out_cols; j += 32) atomicAdd(o + j, r * brow[j]);
+      }
     }
     __syncthreads();
   }
@@ -186,7 +191,7 @@ int b200_score_spmm_device(const int32_t* d_users, int n_users_block, const int3
                            const float* d_a_val, const int32_t* d_b_ptr, const int32_t* d_b_idx, const float* d_b_val,
                            int n_out_cols, float* d_out, void* stream) {
   return guarded([&] {
-    B200_REQUIRE(d_users && d_a_ptr && d_b_ptr && d_out, "b200_score_spmm: NULL argument");
+    B200_REQUIRE(d_users && d_a_ptr && d_b_val && d_out, "b200_score_spmm: NULL argument");
     B200_REQUIRE(n_users_block >= 0 && n_out_cols > 0, "b200_score_spmm: bad shape");
     if (n_users_block == 0) return;
     spmm_rows_kernel<<<std::min(n_users_block, sm_count() * 4), 512, 0, (cudaStream_t)stream>>>(

@@ -74,6 +74,7 @@ struct KParams {
   float* out_val;
   int* out_cnt;
   int signed_data;
+  float* dense_out;  // dense mode (TopK == 0 / full Gram): [n_range, n_cols] row-major, out[target - col_begin, neighbour]
   unsigned long long* prof;  // optional [8] per-phase cycle counters (thread 0 of every CTA), test/bench hook
 };
 
@@ -410,6 +411,20 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
     if (tid == 0 && col >= win_lo && col < win_lo + win_n) acci[col - win_lo] = 0;  // pyx:396
     __syncthreads();
     PROF_MARK(1);
+    if (p.dense_out) {
+      // dense mode (pyx:510-513): every non-zero cell is normalised and written out, no selection
+      float* orow = p.dense_out + (size_t)out_base * p.n_cols;  // out_base = local target index here
+      for (int c = tid; c < win_n; c += THREADS) {
+        const float d = BINARY ? (float)acci[c] : accf[c];
+        if (d != 0.f) {
+          const int2 bn = __ldg(p.BN + win_lo + c);
+          orow[bn.y] = sim_value<F>(p, d, Ai, __int_as_float(bn.x));
+          acci[c] = 0;
+        }
+      }
+      __syncthreads();
+      continue;
+    }
 
     // ---------------- bootstrap: floor of the target-th best similarity from per-cell lower bounds
     nbuf = sh->nbuf;
@@ -580,6 +595,11 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     const int col = p.old2new[p.col_begin + lc];  // new numbering
     const int out_base_row = lc;
     int n_out = 0;
+    if (p.dense_out) {
+      process_column<F, BINARY, false>(p, col, p.K, out_base_row, smem_raw, &sh, s_tileB, &n_out);
+      __syncthreads();
+      continue;
+    }
     process_column<F, BINARY, false>(p, col, p.K, out_base_row * p.K, smem_raw, &sh, s_tileB, &n_out);
     if (p.signed_data && n_out < p.K) {
       // zeros outrank negatives (Compute_Similarity_Python.py:335-345): negatives are only emitted when the
@@ -1115,53 +1135,70 @@ int b200_sim_info(b200_sim_t h, int* K, int* n_windows, int* window_cells, int* 
   });
 }
 
+static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx, float* d_val, int32_t* d_cnt, float* d_dense,
+                        cudaStream_t st) {
+  const int n_range = end_col - start_col;
+  // longest-processing-time-first order of the local columns (cached per range)
+  if (h->order_lo != start_col || h->order_hi != end_col) {
+    h->h_order.resize((size_t)n_range);
+    for (int i = 0; i < n_range; ++i) h->h_order[(size_t)i] = i;
+    const unsigned long long* w = h->h_work.data() + start_col;
+    std::stable_sort(h->h_order.begin(), h->h_order.end(), [w](int a, int b) { return w[a] > w[b]; });
+    B200_CUDA(cudaMemcpyAsync(h->order.get(), h->h_order.data(), sizeof(int) * (size_t)n_range, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    h->order_lo = start_col;
+    h->order_hi = end_col;
+  }
+  B200_CUDA(cudaMemsetAsync(h->counter.get(), 0, sizeof(int), st));
+  KParams p;
+  p.n_cols = h->n_cols; p.K = h->K; p.n_win = h->n_win; p.win = h->win; p.cap = h->cap; p.cap_alloc = h->cap_alloc;
+  p.acc_cells = std::max(h->win, SBINS);
+  p.lpu_log2 = h->lpu_log2;
+  p.tileB = h->tileB.get();
+  p.se = h->shrink + 1e-6f;
+  p.shrink_div = h->shrink != 0.f ? h->shrink : 1.f;
+  p.ta = h->ta; p.tb = h->tb;
+  p.csr_ptr = h->csr_ptr.get(); p.csr_ent = h->csr_ent.get(); p.csr_idx = h->csr_idx.get();
+  p.split = h->split.get();
+  p.csc_ptr = h->csc_ptr.get(); p.csc_ent = h->csc_ent.get(); p.csc_idx = h->csc_idx.get();
+  p.A = h->A.get(); p.BN = h->BN.get(); p.old2new = h->old2new.get();
+  p.col_begin = start_col; p.n_range = n_range;
+  p.order = h->order.get();
+  p.counter = h->counter.get();
+  p.out_idx = d_idx; p.out_val = d_val; p.out_cnt = d_cnt;
+  p.signed_data = h->signed_data ? 1 : 0;
+  p.dense_out = d_dense;
+  p.prof = h->prof_on ? h->prof.get() : nullptr;
+  const int grid = std::min(n_range, h->n_sm);
+  B200_CUDA(cudaEventRecord(h->ev0, st));
+  kernel_for(h->formula, h->binary)<<<grid, THREADS, h->smem_bytes, st>>>(p);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaEventRecord(h->ev1, st));
+  h->timed = true;
+  count_launch();
+}
+
 int b200_sim_compute_device(b200_sim_t h, int start_col, int end_col, int32_t* d_idx, float* d_val, int32_t* d_cnt,
                             void* stream) {
   return guarded([&] {
     B200_REQUIRE(h != nullptr, "b200_sim_compute: NULL handle");
     B200_REQUIRE(0 <= start_col && start_col <= end_col && end_col <= h->n_cols, "b200_sim_compute: bad column range [%d,%d)",
                  start_col, end_col);
-    const int n_range = end_col - start_col;
-    if (n_range == 0) return;
+    if (end_col == start_col) return;
     B200_REQUIRE(d_idx && d_val && d_cnt, "b200_sim_compute: NULL output");
+    launch_topk(h, start_col, end_col, d_idx, d_val, d_cnt, nullptr, (cudaStream_t)stream);
+  });
+}
+
+int b200_sim_compute_dense_device(b200_sim_t h, int start_col, int end_col, float* d_out, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr && d_out != nullptr, "b200_sim_compute_dense: NULL argument");
+    B200_REQUIRE(0 <= start_col && start_col <= end_col && end_col <= h->n_cols, "b200_sim_compute_dense: bad column range [%d,%d)",
+                 start_col, end_col);
+    if (end_col == start_col) return;
     cudaStream_t st = (cudaStream_t)stream;
-    // longest-processing-time-first order of the local columns (cached per range)
-    if (h->order_lo != start_col || h->order_hi != end_col) {
-      h->h_order.resize((size_t)n_range);
-      for (int i = 0; i < n_range; ++i) h->h_order[(size_t)i] = i;
-      const unsigned long long* w = h->h_work.data() + start_col;
-      std::stable_sort(h->h_order.begin(), h->h_order.end(), [w](int a, int b) { return w[a] > w[b]; });
-      B200_CUDA(cudaMemcpyAsync(h->order.get(), h->h_order.data(), sizeof(int) * (size_t)n_range, cudaMemcpyHostToDevice, st));
-      B200_CUDA(cudaStreamSynchronize(st));
-      h->order_lo = start_col;
-      h->order_hi = end_col;
-    }
-    B200_CUDA(cudaMemsetAsync(h->counter.get(), 0, sizeof(int), st));
-    KParams p;
-    p.n_cols = h->n_cols; p.K = h->K; p.n_win = h->n_win; p.win = h->win; p.cap = h->cap; p.cap_alloc = h->cap_alloc;
-    p.acc_cells = std::max(h->win, SBINS);
-    p.lpu_log2 = h->lpu_log2;
-    p.tileB = h->tileB.get();
-    p.se = h->shrink + 1e-6f;
-    p.shrink_div = h->shrink != 0.f ? h->shrink : 1.f;
-    p.ta = h->ta; p.tb = h->tb;
-    p.csr_ptr = h->csr_ptr.get(); p.csr_ent = h->csr_ent.get(); p.csr_idx = h->csr_idx.get();
-    p.split = h->split.get();
-    p.csc_ptr = h->csc_ptr.get(); p.csc_ent = h->csc_ent.get(); p.csc_idx = h->csc_idx.get();
-    p.A = h->A.get(); p.BN = h->BN.get(); p.old2new = h->old2new.get();
-    p.col_begin = start_col; p.n_range = n_range;
-    p.order = h->order.get();
-    p.counter = h->counter.get();
-    p.out_idx = d_idx; p.out_val = d_val; p.out_cnt = d_cnt;
-    p.signed_data = h->signed_data ? 1 : 0;
-    p.prof = h->prof_on ? h->prof.get() : nullptr;
-    const int grid = std::min(n_range, h->n_sm);
-    B200_CUDA(cudaEventRecord(h->ev0, st));
-    kernel_for(h->formula, h->binary)<<<grid, THREADS, h->smem_bytes, st>>>(p);
-    B200_CUDA(cudaGetLastError());
-    B200_CUDA(cudaEventRecord(h->ev1, st));
-    h->timed = true;
-    count_launch();
+    B200_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)(end_col - start_col) * (size_t)h->n_cols, st));
+    launch_topk(h, start_col, end_col, nullptr, nullptr, nullptr, d_out, st);
   });
 }
 

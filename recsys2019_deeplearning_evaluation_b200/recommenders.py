@@ -427,3 +427,49 @@ class SLIM_BPR_Cython(BaseItemSimilarityMatrixRecommender, Incremental_Training_
             from .graph import sparse_column_topk
             W = sparse_column_topk(sps.csr_matrix(W, dtype=np.float32), self.topK)
         self.W_sparse = sps.csr_matrix(W, dtype=np.float32)
+
+
+class EASE_R_Recommender(BaseItemSimilarityMatrixRecommender):
+    """EASE_R/EASE_R_Recommender.py:36-106.  Gram through the dense mode of the similarity kernel, SPD inverse through
+    the blocked-Cholesky kernels of csrc/ease.cu; `topK=None` keeps the dense B on the device for scoring."""
+    RECOMMENDER_NAME = "EASE_R_Recommender"
+
+    def fit(self, topK=None, l2_norm=1e3, normalize_matrix=False, verbose=True):
+        import torch
+        from .similarity import Compute_Similarity_Cython
+        self.verbose = verbose
+        if normalize_matrix:  # :47-51, sklearn.normalize l2 on rows then columns
+            X = self.URM_train.astype(np.float64)
+            rn = np.sqrt(np.asarray(X.multiply(X).sum(axis=1)).ravel()); rn[rn == 0] = 1
+            X = sps.diags(1.0 / rn).dot(X)
+            cn = np.sqrt(np.asarray(X.multiply(X).sum(axis=0)).ravel()); cn[cn == 0] = 1
+            self.URM_train = sps.csr_matrix(X.dot(sps.diags(1.0 / cn)), dtype=np.float32)
+            self._d_urm = None
+        n = self.n_items
+        sim = Compute_Similarity_Cython(self.URM_train, shrink=0, topK=n if n > 2048 else 0, normalize=False, similarity="cosine")
+        G = sim.compute_dense_device(0, n)  # symmetric: orientation is irrelevant
+        sim._dealloc()
+        _, d_idx, _ = self._urm_device()
+        B = torch.empty((n, n), dtype=torch.float32, device=G.device)
+        _lib.check(self._lib.b200_ease_from_gram_device(G.data_ptr(), n, d_idx.data_ptr(), self.URM_train.nnz, float(l2_norm), None,
+                                                        B.data_ptr(), _stream()))
+        del G
+        if topK is None:  # :75-78: dense W, scores = URM[users] . W
+            self._d_B = B
+            self.W_sparse = B.cpu().numpy()
+        else:  # :80-82
+            from .slim_bpr_epoch import dense_topk_to_sparse
+            self._d_B = None
+            self.W_sparse = sps.csr_matrix(dense_topk_to_sparse(B, n, topK, along_columns=True, mode=0), dtype=np.float32)
+
+    def _scores_device(self, d_users, items_to_compute=None):
+        if getattr(self, "_d_B", None) is None:
+            return super(EASE_R_Recommender, self)._scores_device(d_users, items_to_compute)
+        import torch
+        n = self.n_items  # dense W (EASE_R_Recommender.py:87-106): out[b, :] = sum over the user's (i, r) of r * B[i, :]
+        a_ptr, a_idx, a_val = self._urm_device()
+        out = torch.empty((d_users.shape[0], n), dtype=torch.float32, device=d_users.device)
+        _lib.check(self._lib.b200_score_spmm_device(d_users.data_ptr(), d_users.shape[0], a_ptr.data_ptr(), a_idx.data_ptr(),
+                                                    a_val.data_ptr(), None, None, self._d_B.data_ptr(), n,
+                                                    out.data_ptr(), _stream()))
+        return out

@@ -72,14 +72,15 @@ class Compute_Similarity_Cython:
         self.TopK = min(topK, self.n_columns)  # pyx:147
         self.shrink = int(shrink)  # `cdef int shrink`, pyx:65: a float shrink is truncated
         self.normalize = bool(normalize)
-        if self.TopK == 0:
-            raise NotImplementedError("TopK == 0 (dense output, pyx:510-513) goes through Compute_Gram_Dense")
+        # TopK == 0 (dense ndarray out, pyx:510-513) and TopK beyond the selection kernel's buffer go through the dense
+        # mode of the kernel; the handle is then created with a token topK
+        self._dense_mode = self.TopK == 0 or self.TopK > 2048
         X = _as_csr_f32(dataMatrix)
         rw = None if row_weights is None else np.ascontiguousarray(row_weights, dtype=np.float32)
         self._keep = (X, rw)  # host arrays stay alive for the duration of the (synchronous) create call
         _lib.check(self._lib.b200_sim_create(
             ctypes.byref(self._h), X.shape[0], X.shape[1], X.nnz, _lib.ptr(X.indptr), _lib.ptr(X.indices),
-            _lib.ptr(X.data), _KIND[similarity], int(self.TopK), float(self.shrink), int(self.normalize),
+            _lib.ptr(X.data), _KIND[similarity], 1 if self._dense_mode else int(self.TopK), float(self.shrink), int(self.normalize),
             float(asymmetric_alpha), float(tversky_alpha), float(tversky_beta), _lib.ptr(rw), None))
         self._keep = None
         k = ctypes.c_int32(); nw = ctypes.c_int32(); wc = ctypes.c_int32(); bp = ctypes.c_int32(); sd = ctypes.c_int32()
@@ -100,8 +101,34 @@ class Compute_Similarity_Cython:
     def compute_similarity(self, start_col=None, end_col=None):
         """pyx:413-611: W_sparse (n_columns x n_columns) CSR float32 holding columns [start_col, end_col)."""
         lo, hi = self._col_range(start_col, end_col)
+        if self._dense_mode:
+            return self._compute_dense(lo, hi)
         tab = self.compute_topk_device(lo, hi)
         return self.table_to_csr(tab)
+
+    def compute_dense_device(self, lo, hi):
+        """[hi - lo, n_columns] float32 CUDA tensor: out[target - lo, neighbour] = W[neighbour, target]."""
+        import torch
+        out = torch.empty((hi - lo, self.n_columns), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        _lib.check(self._lib.b200_sim_compute_dense_device(self._h, lo, hi, out.data_ptr(),
+                                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
+
+    def _compute_dense(self, lo, hi):
+        import torch
+        n = self.n_columns
+        D = self.compute_dense_device(lo, hi)
+        if lo != 0 or hi != n:
+            full = torch.zeros((n, n), dtype=torch.float32, device=D.device)
+            full[lo:hi] = D
+            D = full
+        if self.TopK == 0:  # pyx:597-599: dense float64 ndarray W_dense[neighbour, target]
+            return D.t().contiguous().cpu().numpy().astype(np.float64)
+        if self.TopK >= n:  # every non-zero similarity (EASE_R asks for topK = n_items)
+            return sps.csr_matrix(D.t().contiguous().cpu().numpy())
+        from .slim_bpr_epoch import dense_topk_to_sparse
+        # rows of D are targets: per target keep the TopK largest over all cells, zeros dropped; transpose into W[j, i]
+        return sps.csr_matrix(dense_topk_to_sparse(D, n, self.TopK, along_columns=False, mode=1).T)
 
     # ------------------------------------------------------------------ device-level API (multi-GPU, bench)
     def compute_topk_device(self, lo, hi, stream=None):

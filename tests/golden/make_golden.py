@@ -130,3 +130,23 @@ def make_graph_golden():
 
 if __name__ == "__main__":
     make_graph_golden()
+
+
+def make_ease_golden():
+    """tests/golden/ease_golden.npz: dense B of the reference's EASE_R_Recommender (fp32 LAPACK inverse)."""
+    ref_loader.ensure_import_path()
+    ref_loader.load("Compute_Similarity_Cython")
+    from EASE_R.EASE_R_Recommender import EASE_R_Recommender
+    out = {}
+    for n, (values, l2) in enumerate((("binary", 50.0), ("ratings", 500.0))):
+        X = synth_urm(600, 200, 0.05, seed=23, values=values)
+        r = EASE_R_Recommender(X)
+        r.fit(topK=None, l2_norm=l2, verbose=False)
+        out["ease%d_B" % n] = np.asarray(r.W_sparse, dtype=np.float32)
+        out["ease%d_scores" % n] = np.asarray(r._compute_item_score(np.arange(30)), dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "ease_golden.npz"), **out)
+    print("wrote ease_golden.npz")
+
+
+if __name__ == "__main__":
+    make_ease_golden()
