@@ -235,6 +235,19 @@ int b200_spd_inverse_device(float* d_A, int n_pad, float* d_work, void* stream);
 int b200_ease_from_gram_device(const float* d_G, int n_items, const int32_t* d_urm_indices, int64_t nnz, float l2_norm,
                                float* h_B, float* d_B, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K4: implicit ALS half epoch  (hot path iii)
+ * replaces  MatrixFactorization/IALSRecommender.py:137-201 (_run_epoch user loop or item loop + _update_row)
+ * For every row r in d_rows (the warm users, or the warm items): profile = d_idx[d_ptr[r] .. d_ptr[r+1]),
+ * confidences c = d_conf[...] (the C or C_csc matrix, :99-123), Y = the other side's factors [n_other, f] fp64:
+ *     X[r, :] = (Y^T Y + Y_p^T diag(c - 1) Y_p + reg I)^-1  Y_p^T c
+ * Rows not listed keep their previous contents (cold rows, :143).  d_YtY_work: f * f doubles of scratch.
+ * n_factors <= 208.
+ * ------------------------------------------------------------------------------------------------ */
+int b200_ials_half_epoch_device(const int32_t* d_rows, int n_solve, const int32_t* d_ptr, const int32_t* d_idx,
+                                const float* d_conf, const double* d_Y, int n_other, int n_factors, double reg,
+                                double* d_X, double* d_YtY_work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -473,3 +473,59 @@ class EASE_R_Recommender(BaseItemSimilarityMatrixRecommender):
                                                     a_val.data_ptr(), None, None, self._d_B.data_ptr(), n,
                                                     out.data_ptr(), _stream()))
         return out
+
+
+class IALSRecommender(BaseMatrixFactorizationRecommender, Incremental_Training_Early_Stopping):
+    """MatrixFactorization/IALSRecommender.py:19-213.  Factors live on the device in fp64; one `_run_epoch` is two calls
+    of the per-row normal-equation kernel (csrc/ials.cu).  Initial factors come from numpy's global RNG exactly like
+    :204-210 (seed it before fit() to reproduce a reference run); cold rows keep whatever np.empty gave the reference --
+    here zeros."""
+    RECOMMENDER_NAME = "IALSRecommender"
+    AVAILABLE_CONFIDENCE_SCALING = ["linear", "log"]
+
+    def fit(self, epochs=300, num_factors=20, confidence_scaling="linear", alpha=1.0, epsilon=1.0, reg=1e-3, init_mean=0.0,
+            init_std=0.1, **earlystopping_kwargs):
+        import torch
+        if confidence_scaling not in self.AVAILABLE_CONFIDENCE_SCALING:  # :63-64
+            raise ValueError("Value for 'confidence_scaling' not recognized. Acceptable values are {}, provided was '{}'".format(
+                self.AVAILABLE_CONFIDENCE_SCALING, confidence_scaling))
+        self.num_factors, self.alpha, self.epsilon, self.reg = num_factors, alpha, epsilon, reg
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.ITEM_factors = self.num_factors ** -0.5 * np.random.random_sample((self.n_items, self.num_factors))  # :71-72, :204-207
+        self.USER_factors = np.zeros((self.n_users, self.num_factors))
+        C = self.URM_train.copy()  # :99-123
+        if confidence_scaling == "linear":
+            C.data = (1.0 + alpha * C.data).astype(np.float32)
+        else:
+            C.data = (1.0 + alpha * np.log(1.0 + C.data / epsilon)).astype(np.float32)
+        C_csc = sps.csc_matrix(C, dtype=np.float32)
+        self._d_C = _dev_csr(C)
+        self._d_Ct = (torch.from_numpy(np.ascontiguousarray(C_csc.indptr, np.int32)).to(dev),
+                      torch.from_numpy(np.ascontiguousarray(C_csc.indices, np.int32)).to(dev),
+                      torch.from_numpy(np.ascontiguousarray(C_csc.data, np.float32)).to(dev))
+        self._d_warm_users = torch.from_numpy(np.flatnonzero(np.diff(C.indptr) > 0).astype(np.int32)).to(dev)  # :78-82
+        self._d_warm_items = torch.from_numpy(np.flatnonzero(np.diff(C_csc.indptr) > 0).astype(np.int32)).to(dev)
+        self._d_U = torch.from_numpy(self.USER_factors).to(dev)
+        self._d_V = torch.from_numpy(np.ascontiguousarray(self.ITEM_factors)).to(dev)
+        self._d_work = torch.empty((num_factors, num_factors), dtype=torch.float64, device=dev)
+        self._update_best_model()
+        self._train_with_early_stopping(epochs, algorithm_name=self.RECOMMENDER_NAME, **earlystopping_kwargs)
+        self.USER_factors, self.ITEM_factors = self.USER_factors_best, self.ITEM_factors_best
+
+    def _half(self, rows, csr, Y, X):
+        ptr, idx, conf = csr
+        _lib.check(self._lib.b200_ials_half_epoch_device(rows.data_ptr(), rows.shape[0], ptr.data_ptr(), idx.data_ptr(), conf.data_ptr(),
+                                                         Y.data_ptr(), Y.shape[0], self.num_factors, float(self.reg), X.data_ptr(),
+                                                         self._d_work.data_ptr(), _stream()))
+
+    def _run_epoch(self, num_epoch):  # :137-166
+        self._half(self._d_warm_users, self._d_C, self._d_V, self._d_U)
+        self._half(self._d_warm_items, self._d_Ct, self._d_U, self._d_V)
+
+    def _prepare_model_for_validation(self):
+        self.USER_factors = self._d_U.cpu().numpy()
+        self.ITEM_factors = self._d_V.cpu().numpy()
+
+    def _update_best_model(self):
+        self._prepare_model_for_validation()
+        self.USER_factors_best, self.ITEM_factors_best = self.USER_factors.copy(), self.ITEM_factors.copy()

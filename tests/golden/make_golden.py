@@ -150,3 +150,31 @@ def make_ease_golden():
 
 if __name__ == "__main__":
     make_ease_golden()
+
+
+IALS_CASES = [dict(num_factors=24, confidence_scaling="linear", alpha=2.0, reg=1e-3, values="binary"),
+              dict(num_factors=40, confidence_scaling="log", alpha=5.0, epsilon=0.5, reg=1e-2, values="ratings")]
+
+
+def make_ials_golden():
+    """tests/golden/ials_golden.npz: initial item factors + factors after 2 epochs of the reference's IALSRecommender."""
+    ref_loader.ensure_import_path()
+    from MatrixFactorization.IALSRecommender import IALSRecommender
+    out = {}
+    for n, c in enumerate(IALS_CASES):
+        c = dict(c)
+        X = synth_urm(500, 180, 0.05, seed=29, values=c.pop("values"))
+        X = X[:, :] .tolil(); X[7, :] = 0; X[:, 11] = 0  # a cold user and a cold item
+        X = sps.csr_matrix(X.tocsr(), dtype=np.float32); X.eliminate_zeros()
+        np.random.seed(100 + n)
+        r = IALSRecommender(X)
+        r.fit(epochs=2, **c)
+        np.random.seed(100 + n)
+        out["ials%d_V0" % n] = c["num_factors"] ** -0.5 * np.random.random_sample((180, c["num_factors"]))
+        out["ials%d_U" % n], out["ials%d_V" % n] = r.USER_factors, r.ITEM_factors
+    np.savez_compressed(os.path.join(HERE, "ials_golden.npz"), **out)
+    print("wrote ials_golden.npz")
+
+
+if __name__ == "__main__":
+    make_ials_golden()
