@@ -447,7 +447,7 @@ def main():
     ap.add_argument("--cpu-cols", type=int, default=2000, help="columns in the CPU-baseline slice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bpr", action="store_true", help="skip the BPR-MF samples/sec leg")
-    ap.add_argument("--ref-workers", type=int, default=16)
+    ap.add_argument("--ref-workers", type=int, default=64, help="worker processes of the reference arm (capped by the host core count)")
     ap.add_argument("--ref-slice", type=int, default=250)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
