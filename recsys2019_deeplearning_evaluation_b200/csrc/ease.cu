@@ -10,97 +10,19 @@
 //      panel L21 = A21 inv(L11)^T and trailing update A22 -= L21 L21^T as GEMMs;
 //   2. inverse of the factor block column by block column, one batched GEMM pair per block diagonal;
 //   3. P = Linv^T Linv with the K range of every tile clipped to the non-zero (lower-triangular) part.
-// All three are O(n^3) GEMM work in fp32 (like the reference's fp32 LAPACK).  ROUND-1 STATUS: the GEMM below runs on
-// the CUDA cores (128x128x16 tiles, 8x8 register blocking); the tcgen05 / TMEM version (3xTF32 split to keep the
-// fp32-level accuracy the 1e-4 parity bar needs) is the round-2 item for this kernel -- see DESIGN.md K5.
+// All three are O(n^3) GEMM work and run on the tensor cores: gemm_tc.cuh (tcgen05.mma kind::tf32 with a 3xTF32 operand
+// split for fp32-level accuracy -- the reference inverts in fp32 LAPACK -- accumulators in TMEM).  Only the 128 x 128
+// diagonal-block factorisations stay on the CUDA cores (one CTA each, O(n * NB^2) work in total).
 #include <algorithm>
 #include <vector>
 
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace b200 {
 namespace ease {
 
-constexpr int NB = 128;          // Cholesky block size
-constexpr int BM = 128, BN = 128, BK = 16;
-
-// C = alpha * op(A) * op(B) + beta * C, row-major, all dimensions multiples of the tile sizes.
-// TA: op(A)(m,k) = A[k*lda + m]; TB: op(B)(k,n) = B[n*ldb + k].  blockIdx.z selects a batch entry (strided).
-// TRI: op(A) = Linv^T, op(B) = Linv with Linv lower triangular => the product over k only needs k >= max(m0, n0).
-template <bool TA, bool TB, bool TRI>
-__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
-                                                    long long strideA, const float* __restrict__ B, int ldb, long long strideB,
-                                                    float beta, float* C, int ldc, long long strideC) {
-  __shared__ float As[2][BK][BM + 4];
-  __shared__ float Bs[2][BK][BN + 4];
-  A += (long long)blockIdx.z * strideA;
-  B += (long long)blockIdx.z * strideB;
-  C += (long long)blockIdx.z * strideC;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads, each an 8 x 8 micro-tile
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const int k_begin = TRI ? (max(m0, n0) / BK) * BK : 0;
-
-  auto load_tiles = [&](int buf, int k0) {
-    // A tile: BM x BK elements -> As[k][m]; 2048 elements / 256 threads = 8 each
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int idx = tid + e * 256;
-      if (TA) {  // op(A)(m,k) = A[(k0+k)*lda + m0+m]: m fastest
-        const int m = idx % BM, k = idx / BM;
-        As[buf][k][m] = A[(long long)(k0 + k) * lda + m0 + m];
-      } else {   // A[(m0+m)*lda + k0+k]: k fastest
-        const int k = idx % BK, m = idx / BK;
-        As[buf][k][m] = A[(long long)(m0 + m) * lda + k0 + k];
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int idx = tid + e * 256;
-      if (TB) {  // op(B)(k,n) = B[(n0+n)*ldb + k0+k]: k fastest
-        const int k = idx % BK, n = idx / BK;
-        Bs[buf][k][n] = B[(long long)(n0 + n) * ldb + k0 + k];
-      } else {   // B[(k0+k)*ldb + n0+n]: n fastest
-        const int n = idx % BN, k = idx / BN;
-        Bs[buf][k][n] = B[(long long)(k0 + k) * ldb + n0 + n];
-      }
-    }
-  };
-
-  if (k_begin < K) {
-    load_tiles(0, k_begin);
-    __syncthreads();
-    int buf = 0;
-    for (int k0 = k_begin; k0 < K; k0 += BK) {
-      if (k0 + BK < K) load_tiles(buf ^ 1, k0 + BK);
-#pragma unroll
-      for (int k = 0; k < BK; ++k) {
-        float a[8], b[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = As[buf][k][ty * 8 + i];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = Bs[buf][k][tx * 8 + j];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] += a[i] * b[j];
-      }
-      __syncthreads();
-      buf ^= 1;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float* crow = C + (long long)(m0 + ty * 8 + i) * ldc + n0 + tx * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) crow[j] = alpha * acc[i][j] + (beta != 0.f ? beta * crow[j] : 0.f);
-  }
-}
+constexpr int NB = 128;  // Cholesky block size == GEMM tile size
 
 // Cholesky of the NB x NB diagonal block at A (row-major, lda) in place (lower triangle; the strict upper triangle is
 // zeroed) and its inverse into Inv (NB x NB, dense row-major, upper part zero).  One CTA, the block lives in smem.
@@ -174,7 +96,13 @@ template <bool TA, bool TB, bool TRI>
 void gemm(cudaStream_t st, int M, int N, int K, float alpha, const float* A, int lda, long long sA, const float* B, int ldb,
           long long sB, float beta, float* C, int ldc, long long sC, int batch) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
-  sgemm_kernel<TA, TB, TRI><<<dim3(N / BN, M / BM, batch), 256, 0, st>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC);
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(tc::tc_gemm_kernel<TA, TB, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    configured = true;
+  }
+  tc::tc_gemm_kernel<TA, TB, TRI><<<dim3(N / tc::BN, M / tc::BM, batch), tc::THREADS, tc::SMEM_BYTES, st>>>(
+      M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC);
   count_launch();
 }
 
