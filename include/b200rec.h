@@ -146,6 +146,10 @@ int b200_mf_create(b200_mf_t* out, int64_t n_users, int64_t n_items, int64_t nnz
 int b200_mf_destroy(b200_mf_t h);
 /* epochIteration_Cython() (pyx:276-286): (n_users or nnz)/batch_size + 1 mini-batches */
 int b200_mf_epoch(b200_mf_t h, void* stream);
+/* multi-GPU data parallelism: this rank's device sampler draws users from [user_lo, user_hi) only (so user rows are
+ * never shared between ranks) and an epoch consumes samples_per_epoch samples (0 = the reference's epoch length); stream_id (the rank)
+ * selects a distinct Philox stream */
+int b200_mf_set_user_shard(b200_mf_t h, int user_lo, int user_hi, int64_t samples_per_epoch, uint32_t stream_id);
 int b200_mf_samples_last_epoch(b200_mf_t h, int64_t* n);
 /* the (user, item, neg item | rating) stream the last epoch consumed (for replaying it through the oracle) */
 int b200_mf_get_samples(b200_mf_t h, int32_t* u, int32_t* i, int32_t* j, float* r);

@@ -44,6 +44,7 @@ SIGNATURES = {
                                       ctypes.c_int, ctypes.c_int]),
     "b200_mf_destroy": (ctypes.c_int, [c_void]),
     "b200_mf_epoch": (ctypes.c_int, [c_void, c_void]),
+    "b200_mf_set_user_shard": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32]),
     "b200_mf_samples_last_epoch": (ctypes.c_int, [c_void, c_i64_p]),
     "b200_mf_get_samples": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_void]),
     "b200_mf_get_factors": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_void, c_void]),

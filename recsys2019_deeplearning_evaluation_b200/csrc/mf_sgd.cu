@@ -350,14 +350,14 @@ struct Draws {
 // same acceptance rules as sampleBPR_Cython / sampleMSE_Cython (users with 0 < profile < n_items; negative item
 // not in the sorted profile, binary search instead of the linear scan), different random stream
 __global__ void mf_sample_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ data,
-                                 int n_users, int n_items, int algorithm, float quota, long long n_samples, unsigned seed,
+                                 int user_lo, int n_users, int n_items, int algorithm, float quota, long long n_samples, unsigned seed,
                                  unsigned epoch, int* su, int* si, int* sj, float* sr) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_samples) return;
   Draws d((unsigned long long)g, seed, epoch);
   int u, s, n;
   do {
-    u = (int)(d.next() % (unsigned)n_users);
+    u = user_lo + (int)(d.next() % (unsigned)n_users);  // n_users = size of this rank's user shard
     s = indptr[u];
     n = indptr[u + 1] - s;
   } while (n == 0 || n == n_items);
@@ -436,7 +436,8 @@ struct b200_mf_s {
   DevBuf<double> pow_out;
   std::vector<int> hs_u, hs_i, hs_j;
   std::vector<float> hs_r;
-  long long samples_last = 0, cap_samples = 0;
+  long long samples_last = 0, cap_samples = 0, epoch_samples_override = 0;
+  int shard_lo = 0, shard_hi = 0;  // device sampler draws users from [shard_lo, shard_hi) when set (multi-GPU user sharding)
   int grid = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -602,6 +603,7 @@ int b200_mf_epoch(b200_mf_t h, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     Params& p = h->p;
     p.n_batches = epoch_batches(h);
+    if (h->epoch_samples_override > 0) p.n_batches = std::max<long long>(1, h->epoch_samples_override / p.batch_size);
     const long long n = p.n_batches * p.batch_size;
     if (h->sampler == 0) {
       host_samples(h, n);
@@ -612,7 +614,8 @@ int b200_mf_epoch(b200_mf_t h, void* stream) {
     }
     B200_CUDA(cudaEventRecord(h->ev0, st));
     if (h->sampler != 0) {
-      mf_sample_kernel<<<div_up(n, 256), 256, 0, st>>>(h->d_indptr.get(), h->d_indices.get(), h->d_data.get(), p.n_users, p.n_items,
+      mf_sample_kernel<<<div_up(n, 256), 256, 0, st>>>(h->d_indptr.get(), h->d_indices.get(), h->d_data.get(), h->shard_lo,
+                                                      (h->shard_hi > h->shard_lo ? h->shard_hi - h->shard_lo : p.n_users), p.n_items,
                                                       p.algorithm, h->quota, n, h->seed, h->epoch, h->su.get(), h->si.get(),
                                                       h->sj.get(), h->sr.get());
       count_launch();
@@ -643,6 +646,19 @@ int b200_mf_epoch(b200_mf_t h, void* stream) {
     }
     h->samples_last = n;
     h->epoch += 1;
+  });
+}
+
+int b200_mf_set_user_shard(b200_mf_t h, int user_lo, int user_hi, int64_t samples_per_epoch, uint32_t stream_id) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr, "b200_mf_set_user_shard: NULL handle");
+    B200_REQUIRE(h->sampler != 0, "b200_mf_set_user_shard: only the device (Philox) sampler can be sharded");
+    B200_REQUIRE(0 <= user_lo && user_lo < user_hi && user_hi <= h->p.n_users, "b200_mf_set_user_shard: bad range [%d,%d)", user_lo, user_hi);
+    B200_REQUIRE(samples_per_epoch >= 0 && samples_per_epoch <= h->cap_samples, "b200_mf_set_user_shard: samples_per_epoch out of range");
+    h->shard_lo = user_lo;
+    h->shard_hi = user_hi;
+    h->epoch_samples_override = samples_per_epoch;
+    h->seed += 0x9E3779B9u * stream_id;  // decorrelates the ranks' Philox streams
   });
 }
 

@@ -71,3 +71,54 @@ def compute_similarity_sharded(sim, group=None, assemble=True):
     if not assemble:
         return g_idx, g_val, g_cnt
     return topk_table_to_csr(sim.n_columns, sim.K, g_idx.contiguous(), g_val.contiguous(), g_cnt.contiguous())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K2 data parallelism: user-sharded Hogwild BPR-MF with a replicated item-factor table.
+# Rank r draws its samples from users [lo_r, hi_r) only, so user rows are private; the item factors are replicated and
+# after every epoch the ranks' item-factor DELTAS are summed over NCCL:  V <- V_prev + sum_r (V_r - V_prev)
+# (every rank's updates count once, the Hogwild reading of "all updates are applied").
+
+def sync_replicated_delta(V, V_prev, group=None):
+    """In place: V <- V_prev + all_reduce_sum(V - V_prev); V_prev <- V.  Works on CPU tensors (gloo) and CUDA (NCCL)."""
+    import torch.distributed as dist
+    delta = V - V_prev
+    dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
+    V.copy_(V_prev + delta)
+    V_prev.copy_(V)
+    return V
+
+
+class ShardedBPR:
+    """One rank of a user-sharded Hogwild BPR-MF run (MatrixFactorization_Cython_Epoch semantics per sample)."""
+
+    def __init__(self, URM, group=None, **mf_kwargs):
+        import torch.distributed as dist
+        from .mf_epoch import MatrixFactorization_Cython_Epoch
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n_users = URM.shape[0]
+        bounds = balanced_ranges(np.diff(URM.indptr), self.world)  # equal interaction mass per rank
+        self.lo, self.hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
+        mf_kwargs.setdefault("algorithm_name", "MF_BPR")
+        mf_kwargs.update(sampler="philox", hogwild=True)
+        self.epoch_obj = MatrixFactorization_Cython_Epoch(URM, **mf_kwargs)  # same seed -> identical initial factors on every rank
+        bs = self.epoch_obj.batch_size
+        total = (n_users // bs + 1) * bs  # the reference's epoch length, split over the ranks
+        self.samples_per_rank = max(bs, (total // self.world // bs) * bs)
+        self.epoch_obj.set_user_shard(self.lo, self.hi, self.samples_per_rank, stream_id=self.rank)
+        self.U, self.V = self.epoch_obj.device_factors()
+        self.V_prev = self.V.clone()
+        self.U0 = self.U.clone()
+
+    def epoch(self):
+        self.epoch_obj.epochIteration_Cython()
+        sync_replicated_delta(self.V, self.V_prev, self.group)
+        return self.samples_per_rank * self.world
+
+    def gather_user_factors(self):
+        """Every rank ends with the full user-factor table (rows outside a rank's shard never moved there)."""
+        import torch.distributed as dist
+        delta = self.U - self.U0
+        dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.group)
+        return self.U0 + delta

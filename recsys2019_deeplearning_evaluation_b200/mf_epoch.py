@@ -72,6 +72,24 @@ class MatrixFactorization_Cython_Epoch:
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(self._lib.b200_mf_epoch(self._h, st))
 
+    def set_user_shard(self, user_lo, user_hi, samples_per_epoch=0, stream_id=0):
+        _lib.check(self._lib.b200_mf_set_user_shard(self._h, int(user_lo), int(user_hi), int(samples_per_epoch), int(stream_id)))
+
+    def device_factors(self):
+        """(USER_factors, ITEM_factors) as torch CUDA float32 tensors that ALIAS the trainer's device memory."""
+        import torch
+        pu, pv = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(self._lib.b200_mf_device_factors(self._h, ctypes.byref(pu), ctypes.byref(pv)))
+
+        class _Arr:
+            def __init__(s, ptr, shape):
+                s.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        U = torch.as_tensor(_Arr(pu.value, (self.n_users, self.n_factors)), device=dev)
+        V = torch.as_tensor(_Arr(pv.value, (self.n_items, self.n_factors)), device=dev)
+        return U, V
+
     def samples_last_epoch(self):
         n = ctypes.c_int64()
         _lib.check(self._lib.b200_mf_samples_last_epoch(self._h, ctypes.byref(n)))

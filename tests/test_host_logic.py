@@ -78,3 +78,38 @@ def test_allgather_topk_tables_gloo_world2(sizes):
     for rank, gi, gv, gc in res:
         assert gi.shape == (n, K) and (gi == want_idx).all()
         assert np.allclose(gv, want_idx * 0.5) and (gc == want_cnt).all()
+
+
+def _delta_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from recsys2019_deeplearning_evaluation_b200.dist import sync_replicated_delta
+    V_prev = torch.arange(12, dtype=torch.float32).reshape(4, 3)
+    V = V_prev.clone()
+    V[rank] += 1.0 + rank          # each rank moved a different row ...
+    V[3] += 0.5                    # ... and both moved row 3
+    sync_replicated_delta(V, V_prev)
+    q.put((rank, V.numpy().copy(), V_prev.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_sync_replicated_delta_gloo_world2():
+    """K2 data parallelism: V <- V_prev + sum_r (V_r - V_prev) on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_delta_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.arange(12, dtype=np.float32).reshape(4, 3)
+    want[0] += 1.0; want[1] += 2.0; want[3] += 1.0
+    for rank, V, Vp in res:
+        assert np.allclose(V, want) and np.allclose(Vp, want)
