@@ -35,6 +35,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Everything any library writes to stdout (NCCL prints its version banner there) is diverted to stderr; the ONE JSON
+# line goes to the original stdout through emit_json().
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 # ----------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
@@ -163,7 +173,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": e2e_rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores": cores,
     }
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 def _ref_worker(conn, X, kind, w):
@@ -384,7 +394,7 @@ def run_b200(args, rank, world, local_rank):
         "secondary": secondary,
         "device": name,
     }
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 def bpr_leg_sharded(args, X, rank, world):
