@@ -26,6 +26,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -51,7 +53,7 @@ enum Formula { F_PROD = 0, F_NONORM = 1, F_JACCARD = 2, F_DICE = 3, F_TVERSKY = 
 
 struct KParams {
   int n_cols, K, n_win, win, cap, cap_alloc;  // cap <= cap_alloc (a smaller logical cap is a test hook)
-  int acc_cells;     // accumulator cells allocated: max(win, SBINS), the cleared window doubles as select scratch
+  int acc_cells;     // 4-byte accumulator words allocated (>= SBINS: the cleared window doubles as select scratch)
   int lpu_log2;      // lanes that share one row segment in the accumulate phase (2^lpu_log2, 2..32)
   float se;          // shrink + 1e-6
   float shrink_div;  // shrink if != 0 else 1
@@ -286,9 +288,43 @@ __device__ __forceinline__ u64 block_select(u64* buf, int n, int K, Shared* sh, 
   return sh->sel_thr;
 }
 
-template <int F, bool BINARY, bool NEG>
+// cells of one 16-byte vector of the accumulator window as floats: 4 fp32 / int32 cells, or 8 packed 16-bit counters
+template <bool BINARY, bool PACK>
+__device__ __forceinline__ bool load_cells(const void* acc, int iv, float* d) {
+  if (PACK) {
+    const int4 v = reinterpret_cast<const int4*>(acc)[iv];
+    if ((v.x | v.y | v.z | v.w) == 0) return false;
+    d[0] = (float)(v.x & 0xFFFF); d[1] = (float)((unsigned)v.x >> 16); d[2] = (float)(v.y & 0xFFFF); d[3] = (float)((unsigned)v.y >> 16);
+    d[4] = (float)(v.z & 0xFFFF); d[5] = (float)((unsigned)v.z >> 16); d[6] = (float)(v.w & 0xFFFF); d[7] = (float)((unsigned)v.w >> 16);
+    return true;
+  } else if (BINARY) {
+    const int4 v = reinterpret_cast<const int4*>(acc)[iv];
+    if ((v.x | v.y | v.z | v.w) == 0) return false;
+    d[0] = (float)v.x; d[1] = (float)v.y; d[2] = (float)v.z; d[3] = (float)v.w;
+    return true;
+  } else {
+    const float4 v = reinterpret_cast<const float4*>(acc)[iv];
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return false;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    return true;
+  }
+}
+
+template <bool BINARY, bool PACK>
+__device__ __forceinline__ void store_cells(void* acc, int iv, const float* k) {
+  if (PACK) {
+    reinterpret_cast<int4*>(acc)[iv] = make_int4((int)k[0] | ((int)k[1] << 16), (int)k[2] | ((int)k[3] << 16),
+                                                 (int)k[4] | ((int)k[5] << 16), (int)k[6] | ((int)k[7] << 16));
+  } else if (BINARY) {
+    reinterpret_cast<int4*>(acc)[iv] = make_int4((int)k[0], (int)k[1], (int)k[2], (int)k[3]);
+  } else {
+    reinterpret_cast<float4*>(acc)[iv] = make_float4(k[0], k[1], k[2], k[3]);
+  }
+}
+
+template <int F, bool BINARY, bool PACK, bool NEG>
 __device__ void process_column(const KParams& p, int col, int target, int out_base, unsigned char* smem_raw,
-                               Shared* sh, const float* s_tileB, int* n_emitted) {
+                               Shared* sh, const float* s_tileB, int* n_emitted, float* guess) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* accf = reinterpret_cast<float*>(smem_raw);
   int* acci = reinterpret_cast<int*>(smem_raw);
@@ -319,11 +355,13 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
   for (int w = 0; w < p.n_win; ++w) {
     const int win_lo = w * p.win;
     const int win_n = min(p.win, p.n_cols - win_lo);
-    const int win4 = (win_n + 3) >> 2;
-    const int ntiles = (win4 + THREADS - 1) / THREADS;
+    constexpr int CPV = PACK ? 8 : 4;  // cells per 16-byte vector
+    const int winv = (win_n + CPV - 1) / CPV;
+    const int ntiles = (winv + THREADS - 1) / THREADS;
     const float* tB = s_tileB + w * (MAXTILES + 1);
     int* accw_i = acci - win_lo;
     float* accw_f = accf - win_lo;
+    unsigned* accw_u = reinterpret_cast<unsigned*>(acci) - (win_lo >> 1);  // packed: cell j lives in word j >> 1
 
     // ---------------- accumulate: acc[j - win_lo] += x_ui * x_uj over users u of column `col`
     for (int k0 = cs; k0 < ce; k0 += colchunk) {
@@ -393,11 +431,17 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
               const int jj[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
               if (g >= s[k] && g + 4 <= e[k]) {  // interior chunk: no bounds checks
 #pragma unroll
-                for (int c = 0; c < 4; ++c) atomicAdd(&accw_i[jj[c]], 1);
+                for (int c = 0; c < 4; ++c) {
+                  if (PACK) atomicAdd(&accw_u[jj[c] >> 1], (jj[c] & 1) ? 65536u : 1u);
+                  else atomicAdd(&accw_i[jj[c]], 1);
+                }
               } else {
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                  if (g + c >= s[k] && g + c < e[k]) atomicAdd(&accw_i[jj[c]], 1);
+                  if (g + c >= s[k] && g + c < e[k]) {
+                    if (PACK) atomicAdd(&accw_u[jj[c] >> 1], (jj[c] & 1) ? 65536u : 1u);
+                    else atomicAdd(&accw_i[jj[c]], 1);
+                  }
               }
             } else {
               if (g >= s[k] && g < e[k]) atomicAdd(&accw_f[v[k].x], x[k] * __int_as_float(v[k].y));
@@ -408,44 +452,70 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
       }
     }
     __syncthreads();
-    if (tid == 0 && col >= win_lo && col < win_lo + win_n) acci[col - win_lo] = 0;  // pyx:396
+    if (tid == 0 && col >= win_lo && col < win_lo + win_n) {  // pyx:396
+      const int c = col - win_lo;
+      if (PACK) acci[c >> 1] &= (c & 1) ? 0x0000FFFF : (int)0xFFFF0000; else acci[c] = 0;
+    }
     __syncthreads();
     PROF_MARK(1);
     if (p.dense_out) {
       // dense mode (pyx:510-513): every non-zero cell is normalised and written out, no selection
       float* orow = p.dense_out + (size_t)out_base * p.n_cols;  // out_base = local target index here
       for (int c = tid; c < win_n; c += THREADS) {
-        const float d = BINARY ? (float)acci[c] : accf[c];
+        const float d = PACK ? (float)(((unsigned)acci[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu) : (BINARY ? (float)acci[c] : accf[c]);
         if (d != 0.f) {
           const int2 bn = __ldg(p.BN + win_lo + c);
           orow[bn.y] = sim_value<F>(p, d, Ai, __int_as_float(bn.x));
-          acci[c] = 0;
         }
       }
+      __syncthreads();
+      for (int iv = tid; iv < winv; iv += THREADS) reinterpret_cast<int4*>(acci)[iv] = make_int4(0, 0, 0, 0);
       __syncthreads();
       continue;
     }
 
-    // ---------------- bootstrap: floor of the target-th best similarity from per-cell lower bounds
+    // ---------------- packed binary path: try the previous column's floor first.  A cell with d * lbs[tile] >= g is
+    // guaranteed a similarity >= g, so if at least `target` cells pass that integer test g is a valid floor and the
+    // histogram below is skipped (one cheap SIMD-compare pass instead of an atomic per non-zero cell).
     nbuf = sh->nbuf;
+    if (PACK && !NEG && thr == 0 && nbuf == 0 && win_n > 2 * target && *guess > 0.f) {
+      const float g = *guess * 0.8f;
+      if (tid == 0) sh->cnt = 0;
+      if (tid < ntiles) {
+        const float sc = lower_bound_scale<F>(p, Ai, tB[tid], tB[tid + 1]);
+        sh->lbs[tid] = sc;
+        sh->dthr[tid] = sc > 0.f ? fminf(ceilf(g / sc), 65535.f) : 65535.f;
+      }
+      __syncthreads();
+      int c = 0;
+      for (int iv = tid; iv < winv; iv += THREADS) {
+        const int4 v = reinterpret_cast<const int4*>(acci)[iv];
+        if ((v.x | v.y | v.z | v.w) == 0) continue;
+        const unsigned it = (unsigned)sh->dthr[iv / THREADS];
+        const unsigned t2 = it | (it << 16);
+        c += __popc(__vcmpgeu2((unsigned)v.x, t2)) + __popc(__vcmpgeu2((unsigned)v.y, t2)) + __popc(__vcmpgeu2((unsigned)v.z, t2)) +
+             __popc(__vcmpgeu2((unsigned)v.w, t2));
+      }
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0 && c) atomicAdd(&sh->cnt, c);
+      __syncthreads();
+      const int passed = sh->cnt >> 4;  // 16 mask bits per passing half-word
+      if (passed >= target && passed <= p.cap / 2) thr = ((u64)__float_as_uint(g)) << 32;
+      __syncthreads();
+    }
+
+    // ---------------- bootstrap: floor of the target-th best similarity from per-cell lower bounds
     if (!NEG && thr == 0 && nbuf == 0 && win_n > 2 * target) {
       for (int i = tid; i < HBINS; i += THREADS) hist[i] = 0;
       if (tid == 0) sh->b0 = -1;
       if (tid < ntiles) sh->lbs[tid] = lower_bound_scale<F>(p, Ai, tB[tid], tB[tid + 1]);
       __syncthreads();
-      for (int i4 = tid; i4 < win4; i4 += THREADS) {
-        const float sc = sh->lbs[i4 / THREADS];
-        float d[4];
-        if (BINARY) {
-          const int4 v = reinterpret_cast<const int4*>(acci)[i4];
-          if ((v.x | v.y | v.z | v.w) == 0) continue;
-          d[0] = (float)v.x; d[1] = (float)v.y; d[2] = (float)v.z; d[3] = (float)v.w;
-        } else {
-          const float4 v = reinterpret_cast<const float4*>(accf)[i4];
-          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
+      for (int iv = tid; iv < winv; iv += THREADS) {
+        const float sc = sh->lbs[iv / THREADS];
+        float d[CPV];
+        if (!load_cells<BINARY, PACK>(acci, iv, d)) continue;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPV; ++c) {
           const float lb = d[c] * sc;
           if (lb > 0.f) atomicAdd(&hist[min(__float_as_uint(lb) >> 19, (unsigned)(HBINS - 1))], 1);
         }
@@ -479,40 +549,41 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
       int cpos = 0, cneg = 0;
       const bool count_signs = !NEG && first && p.signed_data;
       __syncthreads();
-      for (int i4 = tid; i4 < win4; i4 += THREADS) {
-        const float dthr = sh->dthr[i4 / THREADS];
-        float d[4];
-        if (BINARY) {
-          const int4 v = reinterpret_cast<const int4*>(acci)[i4];
+      for (int iv = tid; iv < winv; iv += THREADS) {
+        const float dthr = sh->dthr[iv / THREADS];
+        if (PACK && !NEG) {  // counts are non-negative integers: test all 8 against ceil(dthr) with two-lane SIMD compares
+          const int4 v = reinterpret_cast<const int4*>(acci)[iv];
           if ((v.x | v.y | v.z | v.w) == 0) continue;
-          d[0] = (float)v.x; d[1] = (float)v.y; d[2] = (float)v.z; d[3] = (float)v.w;
-        } else {
-          const float4 v = reinterpret_cast<const float4*>(accf)[i4];
-          if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
-          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+          const unsigned it = dthr <= 1.f ? 1u : (unsigned)fminf(ceilf(dthr), 65535.f);
+          const unsigned t2 = it | (it << 16);
+          if ((__vcmpgeu2((unsigned)v.x, t2) | __vcmpgeu2((unsigned)v.y, t2) | __vcmpgeu2((unsigned)v.z, t2) | __vcmpgeu2((unsigned)v.w, t2)) == 0u) {
+            reinterpret_cast<int4*>(acci)[iv] = make_int4(0, 0, 0, 0);
+            continue;
+          }
         }
+        float d[CPV];
+        if (!load_cells<BINARY, PACK>(acci, iv, d)) continue;
         if (count_signs) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { cpos += d[c] > 0.f; cneg += d[c] < 0.f; }
+          for (int c = 0; c < CPV; ++c) { cpos += d[c] > 0.f; cneg += d[c] < 0.f; }
         }
-        float keepv[4] = {0.f, 0.f, 0.f, 0.f};
-        const float dmax = NEG ? -fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) : fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3]));
+        float keepv[CPV];
+        float dmax = NEG ? -d[0] : d[0];
+#pragma unroll
+        for (int c = 0; c < CPV; ++c) { keepv[c] = 0.f; dmax = fmaxf(dmax, NEG ? -d[c] : d[c]); }
         if (dmax > 0.f && dmax >= dthr) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < CPV; ++c) {
             const float dd = d[c];
             if (NEG ? (dd < 0.f) : (dd > 0.f && dd >= dthr)) {
               const int pos = atomicAdd(&sh->nbuf, 1);
               if (pos < p.cap)
-                buf[pos] = (((u64)__float_as_uint(dd)) << 32) | (u64)(unsigned)(win_lo + i4 * 4 + c);
+                buf[pos] = (((u64)__float_as_uint(dd)) << 32) | (u64)(unsigned)(win_lo + iv * CPV + c);
               else { sh->overflow = 1; keepv[c] = dd; }
             }
           }
         }
-        if (BINARY)
-          reinterpret_cast<int4*>(acci)[i4] = make_int4((int)keepv[0], (int)keepv[1], (int)keepv[2], (int)keepv[3]);
-        else
-          reinterpret_cast<float4*>(accf)[i4] = make_float4(keepv[0], keepv[1], keepv[2], keepv[3]);
+        store_cells<BINARY, PACK>(acci, iv, keepv);
       }
       if (count_signs) {
 #pragma unroll
@@ -560,6 +631,7 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
     PROF_MARK(5);
   }
 
+  if (PACK && !NEG && thr) *guess = __uint_as_float((unsigned)(thr >> 32));
   // ---------------- emit (keys carry the ORIGINAL neighbour index; the last select left no dead slots)
   for (int t = tid; t < nbuf; t += THREADS) {
     const u64 k = buf[t];
@@ -572,7 +644,7 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
   PROF_MARK(6);
 }
 
-template <int F, bool BINARY>
+template <int F, bool BINARY, bool PACK>
 __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Shared sh;
@@ -586,6 +658,7 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     for (int i = tid; i < p.n_win * (MAXTILES + 1); i += THREADS) s_tileB[i] = p.tileB[i];
   }
   __syncthreads();
+  float guess = 0.f;  // floor of the previous column's K-th similarity (packed binary path)
   while (true) {
     if (tid == 0) sh.col = atomicAdd(p.counter, 1);
     __syncthreads();
@@ -596,11 +669,11 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     const int out_base_row = lc;
     int n_out = 0;
     if (p.dense_out) {
-      process_column<F, BINARY, false>(p, col, p.K, out_base_row, smem_raw, &sh, s_tileB, &n_out);
+      process_column<F, BINARY, PACK, false>(p, col, p.K, out_base_row, smem_raw, &sh, s_tileB, &n_out, &guess);
       __syncthreads();
       continue;
     }
-    process_column<F, BINARY, false>(p, col, p.K, out_base_row * p.K, smem_raw, &sh, s_tileB, &n_out);
+    process_column<F, BINARY, PACK, false>(p, col, p.K, out_base_row * p.K, smem_raw, &sh, s_tileB, &n_out, &guess);
     if (p.signed_data && n_out < p.K) {
       // zeros outrank negatives (Compute_Similarity_Python.py:335-345): negatives are only emitted when the
       // positives plus the implicit zeros (every column without a non-zero similarity, the diagonal
@@ -611,7 +684,7 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
       __syncthreads();
       if (m > 0 && nneg > 0) {
         int n_neg_out = 0;
-        process_column<F, BINARY, true>(p, col, m, out_base_row * p.K + n_out, smem_raw, &sh, s_tileB, &n_neg_out);
+        process_column<F, BINARY, PACK, true>(p, col, m, out_base_row * p.K + n_out, smem_raw, &sh, s_tileB, &n_neg_out, &guess);
         n_out += n_neg_out;
       }
     }
@@ -625,12 +698,12 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
 }
 
 // B at the tile boundaries of every window: tileB[w][t] = B[min(w*win + t*TILE, last column of window w)]
-__global__ void tile_bounds_kernel(const int2* __restrict__ BN, int n_cols, int n_win, int win, float* tileB) {
+__global__ void tile_bounds_kernel(const int2* __restrict__ BN, int n_cols, int n_win, int win, int tile, float* tileB) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_win * (MAXTILES + 1)) return;
   const int w = g / (MAXTILES + 1), t = g % (MAXTILES + 1);
   const int win_lo = w * win, win_n = min(win, n_cols - win_lo);
-  const int j = min(win_lo + t * TILE, win_lo + win_n - 1);
+  const int j = min(win_lo + t * tile, win_lo + win_n - 1);
   tileB[g] = __int_as_float(BN[j].x);
 }
 
@@ -811,6 +884,9 @@ struct b200_sim_s {
   float shrink = 0.f, asym_alpha = 0.5f, ta = 1.f, tb = 1.f;
   int formula = F_PROD;
   bool binary = false, signed_data = false;
+  bool pack = false;               // binary path with 16-bit counters (two cells per accumulator word)
+  bool allow_pack = true;
+  int acc_words = 0;               // 4-byte words allocated for the accumulator window
   bool scaled = false;             // P3alpha / RP3beta product: CSC values are 1, A and B come from the caller
   const float* h_A = nullptr;
   const float* h_B = nullptr;
@@ -836,14 +912,20 @@ namespace {
 constexpr int GRID1D = 148 * 8;
 
 typedef void (*sim_kernel_t)(const KParams);
-sim_kernel_t kernel_for(int formula, bool binary) {
+template <int F>
+sim_kernel_t kernel_of(bool binary, bool pack) {
+  if (binary && pack) return sim_topk_kernel<F, true, true>;
+  if (binary) return sim_topk_kernel<F, true, false>;
+  return sim_topk_kernel<F, false, false>;
+}
+sim_kernel_t kernel_for(int formula, bool binary, bool pack) {
   switch (formula) {
-    case F_PROD: return binary ? sim_topk_kernel<F_PROD, true> : sim_topk_kernel<F_PROD, false>;
-    case F_NONORM: return binary ? sim_topk_kernel<F_NONORM, true> : sim_topk_kernel<F_NONORM, false>;
-    case F_JACCARD: return binary ? sim_topk_kernel<F_JACCARD, true> : sim_topk_kernel<F_JACCARD, false>;
-    case F_DICE: return binary ? sim_topk_kernel<F_DICE, true> : sim_topk_kernel<F_DICE, false>;
-    case F_SCALE: return sim_topk_kernel<F_SCALE, false>;
-    default: return binary ? sim_topk_kernel<F_TVERSKY, true> : sim_topk_kernel<F_TVERSKY, false>;
+    case F_PROD: return kernel_of<F_PROD>(binary, pack);
+    case F_NONORM: return kernel_of<F_NONORM>(binary, pack);
+    case F_JACCARD: return kernel_of<F_JACCARD>(binary, pack);
+    case F_DICE: return kernel_of<F_DICE>(binary, pack);
+    case F_SCALE: return sim_topk_kernel<F_SCALE, false, false>;
+    default: return kernel_of<F_TVERSKY>(binary, pack);
   }
 }
 
@@ -1004,24 +1086,44 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   h->cap = cap;
   h->cap_alloc = cap;
   const size_t staging = (size_t)STAGE_INTS * 4;
-  int n_win = 1;
-  long long max_cells = 0;
-  for (;; ++n_win) {  // the tile-bound table grows with the window count
-    const size_t fixed = (size_t)cap * 8 + staging + (size_t)n_win * (MAXTILES + 1) * 4 + sizeof(Shared) + 1024;
-    max_cells = ((long long)max_smem - (long long)fixed) / 4;
-    max_cells = std::min<long long>(max_cells, (long long)MAXTILES * TILE);
-    B200_REQUIRE(max_cells >= 4096, "not enough shared memory (%d bytes) for the similarity kernel", max_smem);
-    if ((long long)n_win * max_cells >= n_cols) break;
+  // binary path: counts fit 16 bits when no column holds 65536 entries (a dot product is at most the shorter column)
+  {
+    std::vector<int> hcnt((size_t)n_cols);
+    B200_CUDA(cudaMemcpy(hcnt.data(), cnt_new.get(), sizeof(int) * (size_t)n_cols, cudaMemcpyDeviceToHost));
+    int mx = 0;
+    for (int j = 0; j < n_cols; ++j) mx = std::max(mx, hcnt[(size_t)j]);
+    h->pack = h->binary && mx < 65535 && h->allow_pack;
   }
+  auto windows_needed = [&](int cells_per_word, long long* cells_out) {
+    int nw = 1;
+    long long mc = 0;
+    for (;; ++nw) {  // the tile-bound table grows with the window count
+      const size_t fixed = (size_t)cap * 8 + staging + (size_t)nw * (MAXTILES + 1) * 4 + sizeof(Shared) + 1024;
+      mc = (((long long)max_smem - (long long)fixed) / 4) * cells_per_word;
+      mc = std::min<long long>(mc, (long long)MAXTILES * THREADS * 4 * cells_per_word);
+      B200_REQUIRE(mc >= 4096, "not enough shared memory (%d bytes) for the similarity kernel", max_smem);
+      if ((long long)nw * mc >= n_cols) break;
+    }
+    *cells_out = mc;
+    return nw;
+  };
+  long long max_cells = 0, max_cells_unpacked = 0;
+  const int n_win_unpacked = windows_needed(1, &max_cells_unpacked);
+  if (h->pack && windows_needed(2, &max_cells) >= n_win_unpacked) h->pack = false;  // 16-bit counters only pay off with fewer windows
+  const int cpw = h->pack ? 2 : 1;       // cells per 4-byte accumulator word
+  const int cpv = 4 * cpw;               // cells per 16-byte vector
+  const int tile = THREADS * cpv;        // cells per block-wide scan iteration
+  int n_win = windows_needed(cpw, &max_cells);
   int win = (n_cols + n_win - 1) / n_win;
-  win = (win + 3) & ~3;
-  if (win < 4) win = 4;
+  win = (win + cpv - 1) / cpv * cpv;
+  if (win < cpv) win = cpv;
   h->n_win = n_win;
   h->win = win;
-  h->smem_bytes = (size_t)std::max(win, SBINS) * 4 + (size_t)cap * 8 + staging + (size_t)n_win * (MAXTILES + 1) * 4;
-  B200_CUDA(cudaFuncSetAttribute(kernel_for(h->formula, h->binary), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  h->acc_words = std::max(win / cpw, SBINS);
+  h->smem_bytes = (size_t)h->acc_words * 4 + (size_t)cap * 8 + staging + (size_t)n_win * (MAXTILES + 1) * 4;
+  B200_CUDA(cudaFuncSetAttribute(kernel_for(h->formula, h->binary, h->pack), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   h->tileB.alloc((size_t)n_win * (MAXTILES + 1));
-  tile_bounds_kernel<<<div_up((long long)n_win * (MAXTILES + 1), 128), 128, 0, st>>>(h->BN.get(), n_cols, n_win, win, h->tileB.get());
+  tile_bounds_kernel<<<div_up((long long)n_win * (MAXTILES + 1), 128), 128, 0, st>>>(h->BN.get(), n_cols, n_win, win, tile, h->tileB.get());
   count_launch();
   {
     // lanes per row segment in the accumulate phase: enough 16-byte chunks for the average segment
@@ -1075,6 +1177,7 @@ int b200_sim_create(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz
     B200_REQUIRE(topK >= 1, "b200_sim_create: topK must be >= 1 (dense output goes through b200_sim_compute_dense)");
     B200_REQUIRE(h_indptr && (nnz == 0 || (h_indices && h_data)), "b200_sim_create: NULL input array");
     h = new b200_sim_s();
+    h->allow_pack = getenv("B200REC_NO_PACK") == nullptr;  // test hook: force 32-bit counters on the binary path
     h->n_rows = (int)n_rows;
     h->n_cols = (int)n_cols;
     h->nnz = nnz;
@@ -1130,7 +1233,7 @@ int b200_sim_info(b200_sim_t h, int* K, int* n_windows, int* window_cells, int* 
     if (K) *K = h->K;
     if (n_windows) *n_windows = h->n_win;
     if (window_cells) *window_cells = h->win;
-    if (binary_path) *binary_path = h->binary ? 1 : 0;
+    if (binary_path) *binary_path = h->binary ? (h->pack ? 2 : 1) : 0;
     if (signed_data) *signed_data = h->signed_data ? 1 : 0;
   });
 }
@@ -1152,7 +1255,7 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   B200_CUDA(cudaMemsetAsync(h->counter.get(), 0, sizeof(int), st));
   KParams p;
   p.n_cols = h->n_cols; p.K = h->K; p.n_win = h->n_win; p.win = h->win; p.cap = h->cap; p.cap_alloc = h->cap_alloc;
-  p.acc_cells = std::max(h->win, SBINS);
+  p.acc_cells = h->acc_words;
   p.lpu_log2 = h->lpu_log2;
   p.tileB = h->tileB.get();
   p.se = h->shrink + 1e-6f;
@@ -1171,7 +1274,7 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   p.prof = h->prof_on ? h->prof.get() : nullptr;
   const int grid = std::min(n_range, h->n_sm);
   B200_CUDA(cudaEventRecord(h->ev0, st));
-  kernel_for(h->formula, h->binary)<<<grid, THREADS, h->smem_bytes, st>>>(p);
+  kernel_for(h->formula, h->binary, h->pack)<<<grid, THREADS, h->smem_bytes, st>>>(p);
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaEventRecord(h->ev1, st));
   h->timed = true;

@@ -150,3 +150,24 @@ def test_candidate_buffer_overflow_path(values):
 def test_overflow_path_multiwindow_signed():
     X = synth_urm(8000, 110_000, 0.0008, seed=22, values="ratings")
     _check(X, cols=np.arange(0, 110_000, 1999), debug_cap=64, topK=20, shrink=1, similarity="pearson")
+
+
+def test_binary_counter_widths(monkeypatch):
+    """Binary path: 16-bit packed counters (chosen when they reduce the window count) and the 32-bit fallback give the
+    same answer, single- and multi-window, and both match the oracle."""
+    from recsys2019_deeplearning_evaluation_b200 import _lib
+    import ctypes
+    Xs = [synth_urm(10_000, 60_000, 0.001, seed=42, values="binary"), synth_urm(20_000, 230_000, 0.0003, seed=8, values="binary")]
+    for X in Xs:
+        kw = dict(topK=60, shrink=20, similarity="cosine")
+        cols = np.arange(0, X.shape[1], max(1, X.shape[1] // 150))
+        W16, sim16, _ = _check(X, cols=cols, **kw)
+        bp = ctypes.c_int32()
+        _lib.check(_lib.load().b200_sim_info(sim16._h, None, None, None, ctypes.byref(bp), None))
+        assert bp.value == 2
+        monkeypatch.setenv("B200REC_NO_PACK", "1")
+        W32, sim32, _ = _check(X, cols=cols, **kw)
+        _lib.check(_lib.load().b200_sim_info(sim32._h, None, None, None, ctypes.byref(bp), None))
+        assert bp.value == 1 and sim32.n_windows > sim16.n_windows
+        monkeypatch.delenv("B200REC_NO_PACK")
+        assert abs(W16 - W32).max() < 1e-7 if (W16 - W32).nnz else True
