@@ -159,7 +159,19 @@ struct Shared {
   int warp_tot[NWARPS];
   float dthr[MAXTILES];
   float lbs[MAXTILES];
+  unsigned k2[MAXTILES];  // packed path: (0x8000 - ceil(dthr)) in both half-words, see half_ge_mask
 };
+
+// Packed 16-bit counters (all < 0x8000): bit q / bit 16+q of the result is set iff the low / high half-word of
+// word q of `v` is >= t, where k2 = (0x8000 - t) * 0x10001 and 1 <= t <= 0x8000 (no carry crosses the half-words).
+__device__ __forceinline__ unsigned half_ge_mask(const uint4 v, const unsigned k2) {
+  const unsigned M = 0x80008000u;
+  return (((v.x + k2) & M) >> 15) | (((v.y + k2) & M) >> 14) | (((v.z + k2) & M) >> 13) | (((v.w + k2) & M) >> 12);
+}
+__device__ __forceinline__ unsigned half_k2(const float dthr) {
+  const unsigned t = dthr <= 1.f ? 1u : (dthr >= 32768.f ? 0x8000u : (unsigned)ceilf(dthr));
+  return (0x8000u - t) * 0x10001u;
+}
 
 __device__ __forceinline__ void bar_sel() { asm volatile("bar.sync 1, %0;" ::"n"(SELT) : "memory"); }
 
@@ -324,7 +336,7 @@ __device__ __forceinline__ void store_cells(void* acc, int iv, const float* k) {
 
 template <int F, bool BINARY, bool PACK, bool NEG>
 __device__ void process_column(const KParams& p, int col, int target, int out_base, unsigned char* smem_raw,
-                               Shared* sh, const float* s_tileB, int* n_emitted, float* guess) {
+                               Shared* sh, const float* s_tileB, int* n_emitted) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* accf = reinterpret_cast<float*>(smem_raw);
   int* acci = reinterpret_cast<int*>(smem_raw);
@@ -378,7 +390,7 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
             u = e.x;
             sm_x[t] = __int_as_float(e.y);
           }
-          if (p.n_win == 1) {
+          if (p.n_win == 1 && !BINARY) {
             sm_sp[t * 2] = p.csr_ptr[u];
             sm_sp[t * 2 + 1] = p.csr_ptr[u + 1];
           } else if (all_splits) {
@@ -408,9 +420,10 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
           } else {
             s[k] = 0; e[k] = 0; x[k] = 0.f;
           }
-          // 16-byte chunks: 4 indices (binary) or 2 (index, value) pairs
-          a0[k] = BINARY ? (s[k] & ~3) : (s[k] & ~1);
-          mych = max(mych, BINARY ? ((e[k] - a0[k] + 3) >> 2) : ((e[k] - a0[k] + 1) >> 1));
+          // 16-byte chunks: 4 indices (binary; every (row, window) segment is 16-byte aligned and padded with a
+          // dummy cell index, so there are no partial chunks) or 2 (index, value) pairs
+          a0[k] = BINARY ? s[k] : (s[k] & ~1);
+          mych = max(mych, BINARY ? ((e[k] - a0[k]) >> 2) : ((e[k] - a0[k] + 1) >> 1));
         }
         const int maxch = __reduce_max_sync(0xffffffffu, mych);
         for (int c0 = 0; c0 < maxch; c0 += lpu) {
@@ -428,20 +441,13 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
             const int g = a0[k] + ch * (BINARY ? 4 : 2);
             // the diagonal is accumulated like any other cell and zeroed after the loop
             if (BINARY) {
-              const int jj[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-              if (g >= s[k] && g + 4 <= e[k]) {  // interior chunk: no bounds checks
+              if (g < e[k]) {
+                const int jj[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   if (PACK) atomicAdd(&accw_u[jj[c] >> 1], (jj[c] & 1) ? 65536u : 1u);
                   else atomicAdd(&accw_i[jj[c]], 1);
                 }
-              } else {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                  if (g + c >= s[k] && g + c < e[k]) {
-                    if (PACK) atomicAdd(&accw_u[jj[c] >> 1], (jj[c] & 1) ? 65536u : 1u);
-                    else atomicAdd(&accw_i[jj[c]], 1);
-                  }
               }
             } else {
               if (g >= s[k] && g < e[k]) atomicAdd(&accw_f[v[k].x], x[k] * __int_as_float(v[k].y));
@@ -474,50 +480,48 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
       continue;
     }
 
-    // ---------------- packed binary path: try the previous column's floor first.  A cell with d * lbs[tile] >= g is
-    // guaranteed a similarity >= g, so if at least `target` cells pass that integer test g is a valid floor and the
-    // histogram below is skipped (one cheap SIMD-compare pass instead of an atomic per non-zero cell).
     nbuf = sh->nbuf;
-    if (PACK && !NEG && thr == 0 && nbuf == 0 && win_n > 2 * target && *guess > 0.f) {
-      const float g = *guess * 0.8f;
-      if (tid == 0) sh->cnt = 0;
-      if (tid < ntiles) {
-        const float sc = lower_bound_scale<F>(p, Ai, tB[tid], tB[tid + 1]);
-        sh->lbs[tid] = sc;
-        sh->dthr[tid] = sc > 0.f ? fminf(ceilf(g / sc), 65535.f) : 65535.f;
-      }
-      __syncthreads();
-      int c = 0;
-      for (int iv = tid; iv < winv; iv += THREADS) {
-        const int4 v = reinterpret_cast<const int4*>(acci)[iv];
-        if ((v.x | v.y | v.z | v.w) == 0) continue;
-        const unsigned it = (unsigned)sh->dthr[iv / THREADS];
-        const unsigned t2 = it | (it << 16);
-        c += __popc(__vcmpgeu2((unsigned)v.x, t2)) + __popc(__vcmpgeu2((unsigned)v.y, t2)) + __popc(__vcmpgeu2((unsigned)v.z, t2)) +
-             __popc(__vcmpgeu2((unsigned)v.w, t2));
-      }
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0 && c) atomicAdd(&sh->cnt, c);
-      __syncthreads();
-      const int passed = sh->cnt >> 4;  // 16 mask bits per passing half-word
-      if (passed >= target && passed <= p.cap / 2) thr = ((u64)__float_as_uint(g)) << 32;
-      __syncthreads();
-    }
-
     // ---------------- bootstrap: floor of the target-th best similarity from per-cell lower bounds
     if (!NEG && thr == 0 && nbuf == 0 && win_n > 2 * target) {
       for (int i = tid; i < HBINS; i += THREADS) hist[i] = 0;
       if (tid == 0) sh->b0 = -1;
       if (tid < ntiles) sh->lbs[tid] = lower_bound_scale<F>(p, Ai, tB[tid], tB[tid + 1]);
       __syncthreads();
-      for (int iv = tid; iv < winv; iv += THREADS) {
-        const float sc = sh->lbs[iv / THREADS];
-        float d[CPV];
-        if (!load_cells<BINARY, PACK>(acci, iv, d)) continue;
+      if (PACK) {
+        // every lane of a warp is in the same tile in the same iteration, so cells with a count of 1 or 2 (the bulk)
+        // land in two bins: count them with half-word compares and add once per warp; counts >= 3 go one by one
+        for (int iv0 = warp * 32; iv0 < winv; iv0 += THREADS) {
+          const int iv = iv0 + lane;
+          const float sc = sh->lbs[iv0 / THREADS];
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (iv < winv) v = reinterpret_cast<const uint4*>(acci)[iv];
+          const int n1 = __popc(half_ge_mask(v, 0x7FFF7FFFu)), n2 = __popc(half_ge_mask(v, 0x7FFE7FFEu));
+          unsigned m3 = half_ge_mask(v, 0x7FFD7FFDu);
+          const int n3 = __popc(m3);
+          while (m3) {
+            const int b = __ffs(m3) - 1;
+            m3 &= m3 - 1;
+            const int q = b & 3;
+            const unsigned wq = q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
+            const float lb = (float)((b >> 4) ? (wq >> 16) : (wq & 0xFFFFu)) * sc;
+            if (lb > 0.f) atomicAdd(&hist[min(__float_as_uint(lb) >> 19, (unsigned)(HBINS - 1))], 1);
+          }
+          const int c1 = __reduce_add_sync(0xffffffffu, n1 - n2), c2 = __reduce_add_sync(0xffffffffu, n2 - n3);
+          if (lane == 0 && sc > 0.f) {
+            if (c1) atomicAdd(&hist[min(__float_as_uint(sc) >> 19, (unsigned)(HBINS - 1))], c1);
+            if (c2) atomicAdd(&hist[min(__float_as_uint(2.f * sc) >> 19, (unsigned)(HBINS - 1))], c2);
+          }
+        }
+      } else {
+        for (int iv = tid; iv < winv; iv += THREADS) {
+          const float sc = sh->lbs[iv / THREADS];
+          float d[CPV];
+          if (!load_cells<BINARY, PACK>(acci, iv, d)) continue;
 #pragma unroll
-        for (int c = 0; c < CPV; ++c) {
-          const float lb = d[c] * sc;
-          if (lb > 0.f) atomicAdd(&hist[min(__float_as_uint(lb) >> 19, (unsigned)(HBINS - 1))], 1);
+          for (int c = 0; c < CPV; ++c) {
+            const float lb = d[c] * sc;
+            if (lb > 0.f) atomicAdd(&hist[min(__float_as_uint(lb) >> 19, (unsigned)(HBINS - 1))], 1);
+          }
         }
       }
       __syncthreads();
@@ -544,22 +548,37 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
       const int nbuf_old = sh->nbuf;
       __syncthreads();
       if (tid == 0) sh->overflow = 0;
-      if (tid < ntiles)
-        sh->dthr[tid] = (!NEG && thr) ? dot_threshold<F>(p, __uint_as_float((unsigned)(thr >> 32)), Ai, tB[tid], tB[tid + 1]) : 0.f;
+      if (tid < ntiles) {
+        const float dt = (!NEG && thr) ? dot_threshold<F>(p, __uint_as_float((unsigned)(thr >> 32)), Ai, tB[tid], tB[tid + 1]) : 0.f;
+        sh->dthr[tid] = dt;
+        if (PACK) sh->k2[tid] = half_k2(dt);
+      }
       int cpos = 0, cneg = 0;
       const bool count_signs = !NEG && first && p.signed_data;
       __syncthreads();
       for (int iv = tid; iv < winv; iv += THREADS) {
         const float dthr = sh->dthr[iv / THREADS];
-        if (PACK && !NEG) {  // counts are non-negative integers: test all 8 against ceil(dthr) with two-lane SIMD compares
-          const int4 v = reinterpret_cast<const int4*>(acci)[iv];
-          if ((v.x | v.y | v.z | v.w) == 0) continue;
-          const unsigned it = dthr <= 1.f ? 1u : (unsigned)fminf(ceilf(dthr), 65535.f);
-          const unsigned t2 = it | (it << 16);
-          if ((__vcmpgeu2((unsigned)v.x, t2) | __vcmpgeu2((unsigned)v.y, t2) | __vcmpgeu2((unsigned)v.z, t2) | __vcmpgeu2((unsigned)v.w, t2)) == 0u) {
-            reinterpret_cast<int4*>(acci)[iv] = make_int4(0, 0, 0, 0);
-            continue;
+        if (PACK && !NEG) {
+          // counts are non-negative integers: d >= dthr <=> d >= ceil(dthr), tested on all 8 half-words at once; the
+          // vector is cleared and only the (few) passing cells are looked at one by one
+          const uint4 v = reinterpret_cast<const uint4*>(acci)[iv];
+          unsigned m = half_ge_mask(v, sh->k2[iv / THREADS]);
+          reinterpret_cast<int4*>(acci)[iv] = make_int4(0, 0, 0, 0);
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int q = b & 3, hf = b >> 4;
+            const unsigned wq = q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
+            const unsigned cntv = hf ? (wq >> 16) : (wq & 0xFFFFu);
+            const int pos = atomicAdd(&sh->nbuf, 1);
+            if (pos < p.cap)
+              buf[pos] = (((u64)__float_as_uint((float)cntv)) << 32) | (u64)(unsigned)(win_lo + iv * CPV + 2 * q + hf);
+            else {  // stays in place for the rescan
+              sh->overflow = 1;
+              reinterpret_cast<unsigned short*>(acci)[iv * CPV + 2 * q + hf] = (unsigned short)cntv;
+            }
           }
+          continue;
         }
         float d[CPV];
         if (!load_cells<BINARY, PACK>(acci, iv, d)) continue;
@@ -631,7 +650,6 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
     PROF_MARK(5);
   }
 
-  if (PACK && !NEG && thr) *guess = __uint_as_float((unsigned)(thr >> 32));
   // ---------------- emit (keys carry the ORIGINAL neighbour index; the last select left no dead slots)
   for (int t = tid; t < nbuf; t += THREADS) {
     const u64 k = buf[t];
@@ -658,7 +676,6 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     for (int i = tid; i < p.n_win * (MAXTILES + 1); i += THREADS) s_tileB[i] = p.tileB[i];
   }
   __syncthreads();
-  float guess = 0.f;  // floor of the previous column's K-th similarity (packed binary path)
   while (true) {
     if (tid == 0) sh.col = atomicAdd(p.counter, 1);
     __syncthreads();
@@ -669,11 +686,11 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     const int out_base_row = lc;
     int n_out = 0;
     if (p.dense_out) {
-      process_column<F, BINARY, PACK, false>(p, col, p.K, out_base_row, smem_raw, &sh, s_tileB, &n_out, &guess);
+      process_column<F, BINARY, PACK, false>(p, col, p.K, out_base_row, smem_raw, &sh, s_tileB, &n_out);
       __syncthreads();
       continue;
     }
-    process_column<F, BINARY, PACK, false>(p, col, p.K, out_base_row * p.K, smem_raw, &sh, s_tileB, &n_out, &guess);
+    process_column<F, BINARY, PACK, false>(p, col, p.K, out_base_row * p.K, smem_raw, &sh, s_tileB, &n_out);
     if (p.signed_data && n_out < p.K) {
       // zeros outrank negatives (Compute_Similarity_Python.py:335-345): negatives are only emitted when the
       // positives plus the implicit zeros (every column without a non-zero similarity, the diagonal
@@ -684,7 +701,7 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
       __syncthreads();
       if (m > 0 && nneg > 0) {
         int n_neg_out = 0;
-        process_column<F, BINARY, PACK, true>(p, col, m, out_base_row * p.K + n_out, smem_raw, &sh, s_tileB, &n_neg_out, &guess);
+        process_column<F, BINARY, PACK, true>(p, col, m, out_base_row * p.K + n_out, smem_raw, &sh, s_tileB, &n_neg_out);
         n_out += n_neg_out;
       }
     }
@@ -853,6 +870,33 @@ __global__ void split_kernel(const int* __restrict__ ptr, const int* __restrict_
     if (idx[mid] < bound) lo = mid + 1; else hi = mid;
   }
   split[g] = lo;
+}
+
+// Binary path: every (row, window) segment is re-laid 16-byte aligned and padded to a multiple of 4 indices with the
+// dummy cell index (w + 1) * win -- one cell past window w's accumulators -- so the accumulate loop has no partial chunks.
+__global__ void seg_len_kernel(const int* __restrict__ split, long long n_seg, int n_win, int* len4) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= n_seg) return;
+  const long long u = g / n_win;
+  const int w = (int)(g % n_win);
+  const int* sp = split + u * (n_win + 1) + w;
+  len4[g] = (sp[1] - sp[0] + 3) & ~3;
+}
+
+__global__ void seg_pad_kernel(const int* __restrict__ split, const int* __restrict__ idx, const int* __restrict__ poff,
+                               long long n_seg, int n_win, int win, int total, int* idx_pad, int* split_pad) {
+  const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;  // 8 lanes per segment
+  const int l = threadIdx.x & 7;
+  if (g >= n_seg) return;
+  const long long u = g / n_win;
+  const int w = (int)(g % n_win);
+  const int* sp = split + u * (n_win + 1) + w;
+  const int s = sp[0], n = sp[1] - sp[0], n4 = (n + 3) & ~3, o = poff[g];
+  for (int t = l; t < n4; t += 8) idx_pad[o + t] = t < n ? idx[s + t] : (w + 1) * win;
+  if (l == 0) {
+    split_pad[u * (n_win + 1) + w] = o;
+    if (w == n_win - 1) split_pad[u * (n_win + 1) + n_win] = o + n4;
+  }
 }
 
 // work[c] = sum over users u of (new) column c of len_u  (the gathered-entry count of SURVEY 8(d))
@@ -1086,13 +1130,13 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   h->cap = cap;
   h->cap_alloc = cap;
   const size_t staging = (size_t)STAGE_INTS * 4;
-  // binary path: counts fit 16 bits when no column holds 65536 entries (a dot product is at most the shorter column)
+  // binary path: counts fit 15 bits when no column holds 32768 entries (a dot product is at most the shorter column)
   {
     std::vector<int> hcnt((size_t)n_cols);
     B200_CUDA(cudaMemcpy(hcnt.data(), cnt_new.get(), sizeof(int) * (size_t)n_cols, cudaMemcpyDeviceToHost));
     int mx = 0;
     for (int j = 0; j < n_cols; ++j) mx = std::max(mx, hcnt[(size_t)j]);
-    h->pack = h->binary && mx < 65535 && h->allow_pack;
+    h->pack = h->binary && mx < 32768 && h->allow_pack;  // half_ge_mask needs counts below 0x8000
   }
   auto windows_needed = [&](int cells_per_word, long long* cells_out) {
     int nw = 1;
@@ -1119,7 +1163,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   if (win < cpv) win = cpv;
   h->n_win = n_win;
   h->win = win;
-  h->acc_words = std::max(win / cpw, SBINS);
+  h->acc_words = std::max(win / cpw, SBINS) + 4;  // + the dummy cell the padded row segments point at (cell index `win`)
   h->smem_bytes = (size_t)h->acc_words * 4 + (size_t)cap * 8 + staging + (size_t)n_win * (MAXTILES + 1) * 4;
   B200_CUDA(cudaFuncSetAttribute(kernel_for(h->formula, h->binary, h->pack), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   h->tileB.alloc((size_t)n_win * (MAXTILES + 1));
@@ -1133,10 +1177,30 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
     while (l2 < 5 && (1 << l2) < chunks) ++l2;
     h->lpu_log2 = l2;
   }
-  if (n_win > 1) {
+  if (n_win > 1 || h->binary) {
     h->split.alloc((size_t)n_rows * (n_win + 1));
     const long long total = (long long)n_rows * (n_win + 1);
     split_kernel<<<div_up(total, 256), 256, 0, st>>>(h->csr_ptr.get(), h->csr_idx.get(), n_rows, n_win, win, h->split.get()); count_launch();
+  }
+  if (h->binary) {  // padded, 16-byte aligned (row, window) segments
+    const long long n_seg = (long long)n_rows * n_win;
+    B200_REQUIRE((long long)nnz + 3 * n_seg < (1ll << 31), "matrix too large for 32-bit positions in the padded row layout");
+    DevBuf<int> len4((size_t)n_seg + 1), poff((size_t)n_seg + 1);
+    B200_CUDA(cudaMemsetAsync(len4.get() + n_seg, 0, sizeof(int), st));
+    seg_len_kernel<<<div_up(n_seg, 256), 256, 0, st>>>(h->split.get(), n_seg, n_win, len4.get()); count_launch();
+    size_t tb = 0;
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len4.get(), poff.get(), (int)(n_seg + 1), st));
+    DevBuf<unsigned char> tmp(tb);
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(), tb, len4.get(), poff.get(), (int)(n_seg + 1), st)); count_launch();
+    int total_pad = 0;
+    B200_CUDA(cudaMemcpyAsync(&total_pad, poff.get() + n_seg, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    DevBuf<int> idx_pad((size_t)total_pad + 8), split_pad((size_t)n_rows * (n_win + 1));
+    seg_pad_kernel<<<div_up(n_seg * 8, 256), 256, 0, st>>>(h->split.get(), h->csr_idx.get(), poff.get(), n_seg, n_win, win, total_pad,
+                                                          idx_pad.get(), split_pad.get()); count_launch();
+    B200_CUDA(cudaStreamSynchronize(st));
+    h->csr_idx = std::move(idx_pad);
+    h->split = std::move(split_pad);
   }
   // ---- per-column work (for LPT ordering and the bytes model), reported by ORIGINAL column index
   {
