@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libb200rec.so")
+LIB_PATH = os.environ.get("B200REC_LIB") or os.path.join(_PKG, "libb200rec.so")  # the override is a development hook
 
 c_int_p = ctypes.POINTER(ctypes.c_int32)
 c_float_p = ctypes.POINTER(ctypes.c_float)

@@ -44,8 +44,14 @@ constexpr int STAGE_INTS = 3072; // staging area: per staged user one value + sp
 constexpr int SPMAX = 5;        // staged split columns per user (all windows at once when n_win + 1 <= SPMAX)
 constexpr int HBINS = 4096;     // bootstrap histogram bins (aliases the candidate buffer)
 constexpr int SBINS = 2048;     // select histogram bins (aliases the staging area)
-constexpr int SELT = 128;       // threads that run the select (one warp per scheduler)
-constexpr int UB = 2;           // 128-bit loads in flight per lane
+#ifndef B200_SELT
+#define B200_SELT 256
+#endif
+constexpr int SELT = B200_SELT;  // threads that run the select
+#ifndef B200_UB
+#define B200_UB 2
+#endif
+constexpr int UB = B200_UB;      // 128-bit loads in flight per lane
 constexpr int TILE = THREADS * 4;
 constexpr int MAXTILES = 16;
 
@@ -161,6 +167,14 @@ struct Shared {
   float lbs[MAXTILES];
   unsigned k2[MAXTILES];  // packed path: (0x8000 - ceil(dthr)) in both half-words, see half_ge_mask
 };
+
+// Bootstrap histogram bins: 6 mantissa bits (1.6% steps) over the exponents 2^-40 .. 2^24; smaller values share
+// bin 0 (never used as a floor), larger ones the top bin (whose lower edge is still a valid floor).
+constexpr int LB_BASE = (127 - 40) << 6;
+__device__ __forceinline__ int lb_bin(const float lb) {
+  return min(max((int)(__float_as_uint(lb) >> 17) - LB_BASE, 0), HBINS - 1);
+}
+__device__ __forceinline__ unsigned lb_bin_floor_bits(const int b) { return ((unsigned)(b + LB_BASE)) << 17; }
 
 // Packed 16-bit counters (all < 0x8000): bit q / bit 16+q of the result is set iff the low / high half-word of
 // word q of `v` is >= t, where k2 = (0x8000 - t) * 0x10001 and 1 <= t <= 0x8000 (no carry crosses the half-words).
@@ -504,12 +518,12 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
             const int q = b & 3;
             const unsigned wq = q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
             const float lb = (float)((b >> 4) ? (wq >> 16) : (wq & 0xFFFFu)) * sc;
-            if (lb > 0.f) atomicAdd(&hist[min(__float_as_uint(lb) >> 19, (unsigned)(HBINS - 1))], 1);
+            if (lb > 0.f) atomicAdd(&hist[lb_bin(lb)], 1);
           }
           const int c1 = __reduce_add_sync(0xffffffffu, n1 - n2), c2 = __reduce_add_sync(0xffffffffu, n2 - n3);
           if (lane == 0 && sc > 0.f) {
-            if (c1) atomicAdd(&hist[min(__float_as_uint(sc) >> 19, (unsigned)(HBINS - 1))], c1);
-            if (c2) atomicAdd(&hist[min(__float_as_uint(2.f * sc) >> 19, (unsigned)(HBINS - 1))], c2);
+            if (c1) atomicAdd(&hist[lb_bin(sc)], c1);
+            if (c2) atomicAdd(&hist[lb_bin(2.f * sc)], c2);
           }
         }
       } else {
@@ -520,7 +534,7 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
 #pragma unroll
           for (int c = 0; c < CPV; ++c) {
             const float lb = d[c] * sc;
-            if (lb > 0.f) atomicAdd(&hist[min(__float_as_uint(lb) >> 19, (unsigned)(HBINS - 1))], 1);
+            if (lb > 0.f) atomicAdd(&hist[lb_bin(lb)], 1);
           }
         }
       }
@@ -536,7 +550,7 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
       }
       __syncthreads();
       const int b0 = sh->b0;
-      if (b0 > 0) thr = ((u64)(((unsigned)b0) << 19)) << 32;
+      if (b0 > 0) thr = ((u64)lb_bin_floor_bits(b0)) << 32;
       __syncthreads();  // hist (aliasing buf) fully consumed before candidates are pushed
     }
     PROF_MARK(2);
