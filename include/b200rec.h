@@ -48,7 +48,8 @@ enum b200_sim_kind {
   B200_SIM_PEARSON = 3,    /* pyx:123, :236-273 */
   B200_SIM_JACCARD = 4,    /* jaccard == tanimoto, pyx:125-128, :488-491 */
   B200_SIM_DICE = 5,       /* pyx:130-132, :493-496 */
-  B200_SIM_TVERSKY = 6     /* pyx:134-136, :498-503 */
+  B200_SIM_TVERSKY = 6,    /* pyx:134-136, :498-503 */
+  B200_SIM_EUCLIDEAN = 7   /* Compute_Similarity_Euclidean.py; created through b200_sim_create_euclidean only */
 };
 
 /* Build the device-side representation of dataMatrix (n_rows x n_cols CSR, int32 indices sorted per row,
@@ -74,6 +75,18 @@ int b200_sim_destroy(b200_sim_t h);
 int b200_sim_create_scaled(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* h_indptr,
                            const int32_t* h_indices, const float* h_data, const float* h_A, const float* h_B,
                            int topK, void* stream);
+
+/* Euclidean similarity (Base/Similarity/Compute_Similarity_Euclidean.py:17-223): for target column i and EVERY other
+ * column j (co-rated or not)  d2 = |i|^2 + |j|^2 - 2 i.j (:144-149), optionally / (|i| |j|) where that is non-zero
+ * (normalize, :152-154) and / n_rows (normalize_avg_row, :156-157), d = sqrt(d2) where d2 > 0 (:159-160),
+ * similarity = 1 / (g(d) + shrink + 1e-9) with g = exp, identity or log(1 + .) (:162-169); the K largest over all
+ * columns except i itself (:172-186).  Same accumulate kernel as b200_sim_create, every cell of the neighbour axis
+ * evaluated; b200_sim_compute* return the top-K table.  row_weights (:152, only well defined for square matrices in
+ * the reference) are not supported. */
+enum b200_euclid_mode { B200_EUCLID_EXP = 0, B200_EUCLID_LIN = 1, B200_EUCLID_LOG = 2 };
+int b200_sim_create_euclidean(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* h_indptr,
+                              const int32_t* h_indices, const float* h_data, int topK, float shrink, int normalize,
+                              int normalize_avg_row, int distance_mode, void* stream);
 
 /* effective K (min(topK, n_cols)), window geometry and path chosen at create time */
 int b200_sim_info(b200_sim_t h, int* K, int* n_windows, int* window_cells, int* binary_path, int* signed_data);

@@ -125,6 +125,63 @@ class SimilarityOracle:
         return sps.csr_matrix((vals, (rows, cols)), shape=(self.n_columns, self.n_columns), dtype=np.float32)  # pyx:607-609
 
 
+class EuclideanOracle:
+    """fp64 restatement of Base/Similarity/Compute_Similarity_Euclidean.py:17-223 (the reference computes in the input
+    dtype, fp32).  Pinned against the reference class itself through tests/golden/euclid_golden.npz
+    (tests/test_oracle_similarity.py).  row_weights are not restated (:152 multiplies an n_columns vector by n_rows
+    weights, only defined for square data)."""
+
+    def __init__(self, dataMatrix, topK=100, shrink=0, normalize=False, normalize_avg_row=False,
+                 similarity_from_distance_mode="lin", row_weights=None, **args):
+        if similarity_from_distance_mode not in ("exp", "lin", "log"):
+            raise ValueError("mode")  # :44-46
+        assert row_weights is None
+        self.n_rows, self.n_columns = dataMatrix.shape
+        self.TopK = min(topK, self.n_columns)  # :26
+        self.shrink, self.normalize, self.avg, self.mode = shrink, normalize, normalize_avg_row, similarity_from_distance_mode
+        self.X = sps.csc_matrix(dataMatrix, dtype=np.float64)
+        self.sq = np.asarray(self.X.multiply(self.X).sum(axis=0)).ravel()  # :112
+        self.norm = np.sqrt(self.sq)  # :113
+
+    def column_values(self, cols):
+        """Dense (n_columns, len(cols)) float64 similarities of every column against `cols` (diagonal 0, :171)."""
+        cols = np.asarray(cols)
+        D = np.asarray(self.X.T.dot(self.X[:, cols]).todense(), dtype=np.float64)  # :135
+        d2 = self.sq[:, None] + self.sq[cols][None, :] - 2.0 * D  # :144-148
+        d2[cols, np.arange(len(cols))] = 0.0  # :149
+        if self.normalize:  # :152-154
+            den = self.norm[:, None] * self.norm[cols][None, :]
+            d2 = np.divide(d2, den, out=d2.copy(), where=den != 0.0)
+        if self.avg:
+            d2 = d2 / self.n_rows  # :156-157
+        d = np.where(d2 > 0.0, np.sqrt(np.maximum(d2, 0.0)), d2)  # :159-160
+        with np.errstate(over="ignore"):
+            g = np.exp(d) if self.mode == "exp" else (d if self.mode == "lin" else np.log(d + 1.0))
+            S = 1.0 / (g + self.shrink + 1e-9)  # :162-169
+        S[cols, np.arange(len(cols))] = 0.0  # :171
+        return S
+
+    def compute_similarity(self, start_col=None, end_col=None, block_size=100):
+        lo, hi = 0, self.n_columns
+        if start_col is not None and 0 < start_col < self.n_columns:  # :96-100
+            lo = start_col
+        if end_col is not None and lo < end_col < self.n_columns:
+            hi = end_col
+        rows, cols, vals = [], [], []
+        for b0 in range(lo, hi, 256):
+            cc = np.arange(b0, min(hi, b0 + 256))
+            V = self.column_values(cc)
+            for k, c in enumerate(cc):
+                idx = SimilarityOracle.select_topk(V[:, k], self.TopK)  # :176-186, ties -> ascending index
+                rows.append(idx)
+                cols.append(np.full(len(idx), c, dtype=np.int64))
+                vals.append(V[idx, k])
+        rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+        cols = np.concatenate(cols) if cols else np.zeros(0, np.int64)
+        vals = np.concatenate(vals) if vals else np.zeros(0)
+        return sps.csr_matrix((vals, (rows, cols)), shape=(self.n_columns, self.n_columns), dtype=np.float32)  # :219-221
+
+
 def check_topk_against_dense(W, oracle, cols, rtol=1e-4, atol=1e-7):
     """Tie-aware parity check of a computed W (CSR/CSC, entries W[j, col]) against the fp64 dense values.
     For every column in `cols`: (1) every emitted value matches the oracle value at that (j, col) within

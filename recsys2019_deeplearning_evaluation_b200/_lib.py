@@ -24,6 +24,8 @@ SIGNATURES = {
                                        ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void, c_void]),
     "b200_sim_create_scaled": (ctypes.c_int, [ctypes.POINTER(c_void), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void, c_void, c_void,
                                               c_void, c_void, ctypes.c_int, c_void]),
+    "b200_sim_create_euclidean": (ctypes.c_int, [ctypes.POINTER(c_void), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void, c_void, c_void,
+                                                 ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void]),
     "b200_sim_destroy": (ctypes.c_int, [c_void]),
     "b200_sim_info": (ctypes.c_int, [c_void, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "b200_sim_compute_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void]),

@@ -55,7 +55,7 @@ constexpr int UB = B200_UB;      // 128-bit loads in flight per lane
 constexpr int TILE = THREADS * 4;
 constexpr int MAXTILES = 16;
 
-enum Formula { F_PROD = 0, F_NONORM = 1, F_JACCARD = 2, F_DICE = 3, F_TVERSKY = 4, F_SCALE = 5 };
+enum Formula { F_PROD = 0, F_NONORM = 1, F_JACCARD = 2, F_DICE = 3, F_TVERSKY = 4, F_SCALE = 5, F_EUCLID = 6 };
 
 struct KParams {
   int n_cols, K, n_win, win, cap, cap_alloc;  // cap <= cap_alloc (a smaller logical cap is a test hook)
@@ -82,6 +82,10 @@ struct KParams {
   float* out_val;
   int* out_cnt;
   int signed_data;
+  // euclidean (Compute_Similarity_Euclidean.py): distance -> similarity mode 0 exp / 1 lin / 2 log, normalize,
+  // divisor of normalize_avg_row (n_rows, or 1), shrink as a float, and whether stored values can be negative
+  int eu_mode, eu_norm, eu_signed;
+  float eu_div, eu_shrink;
   float* dense_out;  // dense mode (TopK == 0 / full Gram): [n_range, n_cols] row-major, out[target - col_begin, neighbour]
   unsigned long long* prof;  // optional [8] per-phase cycle counters (thread 0 of every CTA), test/bench hook
 };
@@ -94,6 +98,21 @@ __device__ __forceinline__ float sim_value(const KParams& p, float d, float a, f
   if (F == F_DICE) return d / (a + b + p.se);
   if (F == F_SCALE) return d * a * b;  // P3alpha / RP3beta: dot * (1/deg_i)^alpha * deg_j^-beta
   return d / (d + (a - d) * p.ta + (b - d) * p.tb + p.se);
+}
+
+// Euclidean similarity of two columns from their squared distance (Compute_Similarity_Euclidean.py:152-173; fp32
+// like the reference's arrays): optional division by the product of the norms where that is non-zero (:152-154) and
+// by n_rows (:156-157), square root where positive (:159-160), then 1 / (g(d) + shrink + 1e-9) (:162-169).
+__device__ __forceinline__ float euclid_sim(const KParams& p, float d2, float sq_i, float sq_j) {
+  float d = d2;
+  if (p.eu_norm) {
+    const float den = sqrtf(sq_i) * sqrtf(sq_j);
+    if (den != 0.f) d = d / den;
+  }
+  d = d / p.eu_div;
+  if (d > 0.f) d = sqrtf(d);
+  const float g = p.eu_mode == 0 ? expf(d) : (p.eu_mode == 1 ? d : logf(d + 1.f));
+  return 1.f / ((g + p.eu_shrink) + 1e-9f);
 }
 
 // Smallest positive dot product whose similarity can reach `t` (>0) for ANY neighbour norm term in
@@ -378,6 +397,32 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
   const int sub = lane & (lpu - 1), uslot = lane >> p.lpu_log2;
   __syncthreads();
 
+  if (F == F_EUCLID) {
+    // Every column -- co-rated or not -- has a finite distance to the target, so the candidates are ALL cells.  A floor
+    // of the target-th best similarity comes from the norms alone: for any neighbour j the squared distance is at most
+    // sq_i + sq_j (non-negative data: dot >= 0) or (|i| + |j|)^2 (signed data), so the target-th best of those bounds
+    // over ANY set of cells is a valid floor.  The set: the columns next to the target in norm order (normalize: the
+    // zero-dot distance |i|/|j| + |j|/|i| is smallest around |j| = |i|) or the smallest norms (plain distance).
+    const int lo = p.eu_norm ? max(0, col - target) : 0;
+    const int hi = p.eu_norm ? min(p.n_cols, col + target + 1) : min(p.n_cols, target + 1);
+    for (int t = lo + tid; t < hi; t += THREADS) {
+      u64 key = 0ull;
+      if (t != col) {
+        const int2 bn = __ldg(p.BN + t);
+        const float b = __int_as_float(bn.x);
+        const float dmax2 = p.eu_signed ? (Ai + b) + 2.f * sqrtf(Ai) * sqrtf(b) : (Ai + b);
+        const float sv = euclid_sim(p, dmax2, Ai, b);
+        if (sv > 0.f) key = (((u64)__float_as_uint(sv)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)bn.y);
+      }
+      buf[t - lo] = key;
+    }
+    int kept;
+    const u64 t0 = block_select(buf, hi - lo, target, sh, acci, &kept);  // the window is all zero here
+    if (t0) thr = ((u64)__float_as_uint(__uint_as_float((unsigned)(t0 >> 32)) * (1.f - 1e-5f))) << 32;
+    if (tid == 0) sh->nbuf = 0;
+    __syncthreads();
+  }
+
   for (int w = 0; w < p.n_win; ++w) {
     const int win_lo = w * p.win;
     const int win_n = min(p.win, p.n_cols - win_lo);
@@ -491,6 +536,50 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
       __syncthreads();
       for (int iv = tid; iv < winv; iv += THREADS) reinterpret_cast<int4*>(acci)[iv] = make_int4(0, 0, 0, 0);
       __syncthreads();
+      continue;
+    }
+
+    if (F == F_EUCLID) {
+      // every cell of the window is evaluated exactly, 1024 at a time; the buffer is pruned to the best `target`
+      // (raising thr to an exact key) whenever the next chunk might not fit, so nothing ever overflows
+      int ub = sh->nbuf;  // block-uniform upper bound of sh->nbuf (every chunk pushes at most THREADS keys)
+      __syncthreads();
+      for (int c0 = 0; c0 < win_n; c0 += THREADS) {
+        if (ub + THREADS > p.cap) {
+          ub = sh->nbuf;      // exact: the pushes of the previous chunk ended at its barrier
+          __syncthreads();    // nobody pushes again before everybody has read it
+          if (ub + THREADS > p.cap) {
+            int kept;
+            staged_valid = false;  // the staging area is the select scratch while cells remain in the window
+            thr = max(thr, block_select(buf, ub, target, sh, shist_stage, &kept));
+            if (tid == 0) sh->nbuf = kept;
+            ub = kept;
+            __syncthreads();
+          }
+        }
+        ub += THREADS;
+        const int c = c0 + tid;
+        if (c < win_n && win_lo + c != col) {
+          const float d = PACK ? (float)(((unsigned)acci[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu) : (BINARY ? (float)acci[c] : accf[c]);
+          const int2 bn = __ldg(p.BN + win_lo + c);
+          const float b = __int_as_float(bn.x);
+          const float sv = euclid_sim(p, (b + Ai) - 2.f * d, Ai, b);
+          const u64 key = (((u64)__float_as_uint(sv)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)bn.y);
+          if (sv > 0.f && key >= thr) buf[atomicAdd(&sh->nbuf, 1)] = key;
+        }
+        __syncthreads();
+      }
+      for (int iv = tid; iv < winv; iv += THREADS) reinterpret_cast<int4*>(acci)[iv] = make_int4(0, 0, 0, 0);
+      __syncthreads();
+      nbuf = sh->nbuf;
+      if (w == p.n_win - 1) {
+        int kept;
+        thr = max(thr, block_select(buf, nbuf, target, sh, acci, &kept));
+        if (tid == 0) sh->nbuf = kept;
+        nbuf = kept;
+        __syncthreads();
+      }
+      PROF_MARK(3);
       continue;
     }
 
@@ -945,6 +1034,7 @@ struct b200_sim_s {
   bool pack = false;               // binary path with 16-bit counters (two cells per accumulator word)
   bool allow_pack = true;
   int acc_words = 0;               // 4-byte words allocated for the accumulator window
+  int eu_mode = 1, eu_norm = 0, eu_avg = 0;  // euclidean: distance->similarity mode, normalize, normalize_avg_row
   bool scaled = false;             // P3alpha / RP3beta product: CSC values are 1, A and B come from the caller
   const float* h_A = nullptr;
   const float* h_B = nullptr;
@@ -983,6 +1073,7 @@ sim_kernel_t kernel_for(int formula, bool binary, bool pack) {
     case F_JACCARD: return kernel_of<F_JACCARD>(binary, pack);
     case F_DICE: return kernel_of<F_DICE>(binary, pack);
     case F_SCALE: return sim_topk_kernel<F_SCALE, false, false>;
+    case F_EUCLID: return kernel_of<F_EUCLID>(binary, pack);
     default: return kernel_of<F_TVERSKY>(binary, pack);
   }
 }
@@ -1050,7 +1141,8 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
     B200_CUDA(cudaMemcpyAsync(B_old.get(), h->h_B, sizeof(float) * (size_t)n_cols, cudaMemcpyHostToDevice, st));
     scaled_keys_kernel<<<div_up(n_cols, 256), 256, 0, st>>>(B_old.get(), n_cols, Bkey.get(), col_iota.get());
   } else {
-    const int norm_mode = set_kind ? 0 : (h->kind == B200_SIM_ASYMMETRIC ? 2 : 1);
+    // euclidean keeps the plain sums of squares too (Compute_Similarity_Euclidean.py:112)
+    const int norm_mode = (set_kind || h->kind == B200_SIM_EUCLIDEAN) ? 0 : (h->kind == B200_SIM_ASYMMETRIC ? 2 : 1);
     norms_kernel<<<div_up(n_cols, 256), 256, 0, st>>>(colsq.get(), n_cols, norm_mode, h->asym_alpha, A_old.get(), B_old.get(),
                                                       Bkey.get(), col_iota.get());
   }
@@ -1130,6 +1222,8 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
     h->formula = F_SCALE;
   } else if (set_kind) {
     h->formula = h->kind == B200_SIM_JACCARD ? F_JACCARD : (h->kind == B200_SIM_DICE ? F_DICE : F_TVERSKY);
+  } else if (h->kind == B200_SIM_EUCLIDEAN) {
+    h->formula = F_EUCLID;
   } else {
     h->formula = h->normalize ? F_PROD : F_NONORM;
   }
@@ -1297,6 +1391,35 @@ int b200_sim_create_scaled(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int6
   return rc;
 }
 
+int b200_sim_create_euclidean(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* h_indptr,
+                              const int32_t* h_indices, const float* h_data, int topK, float shrink, int normalize,
+                              int normalize_avg_row, int distance_mode, void* stream) {
+  if (out) *out = nullptr;
+  b200_sim_s* h = nullptr;
+  int rc = guarded([&] {
+    B200_REQUIRE(out && h_indptr && (nnz == 0 || (h_indices && h_data)), "b200_sim_create_euclidean: NULL argument");
+    B200_REQUIRE(n_rows > 0 && n_cols > 0 && nnz >= 0, "b200_sim_create_euclidean: bad shape %lld x %lld nnz %lld",
+                 (long long)n_rows, (long long)n_cols, (long long)nnz);
+    B200_REQUIRE(n_rows < (1ll << 31) - 1 && n_cols < (1ll << 31) - 1 && nnz < (1ll << 31) - 1,
+                 "b200_sim_create_euclidean: int32 index range exceeded");
+    B200_REQUIRE(topK >= 1, "b200_sim_create_euclidean: topK must be >= 1");
+    B200_REQUIRE(distance_mode >= B200_EUCLID_EXP && distance_mode <= B200_EUCLID_LOG,
+                 "b200_sim_create_euclidean: unknown similarity_from_distance_mode %d", distance_mode);
+    h = new b200_sim_s();
+    h->allow_pack = getenv("B200REC_NO_PACK") == nullptr;
+    h->n_rows = (int)n_rows; h->n_cols = (int)n_cols; h->nnz = nnz;
+    h->kind = B200_SIM_EUCLIDEAN;
+    h->K = (int)std::min<int64_t>(topK, n_cols);
+    h->normalize = 0;
+    h->shrink = shrink;
+    h->eu_mode = distance_mode; h->eu_norm = normalize != 0; h->eu_avg = normalize_avg_row != 0;
+    build(h, h_indptr, h_indices, h_data, nullptr, (cudaStream_t)stream);
+    *out = h;
+  });
+  if (rc != B200_OK && h) delete h;
+  return rc;
+}
+
 int b200_sim_destroy(b200_sim_t h) {
   if (!h) return B200_OK;
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1347,7 +1470,10 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   p.order = h->order.get();
   p.counter = h->counter.get();
   p.out_idx = d_idx; p.out_val = d_val; p.out_cnt = d_cnt;
-  p.signed_data = h->signed_data ? 1 : 0;
+  p.signed_data = (h->signed_data && h->formula != F_EUCLID) ? 1 : 0;  // euclidean similarities are never negative
+  p.eu_mode = h->eu_mode; p.eu_norm = h->eu_norm; p.eu_signed = h->signed_data ? 1 : 0;
+  p.eu_div = h->eu_avg ? (float)h->n_rows : 1.f;
+  p.eu_shrink = h->shrink;
   p.dense_out = d_dense;
   p.prof = h->prof_on ? h->prof.get() : nullptr;
   const int grid = std::min(n_range, h->n_sm);
@@ -1374,6 +1500,7 @@ int b200_sim_compute_device(b200_sim_t h, int start_col, int end_col, int32_t* d
 int b200_sim_compute_dense_device(b200_sim_t h, int start_col, int end_col, float* d_out, void* stream) {
   return guarded([&] {
     B200_REQUIRE(h != nullptr && d_out != nullptr, "b200_sim_compute_dense: NULL argument");
+    B200_REQUIRE(h->formula != F_EUCLID, "b200_sim_compute_dense: the euclidean similarity has no dense output mode");
     B200_REQUIRE(0 <= start_col && start_col <= end_col && end_col <= h->n_cols, "b200_sim_compute_dense: bad column range [%d,%d)",
                  start_col, end_col);
     if (end_col == start_col) return;

@@ -190,6 +190,62 @@ class Compute_Similarity_Cython:
             pass
 
 
+_EUCLID_MODE = {"exp": 0, "lin": 1, "log": 2}
+
+
+class Compute_Similarity_Euclidean(Compute_Similarity_Cython):
+    """Drop-in for Base/Similarity/Compute_Similarity_Euclidean.py:14-223 (same constructor and
+    `compute_similarity(start_col, end_col, block_size)` signature, same error text).  Every column has a finite
+    distance to the target, so the top-K runs over ALL columns (co-rated or not), the target itself excluded
+    (:149,:171); see include/b200rec.h b200_sim_create_euclidean for the formula.
+
+    Declared deviations: `row_weights` raises NotImplementedError (the reference multiplies an n_columns vector by
+    the n_rows weights, :152 -- only defined for square matrices); top-K ties resolve to the ascending neighbour
+    index (binary data ties massively here: all non-co-rated columns of equal norm are equidistant)."""
+
+    def __init__(self, dataMatrix, topK=100, shrink=0, normalize=False, normalize_avg_row=False,
+                 similarity_from_distance_mode="lin", row_weights=None, **args):
+        self._h = ctypes.c_void_p()
+        self._lib = _lib.load()
+        self.n_rows, self.n_columns = dataMatrix.shape
+        self.TopK = min(topK, self.n_columns)  # :26
+        self.shrink = shrink  # a Python number here (:22), not a C int
+        self.normalize = bool(normalize)
+        self.normalize_avg_row = bool(normalize_avg_row)
+        self.similarity = "euclidean"
+        if similarity_from_distance_mode not in _EUCLID_MODE:
+            # same text as :44-46
+            raise ValueError("Compute_Similarity_Euclidean: value for argument 'mode' not recognized."
+                             " Allowed values are: 'exp', 'lin', 'log'."
+                             " Passed value was '{}'".format(similarity_from_distance_mode))
+        if row_weights is not None:
+            if dataMatrix.shape[0] != len(row_weights):
+                # :54-55
+                raise ValueError("Compute_Similarity_Euclidean: provided row_weights and dataMatrix have different number of rows."
+                                 "row_weights has {} rows, dataMatrix has {}.".format(len(row_weights), dataMatrix.shape[0]))
+            raise NotImplementedError("Compute_Similarity_Euclidean: row_weights are not supported on the CUDA path")
+        if self.TopK < 1 or self.TopK > 2048:
+            raise ValueError("Compute_Similarity_Euclidean: topK must be in [1, 2048] on the CUDA path, got {}".format(topK))
+        self._dense_mode = False
+        X = _as_csr_f32(dataMatrix)
+        self._keep = X
+        _lib.check(self._lib.b200_sim_create_euclidean(
+            ctypes.byref(self._h), X.shape[0], X.shape[1], X.nnz, _lib.ptr(X.indptr), _lib.ptr(X.indices),
+            _lib.ptr(X.data), int(self.TopK), float(shrink), int(self.normalize), int(self.normalize_avg_row),
+            _EUCLID_MODE[similarity_from_distance_mode], None))
+        self._keep = None
+        k = ctypes.c_int32(); nw = ctypes.c_int32(); wc = ctypes.c_int32(); bp = ctypes.c_int32(); sd = ctypes.c_int32()
+        _lib.check(self._lib.b200_sim_info(self._h, ctypes.byref(k), ctypes.byref(nw), ctypes.byref(wc),
+                                           ctypes.byref(bp), ctypes.byref(sd)))
+        self.K, self.n_windows, self.window_cells = int(k.value), int(nw.value), int(wc.value)
+        self.binary_path, self.signed_data = bool(bp.value), bool(sd.value)
+
+    def compute_similarity(self, start_col=None, end_col=None, block_size=100):
+        """:75-223; block_size (the reference's dense block width) has no meaning here and is ignored."""
+        lo, hi = self._col_range(start_col, end_col)
+        return self.table_to_csr(self.compute_topk_device(lo, hi))
+
+
 def topk_table_to_csr(n_cols, K, idx, val, cnt):
     """[n_cols, K] device top-K table -> scipy CSR float32 (row = neighbour j, column = target), sorted indices."""
     import torch
@@ -218,7 +274,10 @@ class Compute_Similarity:
         if use_implementation not in ("density", "cython", "python"):
             raise ValueError("Compute_Similarity: value for argument 'use_implementation' not recognized")
         if similarity == "euclidean":
-            raise NotImplementedError("euclidean similarity (Compute_Similarity_Euclidean.py) is not on the CUDA path yet")
+            # Compute_Similarity.py:52-58: the euclidean class takes the matrix as is (no 1-feature assertion)
+            self.dense = False
+            self.compute_similarity_object = Compute_Similarity_Euclidean(dataMatrix, **args)
+            return
         assert not (dataMatrix.shape[0] == 1 and dataMatrix.nnz == dataMatrix.shape[1]), \
             "Compute_Similarity: data has only 1 feature (shape: {}) with values in all columns," \
             " cosine and set-based similarities are not able to discriminate 1-dimensional dense data," \

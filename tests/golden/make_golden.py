@@ -178,3 +178,36 @@ def make_ials_golden():
 
 if __name__ == "__main__":
     make_ials_golden()
+
+
+EUCLID_CASES = [dict(values=v, topK=12, shrink=s, normalize=nz, normalize_avg_row=av, similarity_from_distance_mode=m)
+                for v, s, nz, av, m in (("continuous", 0, False, False, "lin"), ("continuous", 2, True, False, "exp"),
+                                        ("continuous", 1, False, True, "log"), ("ratings", 3, True, True, "lin"),
+                                        ("ratings", 0, False, False, "log"), ("binary", 1, False, False, "lin"),
+                                        ("binary", 0, True, False, "exp"), ("continuous", 0.5, True, False, "lin"))]
+EUCLID_CASES.append(dict(values="ratings", topK=400, shrink=1, normalize=False, normalize_avg_row=False,
+                         similarity_from_distance_mode="lin"))  # topK > n_columns
+
+
+def make_euclid_golden():
+    """tests/golden/euclid_golden.npz: W of the reference's Compute_Similarity_Euclidean (fp32 arithmetic) on the same
+    three URMs as similarity_golden.npz."""
+    ref_loader.ensure_import_path()
+    from Base.Similarity.Compute_Similarity_Euclidean import Compute_Similarity_Euclidean
+    out = {}
+    meta = []
+    for n, c in enumerate(EUCLID_CASES):
+        c = dict(c)
+        values = c.pop("values")
+        X = synth_urm(400, 150, 0.06, seed=17, values=values)
+        W = sps.csr_matrix(Compute_Similarity_Euclidean(X, **c).compute_similarity())
+        W.sort_indices()
+        out["eu%d_indptr" % n], out["eu%d_indices" % n], out["eu%d_data" % n] = W.indptr, W.indices, W.data
+        meta.append(repr(dict(values=values, **c)))
+    out["meta"] = np.array(meta)
+    np.savez_compressed(os.path.join(HERE, "euclid_golden.npz"), **out)
+    print("wrote euclid_golden.npz", len(EUCLID_CASES), "cases")
+
+
+if __name__ == "__main__":
+    make_euclid_golden()

@@ -39,3 +39,15 @@ def same_sparse(A, B, rtol=1e-4, atol=1e-7):
     if A.nnz != B.nnz or (A.indptr != B.indptr).any() or (A.indices != B.indices).any():
         return False
     return bool(np.allclose(A.data, B.data, rtol=rtol, atol=atol))
+
+
+def load_euclid_golden():
+    """[(values, kwargs, W)] of tests/golden/euclid_golden.npz (reference Compute_Similarity_Euclidean outputs)."""
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "euclid_golden.npz"), allow_pickle=False)
+    cases = []
+    for n, m in enumerate(z["meta"]):
+        kw = ast.literal_eval(str(m))
+        values = kw.pop("values")
+        W = sps.csr_matrix((z["eu%d_data" % n], z["eu%d_indices" % n], z["eu%d_indptr" % n]), shape=(150, 150), dtype=np.float32)
+        cases.append((values, kw, W))
+    return cases

@@ -99,3 +99,33 @@ def test_topk_matches_similarityMatrixTopK_recipe():
         keep = np.argsort(-full[:, c], kind="stable")[:9]
         ref = np.zeros(150); ref[keep] = full[keep, c]
         assert np.allclose(top[:, c], ref, atol=1e-7)
+
+
+# ------------------------------------------------------------------ euclidean (Compute_Similarity_Euclidean.py)
+from golden_util import load_euclid_golden  # noqa: E402
+from oracle.similarity_oracle import EuclideanOracle  # noqa: E402
+
+EU_CASES = load_euclid_golden()
+
+
+@pytest.mark.parametrize("n", range(len(EU_CASES)))
+def test_euclidean_oracle_matches_golden(n):
+    """The reference class computes in fp32; the restatement in fp64: values within 1e-4 (the reference's own
+    Compute_similarity_euclidean_test.py:59-84 checks 1e-4 absolute against a dense control), index sets identical on
+    the tie-free (continuous) inputs, tie-aware otherwise."""
+    values, kw, W = EU_CASES[n]
+    orc = EuclideanOracle(URMS[values], **kw)
+    check_topk_against_dense(W, orc, np.arange(150), rtol=1e-4)
+    if values == "continuous":
+        assert same_sparse(orc.compute_similarity(), W, rtol=1e-4)
+
+
+def test_euclidean_oracle_dense_control():
+    """Recipe of Base/Similarity/Compute_similarity_euclidean_test.py:59-84: 1/(1 + scipy euclidean distance), topK = n."""
+    rng = np.random.default_rng(1)
+    D = (rng.random((40, 12)) * (rng.random((40, 12)) < 0.5)).astype(np.float32)
+    S = EuclideanOracle(sps.csr_matrix(D), topK=12, shrink=1, similarity_from_distance_mode="lin").compute_similarity().toarray()
+    diff = D.astype(np.float64)[:, :, None] - D.astype(np.float64)[:, None, :]
+    ctrl = 1.0 / (np.sqrt((diff ** 2).sum(axis=0)) + 1.0 + 1e-9)
+    np.fill_diagonal(ctrl, 0.0)
+    assert np.allclose(S, ctrl, atol=1e-6)
