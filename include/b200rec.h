@@ -259,7 +259,8 @@ int b200_ease_from_gram_device(const float* d_G, int n_items, const int32_t* d_u
  * confidences c = d_conf[...] (the C or C_csc matrix, :99-123), Y = the other side's factors [n_other, f] fp64:
  *     X[r, :] = (Y^T Y + Y_p^T diag(c - 1) Y_p + reg I)^-1  Y_p^T c
  * Rows not listed keep their previous contents (cold rows, :143).  d_YtY_work: f * f doubles of scratch.
- * n_factors <= 208.
+ * n_factors <= 256 (up to 208 the packed fp64 system lives in shared memory; above, its last rows spill to a per-CTA
+ * slab of global memory and the Gram accumulation takes two passes over the profile).
  * ------------------------------------------------------------------------------------------------ */
 int b200_ials_half_epoch_device(const int32_t* d_rows, int n_solve, const int32_t* d_ptr, const int32_t* d_idx,
                                 const float* d_conf, const double* d_Y, int n_other, int n_factors, double reg,

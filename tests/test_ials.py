@@ -56,7 +56,7 @@ def test_cuda_matches_reference_golden(n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("f", [1, 17, 64, 130, 208])
+@pytest.mark.parametrize("f", [1, 17, 64, 130, 208, 209, 256])
 def test_cuda_factor_sizes_against_restatement(f):
     from recsys2019_deeplearning_evaluation_b200.recommenders import IALSRecommender
     X = synth_urm(700, 260, 0.04, seed=f, values="ratings")
@@ -81,4 +81,4 @@ def test_argument_errors():
     with pytest.raises(ValueError, match="confidence_scaling"):
         IALSRecommender(X, verbose=False).fit(epochs=1, confidence_scaling="sqrt")
     with pytest.raises(ValueError, match="n_factors"):
-        IALSRecommender(X, verbose=False).fit(epochs=1, num_factors=256)
+        IALSRecommender(X, verbose=False).fit(epochs=1, num_factors=257)
