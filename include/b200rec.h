@@ -266,6 +266,39 @@ int b200_ials_half_epoch_device(const int32_t* d_rows, int n_solve, const int32_
                                 const float* d_conf, const double* d_Y, int n_other, int n_factors, double reg,
                                 double* d_X, double* d_YtY_work, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * URM feature weighting in front of the KNN similarity  
+ * replaces  Base/IR_feature_weighting.py:13-51 okapi_BM_25 and :56-78 TF_IDF as KNN/ItemKNNCFRecommender.py:42-50 and
+ *           KNN/UserKNNCFRecommender.py:43-51 apply them: weighting(URM.T).T -- items are the documents, users the terms.
+ * d_data (the CSR values of the n_users x n_items URM on the device) is rewritten in place.
+ * ------------------------------------------------------------------------------------------------ */
+enum b200_weighting { B200_WEIGHT_BM25 = 0, B200_WEIGHT_TFIDF = 1 };
+int b200_feature_weighting_device(int mode, int n_users, int n_items, int64_t nnz, const int32_t* d_indptr,
+                                  const int32_t* d_indices, float* d_data, float K1, float B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation inner loop on the device  
+ * replaces  Base/Evaluation/Evaluator.py:305-388 _compute_metrics_on_recommendation_list and the per-user metric
+ *           functions of Base/Evaluation/metrics.py (:65-287, :615-716) for one block of users.
+ * d_rec_items / d_rec_scores: the [n_block, max_cutoff] tables of b200_score_topn_device (a -inf score ends a list);
+ * test URM in CSR with sorted indices; d_cutoffs: n_cutoffs ascending list lengths; d_idcg: [n_users, n_cutoffs] ideal
+ * DCG of every user (metrics.py:268); d_item_novelty / d_item_pop_norm: the per-item terms of Novelty (:651) and
+ * AveragePopularity (:686).  Accumulates (atomically, across calls) into d_acc [n_cutoffs, B200_EVAL_NACC] doubles
+ * and the per-item counters d_rec_count / d_hit_count [n_cutoffs, n_items] (times recommended / recommended and
+ * relevant), from which the global-distribution metrics (coverage, Gini, Shannon, Herfindahl, mean inter-list) follow.
+ * ------------------------------------------------------------------------------------------------ */
+enum b200_eval_slot {
+  B200_EVAL_PRECISION = 0, B200_EVAL_PRECISION_RECALL_MIN_DEN = 1, B200_EVAL_RECALL = 2, B200_EVAL_MAP = 3,
+  B200_EVAL_MAP_MIN_DEN = 4, B200_EVAL_MRR = 5, B200_EVAL_NDCG = 6, B200_EVAL_HIT_RATE = 7, B200_EVAL_ARHR = 8,
+  B200_EVAL_NOVELTY = 9, B200_EVAL_AVERAGE_POPULARITY = 10, B200_EVAL_USERS_WITH_RECS = 11, B200_EVAL_N_USERS = 12,
+  B200_EVAL_NACC = 16
+};
+int b200_eval_accumulate_device(const int32_t* d_users, int n_block, const int32_t* d_rec_items, const float* d_rec_scores,
+                                int max_cutoff, const int32_t* d_test_ptr, const int32_t* d_test_idx,
+                                const float* d_test_val, const int32_t* d_cutoffs, int n_cutoffs, const double* d_idcg,
+                                const double* d_item_novelty, const double* d_item_pop_norm, int n_items, double* d_acc,
+                                int32_t* d_rec_count, int32_t* d_hit_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,17 @@ class BaseRecommender(object):
             self._d_urm = _dev_csr(self.URM_train)
         return self._d_urm
 
+    def _apply_feature_weighting(self, feature_weighting):
+        """KNN/ItemKNNCFRecommender.py:42-50 / KNN/UserKNNCFRecommender.py:43-51: URM_train is REPLACED by the weighted
+        matrix (later scoring uses it too), weighting applied to URM.T (items are the documents)."""
+        if feature_weighting == "none":
+            return
+        from .weighting import okapi_BM_25, TF_IDF
+        fn = okapi_BM_25 if feature_weighting == "BM25" else TF_IDF
+        self.URM_train = sps.csr_matrix(fn(self.URM_train.astype(np.float32).T).T, dtype=np.float32)
+        self.URM_train.sort_indices()
+        self._d_urm = None
+
     # ---- device-side pieces shared by every model -----------------------------------------------------------------
     def _scores_device(self, d_users, items_to_compute=None):
         """[B, n_items] float32 CUDA tensor of raw scores; model specific."""
@@ -107,27 +118,39 @@ class BaseRecommender(object):
             self._mask_items(scores, items_to_compute)
         return scores.cpu().numpy()
 
+    def _masked_scores_device(self, d_users, remove_seen_flag=True, items_to_compute=None, remove_custom_items_flag=False):
+        """BaseRecommender.py:164-196 on the device: score block with seen / not-to-compute / custom items at -inf."""
+        import torch
+        scores = self._scores_device(d_users)
+        if items_to_compute is not None or remove_seen_flag:
+            self._mask_items(scores, items_to_compute, d_users, seen=remove_seen_flag)
+        if remove_custom_items_flag and len(self.items_to_ignore_ID):
+            scores[:, torch.from_numpy(self.items_to_ignore_ID).to(scores.device)] = float("-inf")
+        return scores
+
+    def _topn_device(self, scores, cutoff):
+        """[B, cutoff] int32 items / float32 scores CUDA tensors, best first, ties by ascending item id (cutoff <= 1024);
+        lists end where the score is -inf."""
+        import torch
+        items = torch.empty((scores.shape[0], cutoff), dtype=torch.int32, device=scores.device)
+        vals = torch.empty((scores.shape[0], cutoff), dtype=torch.float32, device=scores.device)
+        _lib.check(self._lib.b200_score_topn_device(scores.data_ptr(), scores.shape[0], self.n_items, cutoff, items.data_ptr(),
+                                                    vals.data_ptr(), _stream()))
+        return items, vals
+
     def recommend(self, user_id_array, cutoff=None, remove_seen_flag=True, items_to_compute=None, remove_top_pop_flag=False,
                   remove_custom_items_flag=False, return_scores=False):
         """BaseRecommender.py:131-222 on the device: scores -> seen / custom items to -inf -> per-user top-`cutoff`
         (best first, ties by ascending item id) with -inf entries dropped from the lists."""
-        import torch
         single_user = np.isscalar(user_id_array)
         users = np.atleast_1d(user_id_array)
         if cutoff is None:
             cutoff = self.n_items - 1
         cutoff = int(min(cutoff, self.n_items))
         d_users = self._users_tensor(users)
-        scores = self._scores_device(d_users)
-        if items_to_compute is not None or remove_seen_flag:
-            self._mask_items(scores, items_to_compute, d_users, seen=remove_seen_flag)
-        if remove_custom_items_flag and len(self.items_to_ignore_ID):
-            scores[:, torch.from_numpy(self.items_to_ignore_ID).to(scores.device)] = float("-inf")
+        scores = self._masked_scores_device(d_users, remove_seen_flag, items_to_compute, remove_custom_items_flag)
         if cutoff <= 1024:
-            items = torch.empty((len(users), cutoff), dtype=torch.int32, device=scores.device)
-            vals = torch.empty((len(users), cutoff), dtype=torch.float32, device=scores.device)
-            _lib.check(self._lib.b200_score_topn_device(scores.data_ptr(), len(users), self.n_items, cutoff, items.data_ptr(),
-                                                        vals.data_ptr(), _stream()))
+            items, vals = self._topn_device(scores, cutoff)
             items_h, vals_h = items.cpu().numpy(), vals.cpu().numpy()
         else:  # full rankings are host work in the reference too; keep the device scores, sort on the host
             sc = scores.cpu().numpy()
@@ -188,8 +211,7 @@ class ItemKNNCFRecommender(BaseItemSimilarityMatrixRecommender):
         if feature_weighting not in self.FEATURE_WEIGHTING_VALUES:
             raise ValueError("Value for 'feature_weighting' not recognized. Acceptable values are {}, provided was '{}'".format(
                 self.FEATURE_WEIGHTING_VALUES, feature_weighting))
-        if feature_weighting != "none":
-            raise NotImplementedError("BM25 / TF-IDF feature weighting (Base/IR_feature_weighting.py) is a 'next' row")
+        self._apply_feature_weighting(feature_weighting)
         sim = Compute_Similarity(self.URM_train, shrink=shrink, topK=topK, normalize=normalize, similarity=similarity,
                                  **similarity_args)
         self.W_sparse = sps.csr_matrix(sim.compute_similarity(), dtype=np.float32)
@@ -198,12 +220,15 @@ class ItemKNNCFRecommender(BaseItemSimilarityMatrixRecommender):
 
 class UserKNNCFRecommender(BaseUserSimilarityMatrixRecommender):
     RECOMMENDER_NAME = "UserKNNCFRecommender"
+    FEATURE_WEIGHTING_VALUES = ["BM25", "TF-IDF", "none"]
 
     def fit(self, topK=50, shrink=100, similarity="cosine", normalize=True, feature_weighting="none", **similarity_args):
         """KNN/UserKNNCFRecommender.py:32-54: the same kernel on URM^T (columns = users)."""
         self.topK, self.shrink = topK, shrink
-        if feature_weighting != "none":
-            raise NotImplementedError("BM25 / TF-IDF feature weighting is a 'next' row")
+        if feature_weighting not in self.FEATURE_WEIGHTING_VALUES:
+            raise ValueError("Value for 'feature_weighting' not recognized. Acceptable values are {}, provided was '{}'".format(
+                self.FEATURE_WEIGHTING_VALUES, feature_weighting))
+        self._apply_feature_weighting(feature_weighting)
         sim = Compute_Similarity(self.URM_train.T.tocsr(), shrink=shrink, topK=topK, normalize=normalize, similarity=similarity,
                                  **similarity_args)
         self.W_sparse = sps.csr_matrix(sim.compute_similarity(), dtype=np.float32)

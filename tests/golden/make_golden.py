@@ -211,3 +211,85 @@ def make_euclid_golden():
 
 if __name__ == "__main__":
     make_euclid_golden()
+
+
+def make_weighting_golden():
+    """tests/golden/weighting_golden.npz: the reference's okapi_BM_25 / TF_IDF on URM.T of the three golden URMs, and
+    ItemKNNCFRecommender / UserKNNCFRecommender W_sparse fitted with feature_weighting."""
+    ref_loader.ensure_import_path()
+    ref_loader.load("Compute_Similarity_Cython")
+    from Base.IR_feature_weighting import okapi_BM_25, TF_IDF
+    from KNN.ItemKNNCFRecommender import ItemKNNCFRecommender
+    from KNN.UserKNNCFRecommender import UserKNNCFRecommender
+    out = {}
+    for values in ("continuous", "ratings", "binary"):
+        X = synth_urm(400, 150, 0.06, seed=17, values=values)
+        for tag, fn in (("bm25", okapi_BM_25), ("tfidf", TF_IDF)):
+            W = sps.csr_matrix(fn(X.T.astype(np.float32)))
+            W.sort_indices()
+            out["%s_%s_indptr" % (tag, values)], out["%s_%s_indices" % (tag, values)] = W.indptr, W.indices
+            out["%s_%s_data" % (tag, values)] = W.data.astype(np.float64)
+    X = synth_urm(400, 150, 0.06, seed=17, values="ratings")
+    for tag, cls in (("item", ItemKNNCFRecommender), ("user", UserKNNCFRecommender)):
+        for fw in ("BM25", "TF-IDF"):
+            r = cls(X.copy())
+            r.fit(topK=10, shrink=2, similarity="cosine", feature_weighting=fw)
+            W = sps.csr_matrix(r.W_sparse)
+            W.sort_indices()
+            k = "knn_%s_%s" % (tag, fw.replace("-", ""))
+            out[k + "_indptr"], out[k + "_indices"], out[k + "_data"] = W.indptr, W.indices, W.data
+    np.savez_compressed(os.path.join(HERE, "weighting_golden.npz"), **out)
+    print("wrote weighting_golden.npz")
+
+
+if __name__ == "__main__":
+    make_weighting_golden()
+
+
+def eval_case(n):
+    """Inputs of evaluator case n (shared with tests/test_evaluation.py): train/test URMs, dense tie-free scores, kwargs."""
+    rng = np.random.default_rng(300 + n)
+    train = synth_urm(300, 120, 0.06, seed=41 + n, values="ratings").tolil()
+    train[0:4, 0:112] = 1.0  # users whose unseen items do not fill the longest list
+    train = sps.csr_matrix(train.tocsr(), dtype=np.float32)
+    test = synth_urm(300, 120, 0.04, seed=51 + n, values="ratings").tolil()
+    test[10:20, :] = 0  # users without test interactions
+    test = sps.csr_matrix(test.tocsr(), dtype=np.float32)
+    test.eliminate_zeros()
+    S = rng.random((300, 120)).astype(np.float32)
+    kw = [dict(cutoff_list=[5, 10, 20]),
+          dict(cutoff_list=[1, 7], min_ratings_per_user=3, exclude_seen=False),
+          dict(cutoff_list=[10], ignore_items=[3, 17, 44, 90], ignore_users=[1, 25, 26, 200])][n]
+    return train, test, S, kw
+
+
+def make_evaluator_golden():
+    """tests/golden/evaluator_golden.npz: results of the reference's EvaluatorHoldout on a stub recommender that returns a
+    fixed dense score matrix."""
+    ref_loader.ensure_import_path()
+    from Base.BaseRecommender import BaseRecommender
+    from Base.Evaluation.Evaluator import EvaluatorHoldout
+
+    class Stub(BaseRecommender):
+        RECOMMENDER_NAME = "Stub"
+
+        def __init__(self, URM_train, S):
+            super(Stub, self).__init__(URM_train)
+            self.S = S
+
+        def _compute_item_score(self, user_id_array, items_to_compute=None):
+            return self.S[np.asarray(user_id_array)].astype(np.float32).copy()
+
+    out = {}
+    for n in range(3):
+        train, test, S, kw = eval_case(n)
+        res, _ = EvaluatorHoldout(test, **kw).evaluateRecommender(Stub(train, S))
+        for c, d in res.items():
+            for k, v in d.items():
+                out["e%d_c%d_%s" % (n, c, k)] = np.float64(v)
+    np.savez_compressed(os.path.join(HERE, "evaluator_golden.npz"), **out)
+    print("wrote evaluator_golden.npz")
+
+
+if __name__ == "__main__":
+    make_evaluator_golden()
