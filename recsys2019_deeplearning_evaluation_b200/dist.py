@@ -122,3 +122,58 @@ class ShardedBPR:
         delta = self.U - self.U0
         dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.group)
         return self.U0 + delta
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K4 row parallelism: implicit ALS with the rows of each half epoch sharded over the ranks.
+# Every row solve is independent given the other side's factors, so rank r solves a contiguous slice of the warm rows
+# (balanced by profile length), the other side's factor table is replicated, and one all-reduce per half epoch of a
+# buffer that holds every rank's freshly solved rows (zeros elsewhere: the sum adds nothing to a solved row)
+# gives every rank the full updated table.  Y^T Y is recomputed from the replicated table on every rank.
+
+def sync_owned_rows(X, rows, lo, hi, group=None):
+    """In place: X[rows[k]] for k in [lo, hi) are this rank's new values; afterwards X[rows] holds every rank's.
+    `rows` is an integer tensor (the warm rows, same on every rank).  Works with gloo (CPU tensors) and NCCL."""
+    import torch
+    import torch.distributed as dist
+    Z = torch.zeros_like(X)
+    mine = rows[lo:hi].long()
+    if hi > lo:
+        Z[mine] = X[mine]
+    dist.all_reduce(Z, op=dist.ReduceOp.SUM, group=group)
+    X[rows.long()] = Z[rows.long()]
+    return X
+
+
+def make_sharded_ials(group=None):
+    """Returns a subclass of recommenders.IALSRecommender whose _run_epoch shards the row solves over the ranks of
+    `group`.  Every rank must seed numpy identically before fit() (the initial item factors come from np.random,
+    MatrixFactorization/IALSRecommender.py:204-210) and ends every epoch with the full factor tables."""
+    import torch.distributed as dist
+    from .recommenders import IALSRecommender
+
+    class ShardedIALSRecommender(IALSRecommender):
+        RECOMMENDER_NAME = "IALSRecommender"
+
+        def _slice(self, rows, csr):
+            key = rows.data_ptr()
+            cache = self.__dict__.setdefault("_shard_cache", {})
+            if key not in cache:
+                ptr = csr[0].cpu().numpy()
+                r = rows.cpu().numpy()
+                b = balanced_ranges((ptr[r + 1] - ptr[r]).astype(np.float64) + self.num_factors / 8.0, dist.get_world_size(group))
+                rank = dist.get_rank(group)
+                cache[key] = (int(b[rank]), int(b[rank + 1]))
+            return cache[key]
+
+        def _half_sharded(self, rows, csr, Y, X):
+            lo, hi = self._slice(rows, csr)
+            if hi > lo:
+                self._half(rows[lo:hi].contiguous(), csr, Y, X)
+            sync_owned_rows(X, rows, lo, hi, group)
+
+        def _run_epoch(self, num_epoch):
+            self._half_sharded(self._d_warm_users, self._d_C, self._d_V, self._d_U)
+            self._half_sharded(self._d_warm_items, self._d_Ct, self._d_U, self._d_V)
+
+    return ShardedIALSRecommender

@@ -113,3 +113,39 @@ def test_sync_replicated_delta_gloo_world2():
     want[0] += 1.0; want[1] += 2.0; want[3] += 1.0
     for rank, V, Vp in res:
         assert np.allclose(V, want) and np.allclose(Vp, want)
+
+
+def _owned_rows_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from recsys2019_deeplearning_evaluation_b200.dist import sync_owned_rows
+    X = torch.zeros((6, 2), dtype=torch.float64)
+    X[5] = -7.0                                   # a cold row: never listed, must survive
+    rows = torch.tensor([0, 2, 3, 4], dtype=torch.int32)
+    lo, hi = (0, 3) if rank == 0 else (3, 4)      # rank 0 solved rows 0, 2, 3; rank 1 solved row 4
+    X[rows[lo:hi].long()] = 10.0 * (rank + 1) + rows[lo:hi].double()[:, None]
+    sync_owned_rows(X, rows, lo, hi)
+    q.put((rank, X.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_sync_owned_rows_gloo_world2():
+    """K4 row parallelism: after the exchange every rank holds every rank's solved rows; unlisted rows are untouched."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_owned_rows_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.zeros((6, 2))
+    want[0], want[2], want[3], want[4], want[5] = 10.0, 12.0, 13.0, 24.0, -7.0
+    for rank, X in res:
+        assert np.array_equal(X, want)
