@@ -52,6 +52,12 @@ constexpr int SELT = B200_SELT;  // threads that run the select
 #define B200_UB 2
 #endif
 constexpr int UB = B200_UB;      // 128-bit loads in flight per lane
+#ifndef B200_PREFETCH
+#define B200_PREFETCH 0
+#endif
+// B200_PREFETCH: while the select group (SELT threads) prunes the finished column, the other threads walk the NEXT
+// column's CSC entries -> row-segment bounds and issue L2 prefetches for those row segments, so that the next column's
+// stage and accumulate phases find their three dependent levels of data in L2 instead of DRAM.
 constexpr int TILE = THREADS * 4;
 constexpr int MAXTILES = 16;
 
@@ -173,6 +179,7 @@ __device__ __forceinline__ unsigned key32_of(float v) {
 
 struct Shared {
   int col;
+  int next;  // B200_PREFETCH: the counter value (position in the processing order) this CTA handles after `col`
   int nbuf;
   int overflow;
   int npos, nneg;
@@ -364,6 +371,34 @@ __device__ __forceinline__ void store_cells(void* acc, int iv, const float* k) {
     reinterpret_cast<int4*>(acc)[iv] = make_int4((int)k[0], (int)k[1], (int)k[2], (int)k[3]);
   } else {
     reinterpret_cast<float4*>(acc)[iv] = make_float4(k[0], k[1], k[2], k[3]);
+  }
+}
+
+__device__ __forceinline__ void prefetch_l2_range(const void* base, long long byte_lo, long long byte_hi) {
+  const char* b = reinterpret_cast<const char*>(base);
+  for (long long o = byte_lo & ~127ll; o < byte_hi; o += 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+}
+
+// Threads q = 0 .. nthr-1 (the ones that idle during the last select of a column): L2 prefetch of everything the column
+// at position `c_next` of the processing order will gather.
+template <bool BINARY>
+__device__ __forceinline__ void prefetch_column(const KParams& p, int c_next, int q, int nthr) {
+  if (c_next >= p.n_range) return;
+  const int lc = p.order ? p.order[c_next] : c_next;
+  const int col = p.old2new[p.col_begin + lc];
+  const int cs = p.csc_ptr[col], ce = p.csc_ptr[col + 1];
+  for (int t = cs + q; t < ce; t += nthr) {
+    const int u = BINARY ? p.csc_idx[t] : p.csc_ent[t].x;
+    if (p.n_win == 1 && !BINARY) {
+      const int s0 = p.csr_ptr[u], e0 = p.csr_ptr[u + 1];
+      prefetch_l2_range(p.csr_ent, 8ll * s0, 8ll * e0);
+    } else {
+      const int* sp = p.split + (size_t)u * (p.n_win + 1);
+      const int s0 = sp[0], e0 = sp[p.n_win];  // the windows of a row are contiguous in memory
+      if (BINARY) prefetch_l2_range(p.csr_idx, 4ll * s0, 4ll * e0);
+      else prefetch_l2_range(p.csr_ent, 8ll * s0, 8ll * e0);
+    }
   }
 }
 
@@ -745,6 +780,16 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
     nbuf = sh->nbuf;
     if (nbuf > p.cap / 2 || w == p.n_win - 1) {
       int kept;  // the window is all zero here and select leaves its scratch zeroed
+#if B200_PREFETCH
+      if (w == p.n_win - 1) {
+        __syncthreads();
+        if (tid < SELT) select_group(buf, nbuf, target, sh, acci);
+        else prefetch_column<BINARY>(p, sh->next, tid - SELT, THREADS - SELT);
+        __syncthreads();
+        kept = sh->cnt;
+        thr = max(thr, sh->sel_thr);
+      } else
+#endif
       thr = max(thr, block_select(buf, nbuf, target, sh, acci, &kept));
       if (tid == 0) sh->nbuf = kept;
       nbuf = kept;
@@ -779,11 +824,22 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     for (int i = tid; i < p.n_win * (MAXTILES + 1); i += THREADS) s_tileB[i] = p.tileB[i];
   }
   __syncthreads();
+#if B200_PREFETCH
+  if (tid == 0) sh.next = atomicAdd(p.counter, 1);
+#endif
   while (true) {
+#if B200_PREFETCH
+    __syncthreads();
+    const int c = sh.next;
+    __syncthreads();
+    if (c >= p.n_range) break;
+    if (tid == 0) sh.next = atomicAdd(p.counter, 1);  // read by the prefetching threads many barriers later
+#else
     if (tid == 0) sh.col = atomicAdd(p.counter, 1);
     __syncthreads();
     const int c = sh.col;
     if (c >= p.n_range) break;
+#endif
     const int lc = p.order ? p.order[c] : c;
     const int col = p.old2new[p.col_begin + lc];  // new numbering
     const int out_base_row = lc;
