@@ -76,6 +76,32 @@ class BaseRecommender(object):
             self._d_urm = _dev_csr(self.URM_train)
         return self._d_urm
 
+    # ---- model hand-off in the reference's archive format (Base/BaseRecommender.py:236-253, Base/DataIO.py) ----------
+    def _model_dict(self):
+        raise NotImplementedError("BaseRecommender: save_model not implemented")
+
+    def save_model(self, folder_path, file_name=None):
+        from .dataio import DataIO
+        if file_name is None:
+            file_name = self.RECOMMENDER_NAME
+        self._print("Saving model in file '{}'".format(folder_path + file_name))
+        DataIO(folder_path=folder_path).save_data(file_name=file_name, data_dict_to_save=self._model_dict())
+        self._print("Saving complete")
+
+    def load_model(self, folder_path, file_name=None):
+        from .dataio import DataIO
+        if file_name is None:
+            file_name = self.RECOMMENDER_NAME
+        self._print("Loading model from file '{}'".format(folder_path + file_name))
+        data_dict = DataIO(folder_path=folder_path).load_data(file_name=file_name)
+        for attrib_name in data_dict.keys():  # BaseRecommender.py:250-251
+            self.__setattr__(attrib_name, data_dict[attrib_name])
+        self._model_loaded()
+        self._print("Loading complete")
+
+    def _model_loaded(self):
+        """Device-side copies are keyed by the identity of the host arrays, so they refresh by themselves."""
+
     def _apply_feature_weighting(self, feature_weighting):
         """KNN/ItemKNNCFRecommender.py:42-50 / KNN/UserKNNCFRecommender.py:43-51: URM_train is REPLACED by the weighted
         matrix (later scoring uses it too), weighting applied to URM.T (items are the documents)."""
@@ -167,6 +193,9 @@ class BaseRecommender(object):
 class BaseItemSimilarityMatrixRecommender(BaseRecommender):
     """BaseSimilarityMatrixRecommender.py:62-92: scores = URM[users] . W_sparse."""
 
+    def _model_dict(self):
+        return {"W_sparse": self.W_sparse}  # BaseSimilarityMatrixRecommender.py:55
+
     def _w_device(self):
         if getattr(self, "_d_w_src", None) is not self.W_sparse:
             self._d_w = _dev_csr(self.W_sparse)
@@ -186,6 +215,9 @@ class BaseItemSimilarityMatrixRecommender(BaseRecommender):
 
 class BaseUserSimilarityMatrixRecommender(BaseRecommender):
     """BaseSimilarityMatrixRecommender.py:95-116: scores = W_sparse[users] . URM."""
+
+    def _model_dict(self):
+        return {"W_sparse": self.W_sparse}  # BaseSimilarityMatrixRecommender.py:55
 
     def _scores_device(self, d_users, items_to_compute=None):
         import torch
@@ -294,6 +326,12 @@ class Incremental_Training_Early_Stopping(object):
 
 class BaseMatrixFactorizationRecommender(BaseRecommender):
     """BaseMatrixFactorizationRecommender.py:15-102: scores = U[users] . V^T (+ global + user + item bias)."""
+
+    def _model_dict(self):  # BaseMatrixFactorizationRecommender.py:88-96
+        d = {"USER_factors": self.USER_factors, "ITEM_factors": self.ITEM_factors, "use_bias": self.use_bias}
+        if self.use_bias:
+            d["ITEM_bias"], d["USER_bias"], d["GLOBAL_bias"] = self.ITEM_bias, self.USER_bias, self.GLOBAL_bias
+        return d
 
     def __init__(self, URM_train, verbose=True):
         super(BaseMatrixFactorizationRecommender, self).__init__(URM_train, verbose=verbose)
@@ -486,6 +524,12 @@ class EASE_R_Recommender(BaseItemSimilarityMatrixRecommender):
             from .slim_bpr_epoch import dense_topk_to_sparse
             self._d_B = None
             self.W_sparse = sps.csr_matrix(dense_topk_to_sparse(B, n, topK, along_columns=True, mode=0), dtype=np.float32)
+
+    def _model_loaded(self):
+        import torch
+        self._d_B = None
+        if isinstance(self.W_sparse, np.ndarray):  # dense model (topK=None): scoring reads it from the device
+            self._d_B = torch.from_numpy(np.ascontiguousarray(self.W_sparse, np.float32)).to(torch.device("cuda", torch.cuda.current_device()))
 
     def _scores_device(self, d_users, items_to_compute=None):
         if getattr(self, "_d_B", None) is None:

@@ -293,3 +293,22 @@ def make_evaluator_golden():
 
 if __name__ == "__main__":
     make_evaluator_golden()
+
+
+def make_dataio_golden():
+    """tests/golden/dataio_ref.zip: an archive written by the reference's own DataIO (Base/DataIO.py) holding every
+    member type, so that the format-compatible reader is pinned without /root/reference."""
+    ref_loader.ensure_import_path()
+    from Base.DataIO import DataIO
+    import pandas as pd
+    rng = np.random.default_rng(5)
+    d = {"W_sparse": sps.random(30, 30, 0.1, format="csr", random_state=3, dtype=np.float32),
+         "USER_factors": rng.random((7, 4)), "use_bias": False, "topK": np.int64(50), "name": "x",
+         "mapper": {3: "a", 9: "b"}, "nested": {"A": rng.random(3), "k": 2},
+         "frame": pd.DataFrame({"a": [1, 2], "b": [0.5, 1.5]})}
+    DataIO(HERE + "/").save_data("dataio_ref", d)
+    print("wrote dataio_ref.zip")
+
+
+if __name__ == "__main__":
+    make_dataio_golden()
