@@ -55,5 +55,25 @@ def synth_urm(n_users, n_items, density, seed=42, values="binary", popularity=No
 
 
 def synth_config(name, seed=42, values="binary", popularity=None):
+    """The URM of a BASELINE.json config.  B200REC_SYNTH_CACHE=<dir> (e.g. /dev/shm) keeps the three CSR arrays on disk so
+    that several processes of one measurement session (bench arms, profiler passes) do not regenerate them."""
+    import os
     nu, ni, d = CONFIGS[name]
-    return synth_urm(nu, ni, d, seed=seed, values=values, popularity=popularity)
+    cache = os.environ.get("B200REC_SYNTH_CACHE")
+    if not cache:
+        return synth_urm(nu, ni, d, seed=seed, values=values, popularity=popularity)
+    stem = os.path.join(cache, "urm_%s_%d_%s_%s" % (name, seed, values, popularity))
+    try:
+        data, idx, ptr = (np.load(stem + "_%s.npy" % k) for k in ("data", "indices", "indptr"))
+        M = sps.csr_matrix((data, idx, ptr), shape=(nu, ni), dtype=np.float32)
+        M.has_sorted_indices = True
+        return M
+    except (OSError, ValueError):
+        M = synth_urm(nu, ni, d, seed=seed, values=values, popularity=popularity)
+        try:
+            for k, a in (("data", M.data), ("indices", M.indices), ("indptr", M.indptr)):
+                np.save(stem + "_%s.tmp.npy" % k, a)
+                os.replace(stem + "_%s.tmp.npy" % k, stem + "_%s.npy" % k)
+        except OSError:
+            pass
+        return M
