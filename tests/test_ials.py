@@ -58,17 +58,22 @@ def test_cuda_matches_reference_golden(n):
 @pytest.mark.gpu
 @pytest.mark.parametrize("f", [1, 17, 64, 130, 208, 209, 256])
 def test_cuda_factor_sizes_against_restatement(f):
+    from threadpoolctl import threadpool_limits
     from recsys2019_deeplearning_evaluation_b200.recommenders import IALSRecommender
-    X = synth_urm(700, 260, 0.04, seed=f, values="ratings")
+    # the restatement inverts one f x f matrix per row in a Python loop: keep the row count small for the large systems
+    # and BLAS single-threaded (on a many-core box its thread pool spins for minutes on matrices this small)
+    nu = 700 if f <= 64 else 240
+    X = synth_urm(nu, 260, 0.04, seed=f, values="ratings")
     np.random.seed(f)
     V0 = f ** -0.5 * np.random.random_sample((260, f))
     np.random.seed(f)
     r = IALSRecommender(X, verbose=False)
     r.fit(epochs=2, num_factors=f, alpha=3.0, reg=5e-3)
     C = confidence(X, "linear", 3.0)
-    U, V = np.zeros((700, f)), V0.copy()
-    for _ in range(2):
-        U, V = run_epoch(C, U, V, 5e-3)
+    U, V = np.zeros((nu, f)), V0.copy()
+    with threadpool_limits(limits=1):
+        for _ in range(2):
+            U, V = run_epoch(C, U, V, 5e-3)
     warm = np.diff(X.indptr) > 0
     assert np.allclose(r.USER_factors[warm], U[warm], rtol=1e-4, atol=1e-8), float(np.abs(r.USER_factors - U).max())
     assert np.allclose(r.ITEM_factors, V, rtol=1e-4, atol=1e-8)
