@@ -62,7 +62,7 @@ def test_recommender_save_load(tmp_path):
     folder = str(tmp_path) + "/"
     users = np.arange(40)
     for make, fit_kw in ((ItemKNNCFRecommender, dict(topK=10, shrink=2)), (IALSRecommender, dict(epochs=2, num_factors=8)),
-                         (EASE_R_Recommender, dict(l2_norm=50.0, verbose=False))):
+                         (EASE_R_Recommender, dict(l2_norm=500.0, verbose=False))):
         a = make(X, verbose=False)
         a.fit(**fit_kw)
         a.save_model(folder)
