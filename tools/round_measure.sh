@@ -9,8 +9,10 @@ if [ "${1:-}" != "" ]; then export B200REC_LIB=$PWD/recsys2019_deeplearning_eval
 mkdir -p gpurun_out
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 echo "bench rc=$?"; cat gpurun_out/bench_n1.json | cut -c1-600
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-echo "reference rc=$?"; cat gpurun_out/bench_ref.json | cut -c1-300
+if [ "${SKIP_REF:-0}" != "1" ]; then
+  python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+  echo "reference rc=$?"; cat gpurun_out/bench_ref.json | cut -c1-300
+fi
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/b_ncu.log 2>&1
 echo "launch list rc=$?"
