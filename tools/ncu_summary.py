@@ -1,5 +1,7 @@
 """Text summary of one kernel of an ncu report (headline raw metrics + hottest source lines) for profiles/.
-usage: python tools/ncu_summary.py <report.ncu-rep> <lib.so> <kernel-substring> <title>"""
+usage: python tools/ncu_summary.py <report.ncu-rep> <lib.so> <kernel-substring> <title> [mangled-substring]
+The optional mangled substring (e.g. ILi0ELb1ELb1E for sim_topk_kernel<0, true, true>) picks ONE template instantiation for
+the SASS-offset -> source-line mapping; without it the first instantiation in the cubin is used, which is wrong for the others."""
 import csv, io, subprocess, sys
 rep, lib, kern, title = sys.argv[1:5]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -31,4 +33,4 @@ try:
 except Exception as ex:
     print("traffic: n/a (%r)" % ex)
 print()
-print(subprocess.run([sys.executable, "tools/ncu_lines.py", rep, lib, kern, "18"], capture_output=True, text=True).stdout)
+print(subprocess.run([sys.executable, "tools/ncu_lines.py", rep, lib, kern, "22"] + sys.argv[5:6], capture_output=True, text=True).stdout)
