@@ -16,8 +16,11 @@
 #include <algorithm>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 
 namespace b200 {
 namespace ease {
@@ -92,10 +95,56 @@ __global__ void copy_block_kernel(const float* __restrict__ src, int lds, float*
   dst[(long long)r * ldd + c] = src[(long long)r * lds + c];
 }
 
+// 1 = gemm_tc.cuh (default), 2 = gemm_tc2.cuh (packed operands + bulk copies; opt-in through B200REC_GEMM=2 or the
+// debug entry point until it has been validated on hardware)
+int g_gemm_version = -1;
+int gemm_version() {
+  if (g_gemm_version < 0) {
+    const char* e = getenv("B200REC_GEMM");
+    g_gemm_version = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  return g_gemm_version;
+}
+
+DevBuf<float> g_pack_a, g_pack_b;  // packed-operand workspaces of the v2 path, grown on demand
+
+template <bool TA, bool TB, bool TRI>
+void gemm_v2(cudaStream_t st, int M, int N, int K, float alpha, const float* A, int lda, long long sA, const float* B, int ldb,
+             long long sB, float beta, float* C, int ldc, long long sC, int batch) {
+  const int KC = K / tc::BK, RA = M / tc::BM, RB = N / tc::BN;
+  const long long strideAp = (long long)RA * KC * tc2::PAIR_FLOATS, strideBp = (long long)RB * KC * tc2::PAIR_FLOATS;
+  // op(A) and op(B) are the same memory pattern of the same matrix (L21 L21^T, Linv^T Linv): pack once
+  const bool share = (A == B && lda == ldb && sA == sB && M == N && ((!TA) == TB));
+  const size_t needA = (size_t)batch * (size_t)strideAp, needB = share ? 0 : (size_t)batch * (size_t)strideBp;
+  if (g_pack_a.n < needA || g_pack_b.n < needB) {
+    B200_CUDA(cudaStreamSynchronize(st));  // earlier kernels may still read the old workspaces
+    if (g_pack_a.n < needA) g_pack_a.alloc(needA);
+    if (g_pack_b.n < needB) g_pack_b.alloc(needB);
+  }
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(tc2::tc2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+    configured = true;
+  }
+  tc2::pack_tiles_kernel<!TA><<<dim3(KC, RA, batch), tc2::THREADS, 2 * tc::TILE_BYTES, st>>>(A, lda, sA, g_pack_a.get(), strideAp);
+  count_launch();
+  if (!share) {
+    tc2::pack_tiles_kernel<TB><<<dim3(KC, RB, batch), tc2::THREADS, 2 * tc::TILE_BYTES, st>>>(B, ldb, sB, g_pack_b.get(), strideBp);
+    count_launch();
+  }
+  tc2::tc2_gemm_kernel<<<dim3(RB, RA, batch), tc2::THREADS, tc2::SMEM_BYTES, st>>>(
+      K, TRI ? 1 : 0, alpha, g_pack_a.get(), strideAp, share ? g_pack_a.get() : g_pack_b.get(), share ? strideAp : strideBp, beta, C, ldc, sC);
+  count_launch();
+}
+
 template <bool TA, bool TB, bool TRI>
 void gemm(cudaStream_t st, int M, int N, int K, float alpha, const float* A, int lda, long long sA, const float* B, int ldb,
           long long sB, float beta, float* C, int ldc, long long sC, int batch) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
+  if (gemm_version() == 2) {
+    gemm_v2<TA, TB, TRI>(st, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+    return;
+  }
   static bool configured = false;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(tc::tc_gemm_kernel<TA, TB, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -170,6 +219,35 @@ int b200_spd_inverse_device(float* d_A, int n_pad, float* d_work, void* stream) 
     // ---- 3. A^{-1} = Linv^T * Linv  (k >= max(i, j) only)
     gemm<true, false, true>(st, n_pad, n_pad, n_pad, 1.f, Linv, n_pad, 0, Linv, n_pad, 0, 0.f, d_A, n_pad, 0, 1);
     B200_CUDA(cudaGetLastError());
+  });
+}
+
+// TEST HOOK: one GEMM of the blocked inverse through version 1 (gemm_tc.cuh) or 2 (gemm_tc2.cuh):
+//   kind 0: C = alpha A B^T + beta C   (A [M,K] row-major, B [N,K] row-major)        -- panel / trailing updates
+//   kind 1: C = alpha A B + beta C     (A [M,K] row-major, B [K,N] row-major)        -- factor-inverse blocks
+//   kind 2: C = alpha A^T B + beta C restricted to k >= max(row block, column block) (A [K,M], B [K,N]) -- Linv^T Linv
+// M, N multiples of 128, K a multiple of 32; all pointers on the device.
+int b200_debug_gemm_device(int version, int kind, int M, int N, int K, float alpha, const float* d_A, int lda, const float* d_B,
+                           int ldb, float beta, float* d_C, int ldc, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(version == 1 || version == 2, "b200_debug_gemm: version must be 1 or 2");
+    B200_REQUIRE(kind >= 0 && kind <= 2, "b200_debug_gemm: kind must be 0, 1 or 2");
+    B200_REQUIRE(d_A && d_B && d_C && M > 0 && N > 0 && K > 0 && M % 128 == 0 && N % 128 == 0 && K % 32 == 0,
+                 "b200_debug_gemm: M, N must be multiples of 128 and K of 32");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int saved = gemm_version();
+    g_gemm_version = version;
+    try {
+      if (kind == 0) gemm<false, true, false>(st, M, N, K, alpha, d_A, lda, 0, d_B, ldb, 0, beta, d_C, ldc, 0, 1);
+      else if (kind == 1) gemm<false, false, false>(st, M, N, K, alpha, d_A, lda, 0, d_B, ldb, 0, beta, d_C, ldc, 0, 1);
+      else gemm<true, false, true>(st, M, N, K, alpha, d_A, lda, 0, d_B, ldb, 0, beta, d_C, ldc, 0, 1);
+      B200_CUDA(cudaGetLastError());
+      B200_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+      g_gemm_version = saved;
+      throw;
+    }
+    g_gemm_version = saved;
   });
 }
 

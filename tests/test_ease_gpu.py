@@ -66,3 +66,40 @@ def test_dense_similarity_outputs():
         assert sps.issparse(Wn) and np.allclose(Wn.toarray(), D, rtol=1e-4, atol=1e-9)
     Wk = Compute_Similarity_Cython(X, topK=2100, shrink=3).compute_similarity()  # beyond the selection buffer: dense + top-K
     assert (np.diff(Wk.tocsc().indptr) <= 2100).all() and Wk.nnz > 0
+
+
+def _gemm_case(version, kind, M, N, K, beta):
+    import ctypes
+    import torch
+    from recsys2019_deeplearning_evaluation_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(1000 * kind + M + N + K)
+    shape_a = (M, K) if kind in (0, 1) else (K, M)
+    shape_b = (N, K) if kind == 0 else (K, N)
+    A = torch.randn(shape_a, generator=g, dtype=torch.float32).cuda()
+    B = torch.randn(shape_b, generator=g, dtype=torch.float32).cuda()
+    if kind == 2:  # the L^T L product: operands are lower triangular, so dropping k < max(row, col block) changes nothing
+        A, B = torch.tril(A), torch.tril(B)
+    C0 = torch.randn((M, N), generator=g, dtype=torch.float32).cuda()
+    C = C0.clone()
+    _lib.check(_lib.load().b200_debug_gemm_device(version, kind, M, N, K, 0.75, A.data_ptr(), A.shape[1], B.data_ptr(), B.shape[1],
+                                                  beta, C.data_ptr(), N, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    Ad, Bd = A.double(), B.double()
+    ref = 0.75 * (Ad @ Bd.t() if kind == 0 else (Ad @ Bd if kind == 1 else Ad.t() @ Bd)) + beta * C0.double()
+    err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, (version, kind, M, N, K, beta, err)  # 3xTF32: fp32-level accuracy (a single TF32 pass gives ~3e-4)
+
+
+GEMM_SHAPES = [(0, 384, 128, 128, 0.0), (0, 256, 256, 128, 1.0), (1, 128, 128, 640, 0.0), (2, 512, 512, 512, 0.0)]
+
+
+@pytest.mark.parametrize("kind,M,N,K,beta", GEMM_SHAPES)
+def test_tensor_core_gemm_v1(kind, M, N, K, beta):
+    """The three GEMM shapes of the blocked inverse through the default tcgen05 kernel, against fp64."""
+    _gemm_case(1, kind, M, N, K, beta)
+
+
+@pytest.mark.skipif(os.environ.get("B200REC_TEST_GEMM2") != "1",
+                    reason="gemm_tc2.cuh (packed operands + cp.async.bulk) is opt-in until validated: B200REC_TEST_GEMM2=1")
+@pytest.mark.parametrize("kind,M,N,K,beta", GEMM_SHAPES + [(0, 1024, 1024, 128, 1.0), (2, 2048, 2048, 2048, 0.0)])
+def test_tensor_core_gemm_v2(kind, M, N, K, beta):
+    _gemm_case(2, kind, M, N, K, beta)
