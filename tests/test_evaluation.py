@@ -77,3 +77,30 @@ def test_cuda_evaluates_itemknn_like_the_oracle():
     # near-equal scores may swap between two runs: averaged metrics agree to 1e-4, not bit for bit
     ref = evaluate_scores(train, test, rec._compute_item_score(np.arange(3000)), **kw)
     _assert_close(res, ref, 1e-4, "itemknn")
+
+
+def test_host_side_preprocessing_matches_the_restatement():
+    """CPU: the evaluator's one-off host work -- per-user ideal DCG table and the users_to_evaluate selection -- against
+    per-user loops (metrics.py:268, :277-279; Evaluator.py:199-222)."""
+    from recsys2019_deeplearning_evaluation_b200.evaluation import EvaluatorHoldout, _ideal_dcg
+    train, test, S, kw = eval_case(2)
+    cut = [1, 5, 10, 40]
+    T = test.copy()
+    T.sort_indices()
+    table = _ideal_dcg(T, cut)
+    for u in range(T.shape[0]):
+        rel = np.sort(T.data[T.indptr[u]:T.indptr[u + 1]].astype(np.float64))[::-1]
+        for k, c in enumerate(cut):
+            r = rel[:c]
+            want = np.sum((np.power(2.0, r) - 1) / np.log2(np.arange(len(r), dtype=np.float64) + 2))
+            assert np.isclose(table[u, k], want, rtol=1e-12, atol=1e-12)
+    ev = EvaluatorHoldout(test, verbose=False, **kw)
+    pruned = test.tolil()
+    pruned[:, kw["ignore_items"]] = 0
+    n_left = np.diff(pruned.tocsr().indptr)
+    want_users = [u for u in range(test.shape[0]) if n_left[u] >= 1 and u not in set(kw["ignore_users"])]
+    assert ev.users_to_evaluate == want_users
+    with pytest.raises(ValueError):
+        EvaluatorHoldout([test], [5])
+    with pytest.raises(ValueError):
+        EvaluatorHoldout(test, [5, 2000])
