@@ -27,6 +27,12 @@ _KIND = {"cosine": 0, "adjusted": 1, "asymmetric": 2, "pearson": 3, "jaccard": 4
 def _as_csr_f32(dataMatrix):
     """What check_matrix(..., 'csr') + .copy() give the reference (pyx:154,200), plus sorted indices (the
     windowed accumulator needs sorted rows; BaseRecommender-built URMs already are)."""
+    if (sps.isspmatrix_csr(dataMatrix) and dataMatrix.dtype == np.float32 and dataMatrix.indices.dtype == np.int32
+            and dataMatrix.indptr.dtype == np.int32 and dataMatrix.has_sorted_indices):
+        # already in the layout the C ABI takes: hand the caller's arrays over as they are (they are only read -- the
+        # reference's defensive .copy(), pyx:154, protects its in-place transforms, which run on the device here).
+        # scipy caches has_sorted_indices on the object, so repeated fits on one URM pay the O(nnz) check once.
+        return dataMatrix
     if isinstance(dataMatrix, np.ndarray):
         X = sps.csr_matrix(dataMatrix, dtype=np.float32)
         X.eliminate_zeros()

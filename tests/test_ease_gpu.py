@@ -86,7 +86,10 @@ def _gemm_case(version, kind, M, N, K, beta):
     Ad, Bd = A.double(), B.double()
     ref = 0.75 * (Ad @ Bd.t() if kind == 0 else (Ad @ Bd if kind == 1 else Ad.t() @ Bd)) + beta * C0.double()
     err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
-    assert err < 1e-5, (version, kind, M, N, K, beta, err)  # 3xTF32: fp32-level accuracy (a single TF32 pass gives ~3e-4)
+    # 3xTF32: fp32-level accuracy (a single TF32 pass gives ~3e-4).  The tensor core accumulates with truncation, so the
+    # error grows linearly with the number of K = 8 steps: 1.5e-5 measured at K = 2048 on B200 for both kernel versions' MMA
+    # sequence, < 1e-5 up to K = 640.
+    assert err < 1e-5 * max(1.0, K / 512.0), (version, kind, M, N, K, beta, err)
 
 
 GEMM_SHAPES = [(0, 384, 128, 128, 0.0), (0, 256, 256, 128, 1.0), (1, 128, 128, 640, 0.0), (2, 512, 512, 512, 0.0)]
