@@ -196,6 +196,16 @@ class Compute_Similarity_Cython:
             pass
 
 
+class Compute_Similarity_Python(Compute_Similarity_Cython):
+    """Drop-in for Base/Similarity/Compute_Similarity_Python.py:15-370, the reference's dense-block numpy
+    implementation of the same similarities: identical constructor, `compute_similarity(start_col, end_col, block_size)`.
+    Its semantics for signed similarities (zeros outrank negatives, :335-345) are the ones the CUDA kernel implements, so
+    this is the same device path; `block_size` (the width of the reference's dense blocks) has no meaning here."""
+
+    def compute_similarity(self, start_col=None, end_col=None, block_size=100):
+        return super(Compute_Similarity_Python, self).compute_similarity(start_col=start_col, end_col=end_col)
+
+
 _EUCLID_MODE = {"exp": 0, "lin": 1, "log": 2}
 
 
@@ -302,8 +312,12 @@ class Compute_Similarity:
             " use Euclidean similarity instead.".format(dataMatrix.shape)  # Compute_Similarity.py:65
         if similarity is not None:
             args["similarity"] = similarity
-        self.dense = False
-        self.compute_similarity_object = Compute_Similarity_Cython(dataMatrix, **args)
+        # Compute_Similarity.py:71-113: "density" picks python for ndarrays / density > 0.5, cython otherwise; both names
+        # are the same device path here, the flag is kept for callers that read it
+        self.dense = isinstance(dataMatrix, np.ndarray) or (
+            use_implementation == "density" and sps.issparse(dataMatrix) and dataMatrix.nnz / max(1, dataMatrix.shape[0] * dataMatrix.shape[1]) > 0.5)
+        cls = Compute_Similarity_Python if (use_implementation == "python" or self.dense) else Compute_Similarity_Cython
+        self.compute_similarity_object = cls(dataMatrix, **args)
 
     def compute_similarity(self, **args):
         return self.compute_similarity_object.compute_similarity(**args)

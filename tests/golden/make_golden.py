@@ -312,3 +312,49 @@ def make_dataio_golden():
 
 if __name__ == "__main__":
     make_dataio_golden()
+
+
+def knn_variant_inputs():
+    """URM, ICM (items x features), UCM (users x features) of the KNN-variant golden cases (shared with tests/test_knn_variants.py)."""
+    URM = synth_urm(400, 150, 0.06, seed=17, values="ratings")
+    ICM = synth_urm(150, 60, 0.10, seed=71, values="continuous")
+    UCM = synth_urm(400, 45, 0.12, seed=72, values="ratings")
+    return URM, ICM, UCM
+
+
+KNN_VARIANT_CASES = [("ItemKNNCBFRecommender", dict(topK=8, shrink=1, similarity="cosine", feature_weighting="none")),
+                     ("ItemKNNCBFRecommender", dict(topK=8, shrink=0, similarity="asymmetric", asymmetric_alpha=0.4, feature_weighting="TF-IDF")),
+                     ("UserKNNCBFRecommender", dict(topK=9, shrink=2, similarity="cosine", feature_weighting="BM25")),
+                     ("ItemKNN_CFCBF_Hybrid_Recommender", dict(ICM_weight=2.5, topK=10, shrink=3, similarity="cosine")),
+                     ("UserKNN_CFCBF_Hybrid_Recommender", dict(UCM_weight=0.5, topK=7, shrink=1, similarity="cosine"))]
+
+
+def make_knn_variant_golden():
+    """tests/golden/knn_variants_golden.npz: W_sparse of the reference's CBF / hybrid KNN recommenders and the scores of
+    ItemKNNCustomSimilarityRecommender with selectTopK."""
+    ref_loader.ensure_import_path()
+    ref_loader.load("Compute_Similarity_Cython")
+    import importlib
+    URM, ICM, UCM = knn_variant_inputs()
+    out = {}
+    for n, (name, kw) in enumerate(KNN_VARIANT_CASES):
+        cls = getattr(importlib.import_module("KNN." + name), name)
+        r = cls(URM.copy(), (ICM if name.startswith("Item") else UCM).copy())
+        r.fit(**kw)
+        W = sps.csr_matrix(r.W_sparse)
+        W.sort_indices()
+        out["k%d_indptr" % n], out["k%d_indices" % n], out["k%d_data" % n] = W.indptr, W.indices, W.data
+        out["k%d_scores" % n] = r._compute_item_score(np.arange(25)).astype(np.float32)
+    from KNN.ItemKNNCustomSimilarityRecommender import ItemKNNCustomSimilarityRecommender
+    Wc = sps.random(150, 150, 0.2, format="csr", random_state=9, dtype=np.float32)
+    r = ItemKNNCustomSimilarityRecommender(URM.copy())
+    r.fit(Wc, selectTopK=True, topK=6)
+    W = sps.csr_matrix(r.W_sparse)
+    W.sort_indices()
+    out["custom_indptr"], out["custom_indices"], out["custom_data"] = W.indptr, W.indices, W.data
+    np.savez_compressed(os.path.join(HERE, "knn_variants_golden.npz"), **out)
+    print("wrote knn_variants_golden.npz")
+
+
+if __name__ == "__main__":
+    make_knn_variant_golden()

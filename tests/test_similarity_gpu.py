@@ -171,3 +171,18 @@ def test_binary_counter_widths(monkeypatch):
         assert bp.value == 1 and sim32.n_windows > sim16.n_windows
         monkeypatch.delenv("B200REC_NO_PACK")
         assert abs(W16 - W32).max() < 1e-7 if (W16 - W32).nnz else True
+
+
+def test_python_named_implementation_is_the_same_device_path():
+    """Compute_Similarity(use_implementation='python') / dense inputs (Compute_Similarity.py:71-113, a5) run the same kernel."""
+    from recsys2019_deeplearning_evaluation_b200.similarity import Compute_Similarity, Compute_Similarity_Python
+    X = synth_urm(300, 120, 0.05, seed=12, values="continuous")
+    kw = dict(topK=9, shrink=2, similarity="cosine")
+    a = Compute_Similarity(X, use_implementation="cython", **kw)
+    b = Compute_Similarity(X, use_implementation="python", **kw)
+    c = Compute_Similarity(X.toarray(), **kw)
+    assert isinstance(b.compute_similarity_object, Compute_Similarity_Python) and c.dense
+    Wa, Wb, Wc = a.compute_similarity(), b.compute_similarity(block_size=50), c.compute_similarity()
+    assert abs(Wa - Wb).nnz == 0 and abs(Wa - Wc).nnz == 0
+    with pytest.raises(ValueError):
+        Compute_Similarity(X, use_implementation="numba", **kw)
