@@ -180,7 +180,6 @@ def _ref_worker(conn, X, kind, w):
     from oracle import ref_loader
     t = time.perf_counter()
     if kind == "reference":
-        import io, contextlib
         cls = ref_loader.load("Compute_Similarity_Cython").Compute_Similarity_Cython
         obj = cls(X, **SIM_KW)
     else:
@@ -288,12 +287,10 @@ def run_b200(args, rank, world, local_rank):
         sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
     barrier()
     ev0.record()
     for _ in range(args.steps):
         out = step()
-        kernel_ms.append(None)
     ev1.record()
     barrier()
     launches = _lib.launch_count() - launches0

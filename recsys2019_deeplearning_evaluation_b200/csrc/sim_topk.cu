@@ -65,7 +65,6 @@ constexpr int UB = B200_UB;      // 128-bit loads in flight per lane
 // B200_PREFETCH: while the select group (SELT threads) prunes the finished column, the other threads walk the NEXT
 // column's CSC entries -> row-segment bounds and issue L2 prefetches for those row segments, so that the next column's
 // stage and accumulate phases find their three dependent levels of data in L2 instead of DRAM.
-constexpr int TILE = THREADS * 4;
 constexpr int MAXTILES = 16;
 
 enum Formula { F_PROD = 0, F_NONORM = 1, F_JACCARD = 2, F_DICE = 3, F_TVERSKY = 4, F_SCALE = 5, F_EUCLID = 6 };
@@ -945,7 +944,7 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
   }
 }
 
-// B at the tile boundaries of every window: tileB[w][t] = B[min(w*win + t*TILE, last column of window w)]
+// B at the tile boundaries of every window: tileB[w][t] = B[min(w*win + t*tile, last column of window w)], tile = cells per block-wide scan step
 __global__ void tile_bounds_kernel(const int2* __restrict__ BN, int n_cols, int n_win, int win, int tile, float* tileB) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_win * (MAXTILES + 1)) return;
