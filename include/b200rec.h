@@ -123,6 +123,11 @@ int b200_sim_debug_set_cap(b200_sim_t h, int cap);
  * [6] emit.  enable!=0 turns counting on for later launches; out8 (nullable) receives and resets the counters. */
 int b200_sim_debug_phase_cycles(b200_sim_t h, int enable, uint64_t* out8);
 
+/* TEST HOOK for the opt-in sparse-candidate variant of the binary path (csrc/sim_k1b.cuh, B200REC_K1B=1 at create time):
+ * reports whether the handle uses it and the log2 of its hash-table slots; set_tbits > 0 shrinks the table (the launch then
+ * overflows, sets its flag, and the window kernel recomputes the range -- the fallback under test). */
+int b200_sim_debug_k1b(b200_sim_t h, int set_tbits, int* enabled, int* tbits);
+
 /* duration in milliseconds of the last top-K kernel launched through this handle, measured with CUDA
  * events on the launching stream (bench.py roofline leg) */
 int b200_sim_last_kernel_ms(b200_sim_t h, float* ms);

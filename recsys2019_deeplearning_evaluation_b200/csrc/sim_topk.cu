@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -99,6 +100,13 @@ struct KParams {
   int eu_mode, eu_norm, eu_signed;
   float eu_div, eu_shrink;
   float* dense_out;  // dense mode (TopK == 0 / full Gram): [n_range, n_cols] row-major, out[target - col_begin, neighbour]
+  // K1-B (sim_k1b.cuh): words per bitmap, log2 of the table slots, coarse norm tiles and their bounds, the n_win = 1 padded
+  // row layout, and the "table overflowed" flag
+  int bm_words, tbits, ncb;
+  const float* __restrict__ cb;
+  const int* __restrict__ csr_idx1;
+  const int* __restrict__ split1;
+  int* fail;
   unsigned long long* prof;  // optional [8] per-phase cycle counters (thread 0 of every CTA), test/bench hook
 };
 
@@ -954,6 +962,8 @@ __global__ void tile_bounds_kernel(const int2* __restrict__ BN, int n_cols, int 
   tileB[g] = __int_as_float(BN[j].x);
 }
 
+#include "sim_k1b.cuh"
+
 // ------------------------------------------------------------------------------------------------------
 // preprocessing kernels (constructor work of pyx:147-209, on the device)
 // ------------------------------------------------------------------------------------------------------
@@ -1172,6 +1182,12 @@ struct b200_sim_s {
   DevBuf<int2> csr_ent, csc_ent, BN;
   DevBuf<float> A, tileB;
   int lpu_log2 = 3;
+  // K1-B (opt-in, binary path): second row layout with one window, coarse norm bounds, table geometry
+  bool want_k1b = false, k1b = false;
+  DevBuf<int> csr_idx1, split1, fail;
+  DevBuf<float> cb;
+  int bm_words = 0, tbits = 0, ncb = 0, lpu1_log2 = 3;
+  size_t smem1_bytes = 0;
   std::vector<unsigned long long> h_work;  // by ORIGINAL column index
   DevBuf<int> counter, order;
   std::vector<int> h_order;  // cached LPT order for [order_lo, order_hi)
@@ -1202,6 +1218,16 @@ sim_kernel_t kernel_for(int formula, bool binary, bool pack) {
     case F_SCALE: return sim_topk_kernel<F_SCALE, false, false>;
     case F_EUCLID: return kernel_of<F_EUCLID>(binary, pack);
     default: return kernel_of<F_TVERSKY>(binary, pack);
+  }
+}
+
+sim_kernel_t k1b_kernel_for(int formula) {
+  switch (formula) {
+    case F_PROD: return sim_k1b_kernel<F_PROD>;
+    case F_NONORM: return sim_k1b_kernel<F_NONORM>;
+    case F_JACCARD: return sim_k1b_kernel<F_JACCARD>;
+    case F_DICE: return sim_k1b_kernel<F_DICE>;
+    default: return sim_k1b_kernel<F_TVERSKY>;
   }
 }
 
@@ -1434,6 +1460,26 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
     seg_pad_kernel<<<div_up(n_seg * 8, 256), 256, 0, st>>>(h->split.get(), h->csr_idx.get(), poff.get(), n_seg, n_win, win, total_pad,
                                                           idx_pad.get(), split_pad.get()); count_launch();
     B200_CUDA(cudaStreamSynchronize(st));
+    if (h->want_k1b && nnz > 0) {
+      // the same rows once more as ONE window: whole rows padded to 16-byte chunks with the index win1 (>= n_cols)
+      const int win1 = ((n_cols + 7) / 8) * 8;
+      DevBuf<int> sp1((size_t)n_rows * 2), len1((size_t)n_rows + 1), poff1((size_t)n_rows + 1);
+      split_kernel<<<div_up((long long)n_rows * 2, 256), 256, 0, st>>>(h->csr_ptr.get(), h->csr_idx.get(), n_rows, 1, win1, sp1.get()); count_launch();
+      B200_CUDA(cudaMemsetAsync(len1.get() + n_rows, 0, sizeof(int), st));
+      seg_len_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(sp1.get(), n_rows, 1, len1.get()); count_launch();
+      size_t tb1 = 0;
+      B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb1, len1.get(), poff1.get(), n_rows + 1, st));
+      DevBuf<unsigned char> tmp1(tb1 + 16);
+      B200_CUDA(cub::DeviceScan::ExclusiveSum(tmp1.get(), tb1, len1.get(), poff1.get(), n_rows + 1, st)); count_launch();
+      int total1 = 0;
+      B200_CUDA(cudaMemcpyAsync(&total1, poff1.get() + n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaStreamSynchronize(st));
+      h->csr_idx1.alloc((size_t)total1 + 8);
+      h->split1.alloc((size_t)n_rows * 2);
+      seg_pad_kernel<<<div_up((long long)n_rows * 8, 256), 256, 0, st>>>(sp1.get(), h->csr_idx.get(), poff1.get(), n_rows, 1, win1, total1,
+                                                                        h->csr_idx1.get(), h->split1.get()); count_launch();
+      B200_CUDA(cudaStreamSynchronize(st));
+    }
     h->csr_idx = std::move(idx_pad);
     h->split = std::move(split_pad);
   }
@@ -1454,6 +1500,41 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   if (!h->binary) h->csr_idx.release();  // the AoS copy carries the indices
   h->counter.alloc(1);
   h->order.alloc((size_t)n_cols);
+  // ---- K1-B geometry and eligibility (sim_k1b.cuh)
+  h->k1b = false;
+  const bool f_ok = h->formula == F_PROD || h->formula == F_NONORM || h->formula == F_JACCARD || h->formula == F_DICE ||
+                    (h->formula == F_TVERSKY && h->ta >= 0.f && h->tb >= 0.f);
+  if (h->want_k1b && h->binary && f_ok && h->csr_idx1.n > 0) {
+    const int win1 = ((n_cols + 7) / 8) * 8;
+    h->ncb = (n_cols + (1 << CB_LOG2) - 1) >> CB_LOG2;
+    h->bm_words = (((win1 + 32 + 31) / 32) + 3) / 4 * 4;
+    const long long fixed = 2ll * h->bm_words * 4 + (long long)h->cap_alloc * 8 + staging + (2ll * h->ncb + 2) * 4 + (long long)sizeof(Shared) + 1024;
+    const long long avail = (long long)max_smem - fixed;
+    int tbits = 0;
+    while (tbits < 16 && (8ll << (tbits + 1)) <= avail) ++tbits;
+    if (tbits >= 12 && h->ncb <= THREADS) {
+      const double T = (double)(1 << tbits);
+      double worst = 0.0;  // expected cells hit at least twice in one column if its gathered entries spread uniformly
+      for (int c = 0; c < n_cols; ++c) {
+        const double lam = (double)h->h_work[(size_t)c] / (double)n_cols;
+        worst = std::max(worst, (double)n_cols * (1.0 - std::exp(-lam) * (1.0 + lam)));
+      }
+      if (2.0 * worst <= 0.625 * T) {
+        h->tbits = tbits;
+        h->smem1_bytes = (size_t)(2ll * h->bm_words * 4 + (8ll << tbits) + (long long)h->cap_alloc * 8 + staging + (2ll * h->ncb + 2) * 4);
+        h->cb.alloc((size_t)h->ncb + 1);
+        coarse_bounds_kernel<<<div_up(h->ncb + 1, 128), 128, 0, st>>>(h->BN.get(), n_cols, h->ncb, h->cb.get()); count_launch();
+        h->fail.alloc(1);
+        const double chunks = (nnz > 0 ? (double)nnz / (double)n_rows : 1.0) / 4.0 + 1.0;
+        int l2 = 1;
+        while (l2 < 5 && (1 << l2) < chunks) ++l2;
+        h->lpu1_log2 = l2;
+        B200_CUDA(cudaStreamSynchronize(st));
+        h->k1b = true;
+      }
+    }
+  }
+  if (!h->k1b) { h->csr_idx1.release(); h->split1.release(); }
 }
 
 }  // namespace
@@ -1477,6 +1558,7 @@ int b200_sim_create(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz
     B200_REQUIRE(h_indptr && (nnz == 0 || (h_indices && h_data)), "b200_sim_create: NULL input array");
     h = new b200_sim_s();
     h->allow_pack = getenv("B200REC_NO_PACK") == nullptr;  // test hook: force 32-bit counters on the binary path
+    h->want_k1b = getenv("B200REC_K1B") != nullptr && atoi(getenv("B200REC_K1B")) == 1;  // opt-in sparse-candidate kernel
     h->n_rows = (int)n_rows;
     h->n_cols = (int)n_cols;
     h->nnz = nnz;
@@ -1603,7 +1685,30 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   p.eu_shrink = h->shrink;
   p.dense_out = d_dense;
   p.prof = h->prof_on ? h->prof.get() : nullptr;
+  p.bm_words = h->bm_words; p.tbits = h->tbits; p.ncb = h->ncb; p.cb = h->cb.get();
+  p.csr_idx1 = h->csr_idx1.get(); p.split1 = h->split1.get(); p.fail = h->fail.get();
   const int grid = std::min(n_range, h->n_sm);
+  if (h->k1b && d_dense == nullptr) {
+    // sparse-candidate kernel first; a table overflow anywhere discards the launch and the window kernel redoes the range
+    B200_CUDA(cudaMemsetAsync(h->fail.get(), 0, sizeof(int), st));
+    KParams q = p;
+    q.lpu_log2 = h->lpu1_log2;
+    sim_kernel_t k1 = k1b_kernel_for(h->formula);
+    B200_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem1_bytes));
+    B200_CUDA(cudaEventRecord(h->ev0, st));
+    k1<<<grid, THREADS, h->smem1_bytes, st>>>(q);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaEventRecord(h->ev1, st));
+    count_launch();
+    int failed = 0;
+    B200_CUDA(cudaMemcpyAsync(&failed, h->fail.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (!failed) {
+      h->timed = true;
+      return;
+    }
+    B200_CUDA(cudaMemsetAsync(h->counter.get(), 0, sizeof(int), st));
+  }
   B200_CUDA(cudaEventRecord(h->ev0, st));
   kernel_for(h->formula, h->binary, h->pack)<<<grid, THREADS, h->smem_bytes, st>>>(p);
   B200_CUDA(cudaGetLastError());
@@ -1675,6 +1780,18 @@ int b200_sim_debug_phase_cycles(b200_sim_t h, int enable, uint64_t* out8) {
       B200_CUDA(cudaMemset(h->prof.get(), 0, 8 * sizeof(unsigned long long)));
     }
     h->prof_on = enable != 0;
+  });
+}
+
+int b200_sim_debug_k1b(b200_sim_t h, int set_tbits, int* enabled, int* tbits) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr, "b200_sim_debug_k1b: NULL handle");
+    if (set_tbits > 0 && h->k1b) {
+      B200_REQUIRE(set_tbits >= 6 && set_tbits <= h->tbits, "b200_sim_debug_k1b: tbits must be in [6, %d]", h->tbits);
+      h->tbits = set_tbits;  // the allocation keeps its size; a smaller table only overflows earlier
+    }
+    if (enabled) *enabled = h->k1b ? 1 : 0;
+    if (tbits) *tbits = h->k1b ? h->tbits : 0;
   });
 }
 
