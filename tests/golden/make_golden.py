@@ -315,7 +315,7 @@ if __name__ == "__main__":
 
 
 def knn_variant_inputs():
-    """URM, ICM (items x features), UCM (users x features) of the KNN-variant golden cases (shared with tests/test_knn_variants.py)."""
+    """URM, ICM (items x features), UCM (users x features) of the KNN-variant golden cases (shared with tests/test_z_knn_variants.py)."""
     URM = synth_urm(400, 150, 0.06, seed=17, values="ratings")
     ICM = synth_urm(150, 60, 0.10, seed=71, values="continuous")
     UCM = synth_urm(400, 45, 0.12, seed=72, values="ratings")
