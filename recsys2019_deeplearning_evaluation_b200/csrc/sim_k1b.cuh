@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(THREADS, 1) sim_k1b_kernel(const KParams p) {
       }
       ub += THREADS;
       const int sidx = s0 + tid;
-      const int k2 = keys[sidx];
+      const int k2 = sidx < T ? keys[sidx] : -1;  // T < THREADS only under the debug hook
       if (k2 >= 0) {
         const float d = (float)(cnts[sidx] + 1);
         keys[sidx] = -1;
