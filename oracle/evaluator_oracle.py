@@ -13,7 +13,9 @@ def _dcg(scores):  # metrics.py:277-279
 
 
 def evaluate_scores(URM_train, URM_test, S, cutoff_list, min_ratings_per_user=1, exclude_seen=True, ignore_items=None,
-                    ignore_users=None):
+                    ignore_users=None, URM_test_negative=None):
+    """URM_test_negative given: EvaluatorNegativeItemSample (Evaluator.py:466-578) -- every user is ranked over her test items
+    plus her negative items only; otherwise EvaluatorHoldout."""
     URM_train = sps.csr_matrix(URM_train)
     T = sps.csr_matrix(URM_test, dtype=np.float64).copy()
     T.eliminate_zeros()  # metrics.py:375 (in place on the evaluator's own matrix, before any user is scored)
@@ -27,6 +29,10 @@ def evaluate_scores(URM_train, URM_test, S, cutoff_list, min_ratings_per_user=1,
     pruned.eliminate_zeros()
     users = np.flatnonzero(np.ediff1d(sps.csr_matrix(pruned).indptr) >= min_ratings_per_user)  # :204-214
     users = np.array(sorted(set(users.tolist()) - set(ignore_users_arr.tolist())), dtype=np.int64)  # :216-222
+    rank_items = None
+    if URM_test_negative is not None:  # Evaluator.py:497-499
+        rank_items = sps.csr_matrix(T.astype(bool)) + sps.csr_matrix(sps.csr_matrix(URM_test_negative).astype(bool))
+        rank_items.eliminate_zeros()
     pop = np.ediff1d(sps.csc_matrix(URM_train).indptr).astype(np.float64)
     n_inter = pop.sum()
     pop_norm = pop / pop.max()
@@ -40,6 +46,10 @@ def evaluate_scores(URM_train, URM_test, S, cutoff_list, min_ratings_per_user=1,
         if exclude_seen:
             s[URM_train.indices[URM_train.indptr[u]:URM_train.indptr[u + 1]]] = -np.inf  # BaseRecommender.py:166-169
         s[ignore_items] = -np.inf  # :192-193
+        if rank_items is not None:  # Evaluator.py:555-563, BaseSimilarityMatrixRecommender.py:84-90: the other items score -inf
+            keep = np.zeros(n_items, bool)
+            keep[rank_items.indices[rank_items.indptr[u]:rank_items.indptr[u + 1]]] = True
+            s[~keep] = -np.inf
         order = np.lexsort((np.arange(n_items), -s))[:max_cutoff]
         rec = order[np.isfinite(s[order])]  # :203-207
         rel_items = T.indices[T.indptr[u]:T.indptr[u + 1]]

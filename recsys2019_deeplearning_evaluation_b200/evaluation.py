@@ -9,8 +9,9 @@ and its top-`max_cutoff` table stay on the device (recommenders.BaseRecommender.
 and `b200_eval_accumulate_device` (csrc/eval.cu) reduces all per-user metrics of :336-366 into device accumulators;
 the host only combines the final sums and the per-item recommendation counters (O(n_items) once per evaluation).
 
-Not mirrored: `diversity_object` (DIVERSITY_SIMILARITY needs an item-similarity matrix, metrics.py:719-775) and
-EvaluatorNegativeItemSample (Evaluator.py:464-578).
+`EvaluatorNegativeItemSample` (Evaluator.py:466-578) is the same pipeline with one user per step and the user's candidate set
+(test items + sampled negatives) passed through the items_to_compute mask.
+Not mirrored: `diversity_object` (DIVERSITY_SIMILARITY needs an item-similarity matrix, metrics.py:719-775).
 """
 import ctypes
 
@@ -136,6 +137,11 @@ class EvaluatorHoldout(object):
             hit=torch.zeros((len(self.cutoff_list), self.n_items), dtype=torch.int32, device=dev))
         return st
 
+    def _blocks(self, users, block_size):
+        """(user ids of one block, items_to_compute or None): hold-out evaluation scores whole blocks of users (:426-455)."""
+        for b0 in range(0, len(users), block_size):
+            yield users[b0:b0 + block_size], None
+
     def evaluateRecommender(self, recommender_object, block_size=None):
         """Evaluator.py:240-288 + :413-461."""
         import torch
@@ -147,9 +153,10 @@ class EvaluatorHoldout(object):
         st = self._device_state(recommender_object.get_URM_train())
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         cutoff = int(min(self.max_cutoff, self.n_items))
-        for b0 in range(0, len(users), block_size):
-            d_users = recommender_object._users_tensor(users[b0:b0 + block_size])
+        for block_users, items_to_compute in self._blocks(users, block_size):
+            d_users = recommender_object._users_tensor(block_users)
             scores = recommender_object._masked_scores_device(d_users, remove_seen_flag=self.exclude_seen,
+                                                              items_to_compute=items_to_compute,
                                                               remove_custom_items_flag=self.ignore_items_flag)
             items, vals = recommender_object._topn_device(scores, cutoff)
             _lib.check(self._lib.b200_eval_accumulate_device(
@@ -200,3 +207,29 @@ class EvaluatorHoldout(object):
         if self.ignore_items_flag:
             recommender_object.reset_items_to_ignore()
         return results_dict, get_result_string(results_dict)
+
+
+class EvaluatorNegativeItemSample(EvaluatorHoldout):
+    """Base/Evaluation/Evaluator.py:466-578: every user is ranked over HER test items plus her sampled negative items only
+    (the protocol of the NeuMF-style experiments).  Same device pipeline as the hold-out evaluator, one user per step like
+    the reference (:553-571), the per-user candidate set going through the items_to_compute mask of the score block."""
+    EVALUATOR_NAME = "EvaluatorNegativeItemSample"
+
+    def __init__(self, URM_test_list, URM_test_negative, cutoff_list, min_ratings_per_user=1, exclude_seen=True,
+                 diversity_object=None, ignore_items=None, ignore_users=None, verbose=True):
+        super(EvaluatorNegativeItemSample, self).__init__(URM_test_list, cutoff_list, min_ratings_per_user=min_ratings_per_user,
+                                                          exclude_seen=exclude_seen, diversity_object=diversity_object,
+                                                          ignore_items=ignore_items, ignore_users=ignore_users, verbose=verbose)
+        rank = sps.csr_matrix(self.URM_test.astype(bool)) + sps.csr_matrix(sps.csr_matrix(URM_test_negative).astype(bool))  # :497
+        rank.eliminate_zeros()
+        rank.sort_indices()
+        self.URM_items_to_rank = rank
+
+    def _get_user_specific_items_to_compute(self, user_id):
+        r = self.URM_items_to_rank
+        return r.indices[r.indptr[user_id]:r.indptr[user_id + 1]]
+
+    def _blocks(self, users, block_size):
+        for u in users:
+            yield np.atleast_1d(u), self._get_user_specific_items_to_compute(int(u))
+

@@ -358,3 +358,50 @@ def make_knn_variant_golden():
 
 if __name__ == "__main__":
     make_knn_variant_golden()
+
+
+def eval_negative_case():
+    """Inputs of the negative-item-sample evaluator golden case: eval_case(0) plus 30 sampled negatives per user."""
+    train, test, S, _ = eval_case(0)
+    rng = np.random.default_rng(77)
+    neg = sps.lil_matrix(test.shape, dtype=np.float32)
+    seen = (train + test).tocsr()
+    for u in range(test.shape[0]):
+        cand = np.setdiff1d(np.arange(test.shape[1]), seen.indices[seen.indptr[u]:seen.indptr[u + 1]])
+        neg[u, rng.choice(cand, size=min(30, len(cand)), replace=False)] = 1.0
+    return train, test, sps.csr_matrix(neg.tocsr(), dtype=np.float32), S, dict(cutoff_list=[1, 5, 10])
+
+
+def make_evaluator_negative_golden():
+    """tests/golden/evaluator_negative_golden.npz: the reference's EvaluatorNegativeItemSample on the stub recommender."""
+    ref_loader.ensure_import_path()
+    from Base.BaseRecommender import BaseRecommender
+    from Base.Evaluation.Evaluator import EvaluatorNegativeItemSample
+
+    class Stub(BaseRecommender):
+        RECOMMENDER_NAME = "Stub"
+
+        def __init__(self, URM_train, S):
+            super(Stub, self).__init__(URM_train)
+            self.S = S
+
+        def _compute_item_score(self, user_id_array, items_to_compute=None):
+            s = self.S[np.asarray(user_id_array)].astype(np.float32).copy()
+            if items_to_compute is not None:  # BaseSimilarityMatrixRecommender.py:84-90
+                out = -np.ones_like(s) * np.inf
+                out[:, items_to_compute] = s[:, items_to_compute]
+                s = out
+            return s
+
+    train, test, neg, S, kw = eval_negative_case()
+    res, _ = EvaluatorNegativeItemSample(test, neg, **kw).evaluateRecommender(Stub(train, S))
+    out = {}
+    for c, d in res.items():
+        for k, v in d.items():
+            out["c%d_%s" % (c, k)] = np.float64(v)
+    np.savez_compressed(os.path.join(HERE, "evaluator_negative_golden.npz"), **out)
+    print("wrote evaluator_negative_golden.npz")
+
+
+if __name__ == "__main__":
+    make_evaluator_negative_golden()

@@ -104,3 +104,17 @@ def test_host_side_preprocessing_matches_the_restatement():
         EvaluatorHoldout([test], [5])
     with pytest.raises(ValueError):
         EvaluatorHoldout(test, [5, 2000])
+
+
+# ------------------------------------------------------------------ EvaluatorNegativeItemSample (Evaluator.py:466-578)
+eval_negative_case = runpy.run_path(os.path.join(HERE, "golden", "make_golden.py"), run_name="cases")["eval_negative_case"]
+ZN = np.load(os.path.join(HERE, "golden", "evaluator_negative_golden.npz"))
+
+
+def _golden_negative(cutoffs):
+    return {c: {k.split("_", 1)[1]: float(ZN[k]) for k in ZN.files if k.startswith("c%d_" % c)} for c in cutoffs}
+
+
+def test_negative_sample_oracle_matches_reference_golden():
+    train, test, neg, S, kw = eval_negative_case()
+    _assert_close(evaluate_scores(train, test, S, URM_test_negative=neg, **kw), _golden_negative(kw["cutoff_list"]), 1e-9, "oracle")

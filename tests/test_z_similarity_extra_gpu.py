@@ -54,3 +54,12 @@ def test_sparse_candidate_kernel_k1b(monkeypatch):
     # skewed popularity: not eligible (or overflowing) -> still exact through the window kernel
     Xs = synth_urm(30_000, 2_000, 0.01, seed=13, values="binary", popularity=1.1)
     _check(Xs, cols=np.arange(0, 2000, 13), topK=100, shrink=10, similarity="cosine")
+
+
+def test_negative_item_sample_evaluator_matches_reference_golden():
+    """EvaluatorNegativeItemSample on the device pipeline (one user per step, candidate set through items_to_compute)."""
+    import test_evaluation as TE
+    from recsys2019_deeplearning_evaluation_b200.evaluation import EvaluatorNegativeItemSample
+    train, test, neg, S, kw = TE.eval_negative_case()
+    res, _ = EvaluatorNegativeItemSample(test, neg, verbose=False, **kw).evaluateRecommender(TE._stub(train, S))
+    TE._assert_close(res, TE._golden_negative(kw["cutoff_list"]), 1e-6, "cuda negative-sample")
