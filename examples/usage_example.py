@@ -2,7 +2,7 @@
 the evaluators, fit a few recommenders with fit(**hyperparameters), evaluate, save and reload a model -- with the hot
 loops on a B200 and a synthetic data set instead of the Movielens1M reader (no network here).
 
-    python examples/run_example_usage.py
+    python examples/usage_example.py
 """
 import os
 import sys
