@@ -149,3 +149,20 @@ def test_sync_owned_rows_gloo_world2():
     want[0], want[2], want[3], want[4], want[5] = 10.0, 12.0, 13.0, 24.0, -7.0
     for rank, X in res:
         assert np.array_equal(X, want)
+
+
+def test_check_matrix_formats_and_dtypes():
+    """Base/Recommender_utils.py:13-52 semantics of the host helper."""
+    import scipy.sparse as sps
+    from recsys2019_deeplearning_evaluation_b200.recommender_utils import check_matrix
+    D = np.array([[1.0, 0.0, 2.5], [0.0, 0.0, 3.0]])
+    C = sps.csr_matrix(D)
+    for fmt, cls in (("csc", sps.csc_matrix), ("csr", sps.csr_matrix), ("coo", sps.coo_matrix), ("lil", sps.lil_matrix)):
+        out = check_matrix(C, fmt)
+        assert isinstance(out, cls) and out.dtype == np.float32 and np.array_equal(out.toarray(), D.astype(np.float32))
+        out = check_matrix(D, fmt, dtype=np.float64)  # ndarray in: sparse out, explicit zeros dropped
+        assert isinstance(out, cls) and out.dtype == np.float64 and out.nnz == 3
+    same = check_matrix(C, "csr", dtype=np.float64)
+    assert isinstance(same, sps.csr_matrix) and same.dtype == np.float64
+    assert isinstance(check_matrix(C, "npy"), np.ndarray) and check_matrix(C, "npy").dtype == np.float32
+    assert np.array_equal(check_matrix(D, "npy"), D)

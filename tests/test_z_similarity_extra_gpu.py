@@ -63,3 +63,20 @@ def test_negative_item_sample_evaluator_matches_reference_golden():
     train, test, neg, S, kw = TE.eval_negative_case()
     res, _ = EvaluatorNegativeItemSample(test, neg, verbose=False, **kw).evaluateRecommender(TE._stub(train, S))
     TE._assert_close(res, TE._golden_negative(kw["cutoff_list"]), 1e-6, "cuda negative-sample")
+
+
+def test_similarity_matrix_topk_reference_recipes():
+    """Base/Recommender_utils_Test.py:18-50 through recommender_utils.similarityMatrixTopK: k non-zeros per column on a dense
+    input, and dense input == sparse input."""
+    import scipy.sparse as sps
+    from recsys2019_deeplearning_evaluation_b200.recommender_utils import similarityMatrixTopK
+    rng = np.random.default_rng(4)
+    dense = rng.random((100, 100)).astype(np.float32)
+    out = similarityMatrixTopK(dense, k=20)
+    assert sps.isspmatrix_csc(out) and (out.toarray() != 0).sum() == 20 * 100
+    small = rng.random((20, 20)).astype(np.float32)
+    a = similarityMatrixTopK(small, k=5).toarray()
+    b = similarityMatrixTopK(sps.csc_matrix(small), k=5).toarray()
+    assert np.allclose(a, b)
+    kept = np.sort(small, axis=0)[-5:, :]
+    assert np.allclose(np.sort(a, axis=0)[-5:, :], kept)
