@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ials_rows_tc_kernel(const int* 
                                                                      double reg, double* X, int* info, int* redo, int n_refine) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t s_tmem_base;
-  __shared__ double s_norm[2];
+  __shared__ double s_norm[3];  // |r|^2 before the last / the first correction, |b|^2
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* tiles = smem;                                             // TC_STAGES x {A_hi, A_lo, B_hi, B_lo}
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * 4 * tc::TILE_BYTES);
@@ -236,8 +236,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ials_rows_tc_kernel(const int* 
           for (int m = lane; m < f; m += 32) r2 += rs[m] * rs[m];
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+          double b2 = 0.0;
+          for (int m = lane; m < f; m += 32) b2 += b0[m] * b0[m];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) b2 += __shfl_xor_sync(0xffffffffu, b2, off);
           if (lane == 0) {
-            if (it == 0) s_norm[1] = r2;
+            if (it == 0) { s_norm[1] = r2; s_norm[2] = b2; }
             if (it == n_refine - 1) s_norm[0] = r2;
           }
           __syncwarp();
@@ -251,7 +255,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ials_rows_tc_kernel(const int* 
     // the refinement contracts the error by ~cond x (Gram error) per step: the residual must have shrunk at least tenfold
     // between the first and the last correction, otherwise the approximate factor is too far from the exact operator for this
     // row (ill-conditioned system) and the fp64 path has to redo the half epoch
-    if (n_refine >= 2 && tid == 0 && !(s_norm[0] <= 1e-2 * s_norm[1])) atomicExch(redo, 1);
+    // (or be at the rounding floor of the exact operator already, as for tiny systems whose 3xTF32 Gram is exact)
+    if (n_refine >= 2 && tid == 0 && !(s_norm[0] <= 1e-2 * s_norm[1] || s_norm[0] <= 1e-22 * s_norm[2])) atomicExch(redo, 1);
     if (tid < f) X[(size_t)row * f + tid] = xs[tid];
     __syncthreads();
   }
