@@ -252,11 +252,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ials_rows_tc_kernel(const int* 
       if (tid < f) xs[tid] += rs[tid];
       __syncthreads();
     }
-    // the refinement contracts the error by ~cond x (Gram error) per step: the residual must have shrunk at least tenfold
+    // the refinement contracts the error by rho ~ cond x (Gram error) per step and the unrefined error is ~rho too, so after two
+    // steps the error is ~rho^3: rho <= 0.03 keeps it below 3e-5.  The residual must therefore have shrunk at least 30-fold
     // between the first and the last correction, otherwise the approximate factor is too far from the exact operator for this
     // row (ill-conditioned system) and the fp64 path has to redo the half epoch
     // (or be at the rounding floor of the exact operator already, as for tiny systems whose 3xTF32 Gram is exact)
-    if (n_refine >= 2 && tid == 0 && !(s_norm[0] <= 1e-2 * s_norm[1] || s_norm[0] <= 1e-22 * s_norm[2])) atomicExch(redo, 1);
+    if (n_refine >= 2 && tid == 0 && !(s_norm[0] <= 1e-3 * s_norm[1] || s_norm[0] <= 1e-22 * s_norm[2])) atomicExch(redo, 1);
     if (tid < f) X[(size_t)row * f + tid] = xs[tid];
     __syncthreads();
   }
