@@ -37,7 +37,10 @@ struct Params {
   float gamma, beta1, beta2;
   double b1_pow, b2_pow;  // adam powers at the start of the epoch
   float *U, *V, *bu, *bi, *mu;
-  float *accU, *accV, *accbu, *accbi, *accmu;
+  // batch gradient sums are fp64 like pyx:305-354: a double atomic sum is order-independent to ~1e-16 relative, so the
+  // mini-batch mode is run-to-run deterministic at the fp32 precision of the parameters (fp32 RED.ADD was not: the
+  // summation order of a row's samples changed the rounded sum, and Adam's m/(sqrt(v)+eps) amplified it)
+  double *accU, *accV, *accbu, *accbi, *accmu;
   float *cU, *cV, *cbu, *cbi, *cmu;                                    // adagrad / rmsprop cache
   float *m1U, *m2U, *m1V, *m2V, *m1bu, *m2bu, *m1bi, *m2bi, *m1mu, *m2mu;  // adam
   int *flagI, *flagU, *listI, *listU, *cnt;  // cnt[4]: items/users counters, double-buffered by batch parity
@@ -108,27 +111,15 @@ __device__ __forceinline__ void bpr_accumulate(const Params& p, int u, int i, in
   }
   x = warp_sum(x);
   const float sig = 1.f / (1.f + expf(x));  // pyx:622
-  float* aU = p.accU + (size_t)u * f;
-  float* aI = p.accV + (size_t)i * f;
-  float* aJ = p.accV + (size_t)j * f;
-  if (VEC4) {
-    for (int q = lane * 4; q < f; q += 128) {
-      const float4 a = *reinterpret_cast<const float4*>(Uu + q), b = *reinterpret_cast<const float4*>(Vi + q),
-                   c = *reinterpret_cast<const float4*>(Vj + q);
-      red_add4(aI + q, make_float4(sig * a.x - p.positive_reg * b.x, sig * a.y - p.positive_reg * b.y,
-                                   sig * a.z - p.positive_reg * b.z, sig * a.w - p.positive_reg * b.w));
-      red_add4(aJ + q, make_float4(-sig * a.x - p.negative_reg * c.x, -sig * a.y - p.negative_reg * c.y,
-                                   -sig * a.z - p.negative_reg * c.z, -sig * a.w - p.negative_reg * c.w));
-      red_add4(aU + q, make_float4(sig * (b.x - c.x) - p.user_reg * a.x, sig * (b.y - c.y) - p.user_reg * a.y,
-                                   sig * (b.z - c.z) - p.user_reg * a.z, sig * (b.w - c.w) - p.user_reg * a.w));
-    }
-  } else {
-    for (int q = lane; q < f; q += 32) {
-      const float a = Uu[q], b = Vi[q], c = Vj[q];
-      atomicAdd(aI + q, sig * a - p.positive_reg * b);   // pyx:633
-      atomicAdd(aJ + q, -sig * a - p.negative_reg * c);  // pyx:634
-      atomicAdd(aU + q, sig * (b - c) - p.user_reg * a); // pyx:635
-    }
+  double* aU = p.accU + (size_t)u * f;
+  double* aI = p.accV + (size_t)i * f;
+  double* aJ = p.accV + (size_t)j * f;
+  const double sg = (double)sig, rp = (double)p.positive_reg, rn = (double)p.negative_reg, ru = (double)p.user_reg;
+  for (int q = lane; q < f; q += 32) {  // consecutive lanes -> consecutive 8-byte RED.ADD.F64 (coalesced)
+    const double a = (double)Uu[q], b = (double)Vi[q], c = (double)Vj[q];
+    atomicAdd(aI + q, sg * a - rp * b);        // pyx:633
+    atomicAdd(aJ + q, -sg * a - rn * c);       // pyx:634
+    atomicAdd(aU + q, sg * (b - c) - ru * a);  // pyx:635
   }
 }
 
@@ -149,50 +140,42 @@ __device__ __forceinline__ void mse_accumulate(const Params& p, int u, int i, fl
   x = warp_sum(x);
   if (p.use_bias) x += p.mu[0] + p.bu[u] + p.bi[i];  // pyx:313-316
   const float err = r - x;
+  const double er = (double)err;
   if (p.use_bias && lane == 0) {  // pyx:332-339
-    atomicAdd(p.accmu, err - p.bias_reg * p.mu[0]);
-    atomicAdd(p.accbi + i, err - p.bias_reg * p.bi[i]);
-    atomicAdd(p.accbu + u, err - p.bias_reg * p.bu[u]);
+    const double rb = (double)p.bias_reg;
+    atomicAdd(p.accmu, er - rb * (double)p.mu[0]);
+    atomicAdd(p.accbi + i, er - rb * (double)p.bi[i]);
+    atomicAdd(p.accbu + u, er - rb * (double)p.bu[u]);
   }
-  float* aU = p.accU + (size_t)u * f;
-  float* aI = p.accV + (size_t)i * f;
-  if (VEC4) {
-    for (int q = lane * 4; q < f; q += 128) {
-      const float4 a = *reinterpret_cast<const float4*>(Uu + q), b = *reinterpret_cast<const float4*>(Vi + q);
-      // item regulariser is positive_reg, not item_reg (pyx:349)
-      red_add4(aI + q, make_float4(err * a.x - p.positive_reg * b.x, err * a.y - p.positive_reg * b.y,
-                                   err * a.z - p.positive_reg * b.z, err * a.w - p.positive_reg * b.w));
-      red_add4(aU + q, make_float4(err * b.x - p.user_reg * a.x, err * b.y - p.user_reg * a.y,
-                                   err * b.z - p.user_reg * a.z, err * b.w - p.user_reg * a.w));
-    }
-  } else {
-    for (int q = lane; q < f; q += 32) {
-      const float a = Uu[q], b = Vi[q];
-      atomicAdd(aI + q, err * a - p.positive_reg * b);
-      atomicAdd(aU + q, err * b - p.user_reg * a);
-    }
+  double* aU = p.accU + (size_t)u * f;
+  double* aI = p.accV + (size_t)i * f;
+  const double rp = (double)p.positive_reg, ru = (double)p.user_reg;
+  for (int q = lane; q < f; q += 32) {
+    const double a = (double)Uu[q], b = (double)Vi[q];
+    atomicAdd(aI + q, er * a - rp * b);  // item regulariser is positive_reg, not item_reg (pyx:349)
+    atomicAdd(aU + q, er * b - ru * a);
   }
 }
 
 // ---- phase 2: one touched row takes its step (pyx:792-832)
-__device__ __forceinline__ void apply_row(const Params& p, const AdaptCtx& ad, float* P, float* acc, float* c, float* m1,
-                                          float* m2, size_t row, int lane, float inv_bs) {
+__device__ __forceinline__ void apply_row(const Params& p, const AdaptCtx& ad, float* P, double* acc, float* c, float* m1,
+                                          float* m2, size_t row, int lane, double inv_bs) {
   const int f = p.f;
   const size_t o = row * (size_t)f;
   for (int q = lane; q < f; q += 32) {
-    float g = acc[o + q] * inv_bs;
+    float g = (float)(acc[o + q] * inv_bs);
     g = adapt(ad, g, c ? c + o + q : nullptr, m1 ? m1 + o + q : nullptr, m2 ? m2 + o + q : nullptr);
     P[o + q] += p.lr * g;
-    acc[o + q] = 0.f;
+    acc[o + q] = 0.0;
   }
 }
 
-__device__ __forceinline__ void apply_scalar(const Params& p, const AdaptCtx& ad, float* P, float* acc, float* c, float* m1,
-                                             float* m2, size_t k, float inv_bs) {
-  float g = acc[k] * inv_bs;
+__device__ __forceinline__ void apply_scalar(const Params& p, const AdaptCtx& ad, float* P, double* acc, float* c, float* m1,
+                                             float* m2, size_t k, double inv_bs) {
+  float g = (float)(acc[k] * inv_bs);
   g = adapt(ad, g, c ? c + k : nullptr, m1 ? m1 + k : nullptr, m2 ? m2 + k : nullptr);
   P[k] += p.lr * g;
-  acc[k] = 0.f;
+  acc[k] = 0.0;
 }
 
 template <bool VEC4>
@@ -201,7 +184,7 @@ __global__ void __launch_bounds__(256) mf_epoch_kernel(const Params p) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const float inv_bs = 1.f / (float)p.batch_size;
+  const double inv_bs = 1.0 / (double)p.batch_size;
   double b1p = p.b1_pow, b2p = p.b2_pow;
   AdaptCtx ad;
   ad.mode = p.sgd_mode; ad.gamma = p.gamma; ad.beta1 = p.beta1; ad.beta2 = p.beta2;
@@ -431,6 +414,13 @@ struct b200_mf_s {
   DevBuf<int> d_indptr, d_indices;
   DevBuf<float> d_data;
   std::vector<DevBuf<float>> fbufs;  // owns every float device array referenced by p
+  std::vector<DevBuf<double>> dbufs;  // the fp64 gradient accumulators of the mini-batch mode
+  double* dalloc(size_t n) {
+    dbufs.emplace_back(std::max<size_t>(n, 1));
+    double* d = dbufs.back().get();
+    B200_CUDA(cudaMemset(d, 0, std::max<size_t>(n, 1) * sizeof(double)));
+    return d;
+  }
   DevBuf<int> flagI, flagU, listI, listU, cnt, su, si, sj;
   DevBuf<float> sr;
   DevBuf<double> pow_out;
@@ -546,10 +536,11 @@ int b200_mf_create(b200_mf_t* out, int64_t n_users, int64_t n_items, int64_t nnz
     h->fbufs.reserve(40);
     p.U = h->falloc(nUf, h_user_factors);
     p.V = h->falloc(nIf, h_item_factors);
-    if (!p.hogwild) { p.accU = h->falloc(nUf, nullptr); p.accV = h->falloc(nIf, nullptr); }
+    h->dbufs.reserve(8);
+    if (!p.hogwild) { p.accU = h->dalloc(nUf); p.accV = h->dalloc(nIf); }
     if (p.use_bias) {
       p.bu = h->falloc((size_t)n_users, nullptr); p.bi = h->falloc((size_t)n_items, nullptr); p.mu = h->falloc(1, nullptr);
-      p.accbu = h->falloc((size_t)n_users, nullptr); p.accbi = h->falloc((size_t)n_items, nullptr); p.accmu = h->falloc(1, nullptr);
+      p.accbu = h->dalloc((size_t)n_users); p.accbi = h->dalloc((size_t)n_items); p.accmu = h->dalloc(1);
     }
     if (sgd_mode == ADAGRAD || sgd_mode == RMSPROP) {
       p.cU = h->falloc(nUf, nullptr); p.cV = h->falloc(nIf, nullptr);

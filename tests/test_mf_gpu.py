@@ -48,6 +48,29 @@ def test_glibc_stream_parity(algo, kw):
     assert len(u) == g.samples_last_epoch() == ((300 if algo == "MF_BPR" else X.nnz) // kw["batch_size"] + 1) * kw["batch_size"]
 
 
+def test_minibatch_mode_is_run_to_run_deterministic():
+    """The batch gradient sums are fp64 atomics (order-independent at fp32 precision): twenty runs of the FunkSVD /
+    adam / bias case -- the one an fp32 atomic sum made flaky -- agree with each other to the last fp32 bits (1e-6 relative) and are all within tolerance."""
+    algo, kw = CASES[5]
+    X = synth_urm(300, 120, 0.08, seed=3, values="ratings")
+    common = dict(algorithm_name=algo, learning_rate=0.05, random_seed=42, **kw)
+    o = MFOracle(X, **common)
+    for _ in range(3):
+        o.epochIteration_Cython()
+    first = None
+    for _ in range(20):
+        g = _cls()(X, **common)
+        for _ in range(3):
+            g.epochIteration_Cython()
+        _compare(g, o, bias=True)
+        got = (g.get_USER_factors(), g.get_ITEM_factors(), g.get_USER_bias(), g.get_ITEM_bias())
+        if first is None:
+            first = got
+        else:
+            for a, b in zip(got, first):
+                assert np.allclose(a, b, rtol=1e-6, atol=1e-8), float(np.abs(a - b).max())
+
+
 @pytest.mark.parametrize("algo", ["MF_BPR", "FUNK_SVD"])
 def test_philox_stream_parity_and_sample_validity(algo):
     """Device-drawn samples obey the reference's acceptance rules, and replaying them through the oracle gives
