@@ -120,13 +120,15 @@ int b200_sim_debug_set_cap(b200_sim_t h, int cap);
 
 /* TEST/BENCH HOOK: per-phase SM-cycle counters of the top-K kernel, summed over CTAs (thread 0's clock):
  * [0] stage  [1] accumulate  [2] bootstrap histogram  [3] scan+clear  [4] evaluate+compact  [5] select
- * [6] emit.  enable!=0 turns counting on for later launches; out8 (nullable) receives and resets the counters. */
+ * [6] emit (window kernel); the bitmap kernel reports [1] accumulate  [2] level >= 3  [3] level 2  [4] level 1  [6] emit+clear.  enable!=0 turns counting on for later launches; out8 (nullable) receives and resets the counters. */
 int b200_sim_debug_phase_cycles(b200_sim_t h, int enable, uint64_t* out8);
 
-/* TEST HOOK for the opt-in sparse-candidate variant of the binary path (csrc/sim_k1b.cuh, B200REC_K1B=1 at create time):
- * reports whether the handle uses it and the log2 of its hash-table slots; set_tbits > 0 shrinks the table (the launch then
- * overflows, sets its flag, and the window kernel recomputes the range -- the fallback under test). */
-int b200_sim_debug_k1b(b200_sim_t h, int set_tbits, int* enabled, int* tbits);
+/* TEST/BENCH HOOK for the bitmap kernel of the binary path (csrc/sim_k1c.cuh; chosen at create time for binary data with
+ * many columns, B200REC_K1C=0 disables it): reports whether the handle uses it, the log2 of its deep-table slots and the
+ * routing of the last launch (columns sent to the bitmap kernel; columns the window kernel processed, i.e. the dense ones
+ * plus those the bitmap kernel handed back).  set_t4bits > 0 shrinks the deep table (columns then overflow and are redone
+ * by the window kernel -- the fallback under test). */
+int b200_sim_debug_k1c(b200_sim_t h, int set_t4bits, int* enabled, int* t4bits, int* n_bitmap_cols, int* n_window_cols);
 
 /* duration in milliseconds of the last top-K kernel launched through this handle, measured with CUDA
  * events on the launching stream (bench.py roofline leg) */

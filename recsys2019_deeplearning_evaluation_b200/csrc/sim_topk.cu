@@ -100,13 +100,17 @@ struct KParams {
   int eu_mode, eu_norm, eu_signed;
   float eu_div, eu_shrink;
   float* dense_out;  // dense mode (TopK == 0 / full Gram): [n_range, n_cols] row-major, out[target - col_begin, neighbour]
-  // K1-B (sim_k1b.cuh): words per bitmap, log2 of the table slots, coarse norm tiles and their bounds, the n_win = 1 padded
-  // row layout, and the "table overflowed" flag
-  int bm_words, tbits, ncb;
-  const float* __restrict__ cb;
+  // K1-C (sim_k1c.cuh): words per bitmap, ring slots (power of two), log2 of the deep-table slots, norm tiles and their
+  // bounds, the n_win = 1 padded row layout with the CSC-side (row start, row chunks) list, the work items of the launch
+  // (new column, local column, csc begin, csc end), and the list + counter that receive the columns to redo
+  int bm_words, ring_slots, t4bits, ntile;
+  const float* __restrict__ tbnd;
   const int* __restrict__ csr_idx1;
-  const int* __restrict__ split1;
+  const int2* __restrict__ csc_seg;
+  const int4* __restrict__ worklist;
+  int* redo;
   int* fail;
+  const int* n_range_dev;  // window kernel: the number of columns to process is read from here when set
   unsigned long long* prof;  // optional [8] per-phase cycle counters (thread 0 of every CTA), test/bench hook
 };
 
@@ -903,6 +907,7 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     if (tid == 0) sh.guess = 0.f;
   }
   __syncthreads();
+  const int n_range = p.n_range_dev ? *p.n_range_dev : p.n_range;
 #if B200_PREFETCH
   if (tid == 0) sh.next = atomicAdd(p.counter, 1);
 #endif
@@ -911,13 +916,13 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
     __syncthreads();
     const int c = sh.next;
     __syncthreads();
-    if (c >= p.n_range) break;
+    if (c >= n_range) break;
     if (tid == 0) sh.next = atomicAdd(p.counter, 1);  // read by the prefetching threads many barriers later
 #else
     if (tid == 0) sh.col = atomicAdd(p.counter, 1);
     __syncthreads();
     const int c = sh.col;
-    if (c >= p.n_range) break;
+    if (c >= n_range) break;
 #endif
     const int lc = p.order ? p.order[c] : c;
     const int col = p.old2new[p.col_begin + lc];  // new numbering
@@ -962,7 +967,7 @@ __global__ void tile_bounds_kernel(const int2* __restrict__ BN, int n_cols, int 
   tileB[g] = __int_as_float(BN[j].x);
 }
 
-#include "sim_k1b.cuh"
+#include "sim_k1c.cuh"
 
 // ------------------------------------------------------------------------------------------------------
 // preprocessing kernels (constructor work of pyx:147-209, on the device)
@@ -1182,12 +1187,19 @@ struct b200_sim_s {
   DevBuf<int2> csr_ent, csc_ent, BN;
   DevBuf<float> A, tileB;
   int lpu_log2 = 3;
-  // K1-B (opt-in, binary path): second row layout with one window, coarse norm bounds, table geometry
-  bool want_k1b = false, k1b = false;
-  DevBuf<int> csr_idx1, split1, fail;
-  DevBuf<float> cb;
-  int bm_words = 0, tbits = 0, ncb = 0, lpu1_log2 = 3;
+  // K1-C (binary path, large sparse catalogues): second row layout with one window, CSC-side row locations, norm tile
+  // bounds, ring / table geometry, routing threshold (expected hits per neighbour of a column) and last-launch statistics
+  bool want_k1c = true, k1c = false;
+  DevBuf<int> csr_idx1, fail;
+  DevBuf<int2> csc_seg;
+  DevBuf<float> tbnd;
+  DevBuf<int4> worklist;
+  int bm_words = 0, ring_slots = 0, t4bits = 0, ntile = 0;
   size_t smem1_bytes = 0;
+  double k1c_lambda = 0.75;
+  int k1c_min_cols = 32768;
+  std::vector<int> h_old2new, h_csc_ptr;
+  int n_sparse_last = 0, n_dense_last = 0;
   std::vector<unsigned long long> h_work;  // by ORIGINAL column index
   DevBuf<int> counter, order;
   std::vector<int> h_order;  // cached LPT order for [order_lo, order_hi)
@@ -1221,13 +1233,13 @@ sim_kernel_t kernel_for(int formula, bool binary, bool pack) {
   }
 }
 
-sim_kernel_t k1b_kernel_for(int formula) {
+sim_kernel_t k1c_kernel_for(int formula) {
   switch (formula) {
-    case F_PROD: return sim_k1b_kernel<F_PROD>;
-    case F_NONORM: return sim_k1b_kernel<F_NONORM>;
-    case F_JACCARD: return sim_k1b_kernel<F_JACCARD>;
-    case F_DICE: return sim_k1b_kernel<F_DICE>;
-    default: return sim_k1b_kernel<F_TVERSKY>;
+    case F_PROD: return sim_k1c_kernel<F_PROD>;
+    case F_NONORM: return sim_k1c_kernel<F_NONORM>;
+    case F_JACCARD: return sim_k1c_kernel<F_JACCARD>;
+    case F_DICE: return sim_k1c_kernel<F_DICE>;
+    default: return sim_k1c_kernel<F_TVERSKY>;
   }
 }
 
@@ -1460,10 +1472,13 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
     seg_pad_kernel<<<div_up(n_seg * 8, 256), 256, 0, st>>>(h->split.get(), h->csr_idx.get(), poff.get(), n_seg, n_win, win, total_pad,
                                                           idx_pad.get(), split_pad.get()); count_launch();
     B200_CUDA(cudaStreamSynchronize(st));
-    if (h->want_k1b && nnz > 0) {
-      // the same rows once more as ONE window: whole rows padded to 16-byte chunks with the index win1 (>= n_cols)
+    const bool f_ok_c = h->formula == F_PROD || h->formula == F_NONORM || h->formula == F_JACCARD || h->formula == F_DICE ||
+                        (h->formula == F_TVERSKY && h->ta >= 0.f && h->tb >= 0.f);  // decreasing in the neighbour's norm term
+    if (h->want_k1c && f_ok_c && nnz > 0 && n_cols >= h->k1c_min_cols) {
+      // K1-C layout: the same rows once more as ONE window -- whole rows padded to 16-byte chunks with the index win1
+      // (>= n_cols) -- and, per CSC entry, where its user's padded row lives (start, length in 16-byte chunks)
       const int win1 = ((n_cols + 7) / 8) * 8;
-      DevBuf<int> sp1((size_t)n_rows * 2), len1((size_t)n_rows + 1), poff1((size_t)n_rows + 1);
+      DevBuf<int> sp1((size_t)n_rows * 2), len1((size_t)n_rows + 1), poff1((size_t)n_rows + 1), split1((size_t)n_rows * 2);
       split_kernel<<<div_up((long long)n_rows * 2, 256), 256, 0, st>>>(h->csr_ptr.get(), h->csr_idx.get(), n_rows, 1, win1, sp1.get()); count_launch();
       B200_CUDA(cudaMemsetAsync(len1.get() + n_rows, 0, sizeof(int), st));
       seg_len_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(sp1.get(), n_rows, 1, len1.get()); count_launch();
@@ -1475,9 +1490,11 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
       B200_CUDA(cudaMemcpyAsync(&total1, poff1.get() + n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaStreamSynchronize(st));
       h->csr_idx1.alloc((size_t)total1 + 8);
-      h->split1.alloc((size_t)n_rows * 2);
       seg_pad_kernel<<<div_up((long long)n_rows * 8, 256), 256, 0, st>>>(sp1.get(), h->csr_idx.get(), poff1.get(), n_rows, 1, win1, total1,
-                                                                        h->csr_idx1.get(), h->split1.get()); count_launch();
+                                                                        h->csr_idx1.get(), split1.get()); count_launch();
+      h->csc_seg.alloc((size_t)nnz + 2);
+      B200_CUDA(cudaMemsetAsync(h->csc_seg.get() + nnz, 0, 2 * sizeof(int2), st));
+      k1c_csc_seg_kernel<<<GRID1D, 256, 0, st>>>(h->csc_idx.get(), split1.get(), nnz, h->csc_seg.get()); count_launch();
       B200_CUDA(cudaStreamSynchronize(st));
     }
     h->csr_idx = std::move(idx_pad);
@@ -1500,41 +1517,39 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   if (!h->binary) h->csr_idx.release();  // the AoS copy carries the indices
   h->counter.alloc(1);
   h->order.alloc((size_t)n_cols);
-  // ---- K1-B geometry and eligibility (sim_k1b.cuh)
-  h->k1b = false;
-  const bool f_ok = h->formula == F_PROD || h->formula == F_NONORM || h->formula == F_JACCARD || h->formula == F_DICE ||
-                    (h->formula == F_TVERSKY && h->ta >= 0.f && h->tb >= 0.f);
-  if (h->want_k1b && h->binary && f_ok && h->csr_idx1.n > 0) {
+  // ---- K1-C geometry and eligibility (sim_k1c.cuh)
+  h->k1c = false;
+  if (h->csc_seg.n > 0) {
     const int win1 = ((n_cols + 7) / 8) * 8;
-    h->ncb = (n_cols + (1 << CB_LOG2) - 1) >> CB_LOG2;
+    h->ntile = (n_cols + (1 << C_TILE_LOG2) - 1) >> C_TILE_LOG2;
     h->bm_words = (((win1 + 32 + 31) / 32) + 3) / 4 * 4;
-    const long long fixed = 2ll * h->bm_words * 4 + (long long)h->cap_alloc * 8 + staging + (2ll * h->ncb + 2) * 4 + (long long)sizeof(Shared) + 1024;
-    const long long avail = (long long)max_smem - fixed;
-    int tbits = 0;
-    while (tbits < 16 && (8ll << (tbits + 1)) <= avail) ++tbits;
-    if (tbits >= 12 && h->ncb <= THREADS) {
-      const double T = (double)(1 << tbits);
-      double worst = 0.0;  // expected cells hit at least twice in one column if its gathered entries spread uniformly
-      for (int c = 0; c < n_cols; ++c) {
-        const double lam = (double)h->h_work[(size_t)c] / (double)n_cols;
-        worst = std::max(worst, (double)n_cols * (1.0 - std::exp(-lam) * (1.0 + lam)));
-      }
-      if (2.0 * worst <= 0.625 * T) {
-        h->tbits = tbits;
-        h->smem1_bytes = (size_t)(2ll * h->bm_words * 4 + (8ll << tbits) + (long long)h->cap_alloc * 8 + staging + (2ll * h->ncb + 2) * 4);
-        h->cb.alloc((size_t)h->ncb + 1);
-        coarse_bounds_kernel<<<div_up(h->ncb + 1, 128), 128, 0, st>>>(h->BN.get(), n_cols, h->ncb, h->cb.get()); count_launch();
-        h->fail.alloc(1);
-        const double chunks = (nnz > 0 ? (double)nnz / (double)n_rows : 1.0) / 4.0 + 1.0;
-        int l2 = 1;
-        while (l2 < 5 && (1 << l2) < chunks) ++l2;
-        h->lpu1_log2 = l2;
-        B200_CUDA(cudaStreamSynchronize(st));
-        h->k1b = true;
-      }
+    auto total_bytes = [&](int slots, int t4bits) {
+      return (long long)slots * (C_PIECE_BYTES + 16 + 16) + 2ll * (C_STAGE + 2) * 8 + 3ll * h->bm_words * 4 + (8ll << t4bits) +
+             (long long)h->cap_alloc * 8 + (long long)SBINS * 4 + ((long long)h->ntile + 1) * 4 + 16 + 8 + 128;
+    };
+    const long long avail = (long long)max_smem - (long long)sizeof(Shared) - (long long)sizeof(K1CShared) - 256;
+    int slots = 0, t4 = 0;
+    for (int tb4 = 12; tb4 >= 9 && !slots; --tb4)      // deep table: 4096 .. 512 slots
+      for (int sl = 256; sl >= 64 && !slots; sl >>= 1)  // ring: 128 KB .. 32 KB
+        if (total_bytes(sl, tb4) <= avail) { slots = sl; t4 = tb4; }
+    if (slots) {
+      h->ring_slots = slots;
+      h->t4bits = t4;
+      h->smem1_bytes = (size_t)total_bytes(slots, t4);
+      h->tbnd.alloc((size_t)h->ntile + 1);
+      k1c_tile_bounds_kernel<<<div_up(h->ntile + 1, 128), 128, 0, st>>>(h->BN.get(), n_cols, h->ntile, h->tbnd.get()); count_launch();
+      h->fail.alloc(1);
+      h->worklist.alloc((size_t)n_cols);
+      h->h_old2new.resize((size_t)n_cols);
+      h->h_csc_ptr.resize((size_t)n_cols + 1);
+      B200_CUDA(cudaMemcpyAsync(h->h_old2new.data(), h->old2new.get(), sizeof(int) * (size_t)n_cols, cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaMemcpyAsync(h->h_csc_ptr.data(), h->csc_ptr.get(), sizeof(int) * ((size_t)n_cols + 1), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaStreamSynchronize(st));
+      B200_CUDA(cudaFuncSetAttribute(k1c_kernel_for(h->formula), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem1_bytes));
+      h->k1c = true;
     }
   }
-  if (!h->k1b) { h->csr_idx1.release(); h->split1.release(); }
+  if (!h->k1c) { h->csr_idx1.release(); h->csc_seg.release(); }
 }
 
 }  // namespace
@@ -1558,7 +1573,11 @@ int b200_sim_create(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz
     B200_REQUIRE(h_indptr && (nnz == 0 || (h_indices && h_data)), "b200_sim_create: NULL input array");
     h = new b200_sim_s();
     h->allow_pack = getenv("B200REC_NO_PACK") == nullptr;  // test hook: force 32-bit counters on the binary path
-    h->want_k1b = getenv("B200REC_K1B") != nullptr && atoi(getenv("B200REC_K1B")) == 1;  // opt-in sparse-candidate kernel
+    // K1-C routing: on by default for binary data with >= k1c_min_cols columns; B200REC_K1C=0 disables it, the other two
+    // variables are test hooks (small matrices, forced overflow -> redo path)
+    if (const char* e = getenv("B200REC_K1C")) h->want_k1c = atoi(e) != 0;
+    if (const char* e = getenv("B200REC_K1C_LAMBDA")) h->k1c_lambda = atof(e);
+    if (const char* e = getenv("B200REC_K1C_MINCOLS")) h->k1c_min_cols = atoi(e);
     h->n_rows = (int)n_rows;
     h->n_cols = (int)n_cols;
     h->nnz = nnz;
@@ -1651,17 +1670,36 @@ int b200_sim_info(b200_sim_t h, int* K, int* n_windows, int* window_cells, int* 
 static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx, float* d_val, int32_t* d_cnt, float* d_dense,
                         cudaStream_t st) {
   const int n_range = end_col - start_col;
-  // longest-processing-time-first order of the local columns (cached per range)
+  const bool use_k1c = h->k1c && d_dense == nullptr;
+  // Routing + longest-processing-time-first order of the local columns (cached per range).  With K1-C the columns whose
+  // expected hits per neighbour (gathered entries / n_cols) stay below k1c_lambda go to the bitmap kernel (`worklist`);
+  // the rest -- and whatever the bitmap kernel hands back -- go to the window kernel (`order`).
   if (h->order_lo != start_col || h->order_hi != end_col) {
-    h->h_order.resize((size_t)n_range);
-    for (int i = 0; i < n_range; ++i) h->h_order[(size_t)i] = i;
     const unsigned long long* w = h->h_work.data() + start_col;
-    std::stable_sort(h->h_order.begin(), h->h_order.end(), [w](int a, int b) { return w[a] > w[b]; });
-    B200_CUDA(cudaMemcpyAsync(h->order.get(), h->h_order.data(), sizeof(int) * (size_t)n_range, cudaMemcpyHostToDevice, st));
+    std::vector<int> sparse;
+    h->h_order.clear();
+    for (int i = 0; i < n_range; ++i) {
+      const bool sp = use_k1c && w[i] > 0 && (double)w[i] <= h->k1c_lambda * (double)h->n_cols;
+      (sp ? sparse : h->h_order).push_back(i);
+    }
+    auto by_work = [w](int a, int b) { return w[a] > w[b]; };
+    std::stable_sort(h->h_order.begin(), h->h_order.end(), by_work);
+    std::stable_sort(sparse.begin(), sparse.end(), by_work);
+    h->n_dense_last = (int)h->h_order.size();
+    h->n_sparse_last = (int)sparse.size();
+    if (!h->h_order.empty())
+      B200_CUDA(cudaMemcpyAsync(h->order.get(), h->h_order.data(), sizeof(int) * h->h_order.size(), cudaMemcpyHostToDevice, st));
+    std::vector<int4> wl(sparse.size());
+    for (size_t k = 0; k < sparse.size(); ++k) {
+      const int cn = h->h_old2new[(size_t)(start_col + sparse[k])];
+      wl[k] = make_int4(cn, sparse[k], h->h_csc_ptr[(size_t)cn], h->h_csc_ptr[(size_t)cn + 1]);
+    }
+    if (!wl.empty()) B200_CUDA(cudaMemcpyAsync(h->worklist.get(), wl.data(), sizeof(int4) * wl.size(), cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaStreamSynchronize(st));
     h->order_lo = start_col;
     h->order_hi = end_col;
   }
+  const int n_sparse = use_k1c ? h->n_sparse_last : 0, n_dense = use_k1c ? h->n_dense_last : n_range;
   B200_CUDA(cudaMemsetAsync(h->counter.get(), 0, sizeof(int), st));
   KParams p;
   p.n_cols = h->n_cols; p.K = h->K; p.n_win = h->n_win; p.win = h->win; p.cap = h->cap; p.cap_alloc = h->cap_alloc;
@@ -1675,7 +1713,7 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   p.split = h->split.get();
   p.csc_ptr = h->csc_ptr.get(); p.csc_ent = h->csc_ent.get(); p.csc_idx = h->csc_idx.get();
   p.A = h->A.get(); p.BN = h->BN.get(); p.old2new = h->old2new.get();
-  p.col_begin = start_col; p.n_range = n_range;
+  p.col_begin = start_col; p.n_range = n_dense;
   p.order = h->order.get();
   p.counter = h->counter.get();
   p.out_idx = d_idx; p.out_val = d_val; p.out_cnt = d_cnt;
@@ -1685,36 +1723,31 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   p.eu_shrink = h->shrink;
   p.dense_out = d_dense;
   p.prof = h->prof_on ? h->prof.get() : nullptr;
-  p.bm_words = h->bm_words; p.tbits = h->tbits; p.ncb = h->ncb; p.cb = h->cb.get();
-  p.csr_idx1 = h->csr_idx1.get(); p.split1 = h->split1.get(); p.fail = h->fail.get();
-  const int grid = std::min(n_range, h->n_sm);
-  if (h->k1b && d_dense == nullptr) {
-    // sparse-candidate kernel first; a table overflow anywhere discards the launch and the window kernel redoes the range
-    B200_CUDA(cudaMemsetAsync(h->fail.get(), 0, sizeof(int), st));
-    KParams q = p;
-    q.lpu_log2 = h->lpu1_log2;
-    sim_kernel_t k1 = k1b_kernel_for(h->formula);
-    B200_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem1_bytes));
-    B200_CUDA(cudaEventRecord(h->ev0, st));
-    k1<<<grid, THREADS, h->smem1_bytes, st>>>(q);
-    B200_CUDA(cudaGetLastError());
-    B200_CUDA(cudaEventRecord(h->ev1, st));
-    count_launch();
-    int failed = 0;
-    B200_CUDA(cudaMemcpyAsync(&failed, h->fail.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
-    if (!failed) {
-      h->timed = true;
-      return;
-    }
-    B200_CUDA(cudaMemsetAsync(h->counter.get(), 0, sizeof(int), st));
-  }
+  p.bm_words = h->bm_words; p.ring_slots = h->ring_slots; p.t4bits = h->t4bits; p.ntile = h->ntile; p.tbnd = h->tbnd.get();
+  p.csr_idx1 = h->csr_idx1.get(); p.csc_seg = h->csc_seg.get(); p.worklist = h->worklist.get();
+  p.redo = h->order.get(); p.fail = h->fail.get();
+  p.n_range_dev = nullptr;
   B200_CUDA(cudaEventRecord(h->ev0, st));
-  kernel_for(h->formula, h->binary, h->pack)<<<grid, THREADS, h->smem_bytes, st>>>(p);
-  B200_CUDA(cudaGetLastError());
+  if (n_sparse > 0) {
+    // bitmap kernel first; columns whose deep table overflows are appended to the window kernel's list, whose length
+    // the window kernel then reads from the device (no host round trip between the two launches)
+    B200_CUDA(cudaMemcpyAsync(h->fail.get(), &h->n_dense_last, sizeof(int), cudaMemcpyHostToDevice, st));
+    KParams q = p;
+    q.n_range = n_sparse;
+    k1c_kernel_for(h->formula)<<<std::min(n_sparse, h->n_sm), THREADS, h->smem1_bytes, st>>>(q);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+    B200_CUDA(cudaMemsetAsync(h->counter.get(), 0, sizeof(int), st));
+    p.n_range_dev = h->fail.get();
+  }
+  if (n_dense > 0 || n_sparse > 0) {
+    const int grid = n_sparse > 0 ? h->n_sm : std::min(n_dense, h->n_sm);
+    kernel_for(h->formula, h->binary, h->pack)<<<grid, THREADS, h->smem_bytes, st>>>(p);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+  }
   B200_CUDA(cudaEventRecord(h->ev1, st));
   h->timed = true;
-  count_launch();
 }
 
 int b200_sim_compute_device(b200_sim_t h, int start_col, int end_col, int32_t* d_idx, float* d_val, int32_t* d_cnt,
@@ -1783,15 +1816,23 @@ int b200_sim_debug_phase_cycles(b200_sim_t h, int enable, uint64_t* out8) {
   });
 }
 
-int b200_sim_debug_k1b(b200_sim_t h, int set_tbits, int* enabled, int* tbits) {
+int b200_sim_debug_k1c(b200_sim_t h, int set_t4bits, int* enabled, int* t4bits, int* n_bitmap_cols, int* n_window_cols) {
   return guarded([&] {
-    B200_REQUIRE(h != nullptr, "b200_sim_debug_k1b: NULL handle");
-    if (set_tbits > 0 && h->k1b) {
-      B200_REQUIRE(set_tbits >= 6 && set_tbits <= h->tbits, "b200_sim_debug_k1b: tbits must be in [6, %d]", h->tbits);
-      h->tbits = set_tbits;  // the allocation keeps its size; a smaller table only overflows earlier
+    B200_REQUIRE(h != nullptr, "b200_sim_debug_k1c: NULL handle");
+    if (set_t4bits > 0 && h->k1c) {
+      B200_REQUIRE(set_t4bits >= 4 && set_t4bits <= h->t4bits, "b200_sim_debug_k1c: t4bits must be in [4, %d]", h->t4bits);
+      h->t4bits = set_t4bits;  // the allocation keeps its size; a smaller deep table only overflows earlier
     }
-    if (enabled) *enabled = h->k1b ? 1 : 0;
-    if (tbits) *tbits = h->k1b ? h->tbits : 0;
+    if (enabled) *enabled = h->k1c ? 1 : 0;
+    if (t4bits) *t4bits = h->k1c ? h->t4bits : 0;
+    if (n_bitmap_cols) *n_bitmap_cols = h->n_sparse_last;  // routing of the last launch
+    if (n_window_cols) {
+      *n_window_cols = h->n_dense_last;
+      if (h->k1c && h->n_sparse_last > 0) {  // the bitmap kernel's redo count is on the device
+        B200_CUDA(cudaDeviceSynchronize());
+        B200_CUDA(cudaMemcpy(n_window_cols, h->fail.get(), sizeof(int), cudaMemcpyDeviceToHost));
+      }
+    }
   });
 }
 

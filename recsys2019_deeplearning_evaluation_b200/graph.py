@@ -49,7 +49,9 @@ def sparse_column_topk(W, k):
 
 def p3_similarity(URM_train, topK=100, alpha=1.0, beta=0.0, min_rating=0, implicit=False, normalize_similarity=False):
     """Returns W_sparse (CSR float32, row i = item i's outgoing weights) as the reference's fit() leaves it.
-    beta=0 -> P3alpha, beta>0 -> RP3beta."""
+    beta=0 -> P3alpha, beta>0 -> RP3beta.  The recommender classes apply `min_rating` / `implicit` to their own
+    URM_train first (the reference mutates it, P3alphaRecommender.py:47-51); the arguments here serve direct callers and
+    work on a private copy."""
     import torch
     lib = _lib.load()
     URM = _as_csr_f32(URM_train).copy()

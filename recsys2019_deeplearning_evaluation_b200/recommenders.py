@@ -267,24 +267,37 @@ class UserKNNCFRecommender(BaseUserSimilarityMatrixRecommender):
         sim.compute_similarity_object._dealloc()
 
 
-class P3alphaRecommender(BaseItemSimilarityMatrixRecommender):
+class _GraphFilterMixin(object):
+    def _filter_urm_in_place(self, min_rating, implicit):
+        """P3alphaRecommender.py:47-51 / RP3betaRecommender.py:44-48 mutate self.URM_train: ratings below `min_rating` are
+        dropped (and the rest binarised when `implicit`), so the later scoring (URM[users] . W) and the seen-item
+        filter use the filtered matrix too."""
+        if min_rating > 0:
+            self.URM_train.data[self.URM_train.data < min_rating] = 0
+            self.URM_train.eliminate_zeros()
+            if implicit:
+                self.URM_train.data = np.ones(self.URM_train.data.size, dtype=np.float32)
+            self._d_urm = None  # the device copy of the profiles follows the host matrix
+
+
+class P3alphaRecommender(_GraphFilterMixin, BaseItemSimilarityMatrixRecommender):
     RECOMMENDER_NAME = "P3alphaRecommender"
 
     def fit(self, topK=100, alpha=1.0, min_rating=0, implicit=False, normalize_similarity=False):
         from .graph import p3_similarity
         self.topK, self.alpha, self.min_rating, self.implicit, self.normalize_similarity = topK, alpha, min_rating, implicit, normalize_similarity
-        self.W_sparse = p3_similarity(self.URM_train, topK=topK, alpha=alpha, beta=0.0, min_rating=min_rating, implicit=implicit,
-                                      normalize_similarity=normalize_similarity)
+        self._filter_urm_in_place(min_rating, implicit)
+        self.W_sparse = p3_similarity(self.URM_train, topK=topK, alpha=alpha, beta=0.0, normalize_similarity=normalize_similarity)
 
 
-class RP3betaRecommender(BaseItemSimilarityMatrixRecommender):
+class RP3betaRecommender(_GraphFilterMixin, BaseItemSimilarityMatrixRecommender):
     RECOMMENDER_NAME = "RP3betaRecommender"
 
     def fit(self, alpha=1.0, beta=0.6, min_rating=0, topK=100, implicit=False, normalize_similarity=True):
         from .graph import p3_similarity
         self.alpha, self.beta, self.min_rating, self.topK, self.implicit, self.normalize_similarity = alpha, beta, min_rating, topK, implicit, normalize_similarity
-        self.W_sparse = p3_similarity(self.URM_train, topK=topK, alpha=alpha, beta=beta, min_rating=min_rating, implicit=implicit,
-                                      normalize_similarity=normalize_similarity)
+        self._filter_urm_in_place(min_rating, implicit)
+        self.W_sparse = p3_similarity(self.URM_train, topK=topK, alpha=alpha, beta=beta, normalize_similarity=normalize_similarity)
 
 
 class Incremental_Training_Early_Stopping(object):
@@ -295,19 +308,30 @@ class Incremental_Training_Early_Stopping(object):
     def _train_with_early_stopping(self, epochs_max, epochs_min=0, validation_every_n=None, stop_on_validation=False,
                                    validation_metric=None, lower_validations_allowed=None, evaluator_object=None,
                                    algorithm_name="Incremental_Training_Early_Stopping"):
-        assert epochs_max > 0 and 0 <= epochs_min <= epochs_max
-        assert evaluator_object is None or (validation_every_n is not None and validation_metric is not None)
+        # :147-157, same conditions and messages
+        assert epochs_max >= 0, "{}: Number of epochs_max must be >= 0, passed was {}".format(algorithm_name, epochs_max)
+        assert epochs_min >= 0, "{}: Number of epochs_min must be >= 0, passed was {}".format(algorithm_name, epochs_min)
+        assert epochs_min <= epochs_max, "{}: epochs_min must be <= epochs_max, passed are epochs_min {}, epochs_max {}".format(
+            algorithm_name, epochs_min, epochs_max)
+        assert evaluator_object is None or \
+            (not stop_on_validation and validation_every_n is not None and validation_metric is not None) or \
+            (stop_on_validation and validation_every_n is not None and validation_metric is not None and lower_validations_allowed is not None), \
+            "{}: Inconsistent parameters passed, please check the supported uses".format(algorithm_name)
         self.best_validation_metric, lower_validation_count = None, 0
         self.epochs_best, epochs_current, convergence = 0, 0, False
         while epochs_current < epochs_max and not convergence:
             self._run_epoch(epochs_current)
-            if evaluator_object is not None and (epochs_current + 1) % validation_every_n == 0:
+            if evaluator_object is None:  # :174-176: no validation, always keep the latest
+                self.epochs_best = epochs_current
+            elif (epochs_current + 1) % validation_every_n == 0:
                 self._prepare_model_for_validation()
                 results_run, _ = evaluator_object.evaluateRecommender(self)
                 results_run = results_run[list(results_run.keys())[0]]
                 current_metric_value = results_run[validation_metric]
-                if not np.isfinite(current_metric_value):  # :200-205
-                    break
+                if not np.isfinite(current_metric_value):  # :194-199: a diverged run must not return as if it had converged
+                    if hasattr(self, "_clean_temp_folder") and hasattr(self, "temp_file_folder"):
+                        self._clean_temp_folder(temp_file_folder=self.temp_file_folder)
+                    assert False, "{}: metric value is not a finite number, terminating!".format(self.RECOMMENDER_NAME)
                 if self.best_validation_metric is None or self.best_validation_metric < current_metric_value:
                     self.best_validation_metric = current_metric_value
                     self._update_best_model()
@@ -318,10 +342,9 @@ class Incremental_Training_Early_Stopping(object):
                 if stop_on_validation and lower_validation_count >= lower_validations_allowed and epochs_current >= epochs_min:
                     convergence = True
             epochs_current += 1
-        if evaluator_object is None:  # no validation: the last model is the best model
+        if evaluator_object is None:  # :239-242 no validation: the last model is the best model (epochs_best stays epochs_max-1)
             self._prepare_model_for_validation()
             self._update_best_model()
-            self.epochs_best = epochs_current
 
 
 class BaseMatrixFactorizationRecommender(BaseRecommender):
@@ -339,8 +362,9 @@ class BaseMatrixFactorizationRecommender(BaseRecommender):
 
     def _factors_device(self):
         import torch
-        key = (id(self.USER_factors), id(self.ITEM_factors))
-        if getattr(self, "_d_f_key", None) != key:
+        # the source arrays themselves are kept (ids can be recycled after a re-fit)
+        src = getattr(self, "_d_f_src", None)
+        if src is None or src[0] is not self.USER_factors or src[1] is not self.ITEM_factors:
             dev = torch.device("cuda", torch.cuda.current_device())
             U = torch.from_numpy(np.ascontiguousarray(self.USER_factors, np.float32)).to(dev)
             V = torch.from_numpy(np.ascontiguousarray(self.ITEM_factors, np.float32)).to(dev)
@@ -350,7 +374,7 @@ class BaseMatrixFactorizationRecommender(BaseRecommender):
             if self.use_bias:
                 biases = tuple(torch.from_numpy(np.ascontiguousarray(np.atleast_1d(b), np.float32)).to(dev)
                                for b in (self.USER_bias, self.ITEM_bias, self.GLOBAL_bias))
-            self._d_f, self._d_f_key = (U, VT, biases), key
+            self._d_f, self._d_f_src = (U, VT, biases), (self.USER_factors, self.ITEM_factors)
         return self._d_f
 
     def _scores_device(self, d_users, items_to_compute=None):

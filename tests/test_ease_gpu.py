@@ -97,12 +97,11 @@ GEMM_SHAPES = [(0, 384, 128, 128, 0.0), (0, 256, 256, 128, 1.0), (1, 128, 128, 6
 
 @pytest.mark.parametrize("kind,M,N,K,beta", GEMM_SHAPES)
 def test_tensor_core_gemm_v1(kind, M, N, K, beta):
-    """The three GEMM shapes of the blocked inverse through the default tcgen05 kernel, against fp64."""
+    """The three GEMM shapes of the blocked inverse through the first tcgen05 kernel (B200REC_GEMM=1), against fp64."""
     _gemm_case(1, kind, M, N, K, beta)
 
 
-@pytest.mark.skipif(os.environ.get("B200REC_TEST_GEMM2") != "1",
-                    reason="gemm_tc2.cuh (packed operands + cp.async.bulk) is opt-in until validated: B200REC_TEST_GEMM2=1")
 @pytest.mark.parametrize("kind,M,N,K,beta", GEMM_SHAPES + [(0, 1024, 1024, 128, 1.0), (2, 2048, 2048, 2048, 0.0)])
 def test_tensor_core_gemm_v2(kind, M, N, K, beta):
+    """The default kernel (pre-packed hi/lo TF32 operands, cp.async.bulk producer, mbarrier ring)."""
     _gemm_case(2, kind, M, N, K, beta)

@@ -174,3 +174,95 @@ def test_binary_counter_widths(monkeypatch):
         monkeypatch.delenv("B200REC_NO_PACK")
         assert abs(W16 - W32).max() < 1e-7 if (W16 - W32).nnz else True
 
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K1-C: the bitmap kernel of the binary path (csrc/sim_k1c.cuh).  It is chosen by itself for binary data with >= 32768
+# columns; the environment hooks route small matrices through it as well.
+
+def _k1c_info(sim):
+    import ctypes
+    from recsys2019_deeplearning_evaluation_b200 import _lib
+    en, tb, nb, nw = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(_lib.load().b200_sim_debug_k1c(sim._h, 0, ctypes.byref(en), ctypes.byref(tb), ctypes.byref(nb), ctypes.byref(nw)))
+    return en.value, tb.value, nb.value, nw.value
+
+
+@pytest.fixture
+def force_k1c(monkeypatch):
+    monkeypatch.setenv("B200REC_K1C_MINCOLS", "1")
+    monkeypatch.setenv("B200REC_K1C_LAMBDA", "1e9")  # every non-empty column goes to the bitmap kernel first
+    yield monkeypatch
+
+
+@pytest.mark.parametrize("kind", ["cosine", "asymmetric", "jaccard", "tanimoto", "dice", "tversky"])
+def test_k1c_kinds_small_forced(force_k1c, kind):
+    """Every formula the bitmap kernel serves, on a small binary matrix whose counts run deep (deep table + levels)."""
+    X = synth_urm(700, 300, 0.04, seed=3, values="binary")
+    W, sim, _ = _check(X, topK=25, shrink=7, normalize=True, similarity=kind, asymmetric_alpha=0.3, tversky_alpha=0.7,
+                       tversky_beta=1.3)
+    en, tb, nb, nw = _k1c_info(sim)
+    assert en == 1 and nb > 0
+
+
+def test_k1c_not_used_for_valued_or_signed_data(force_k1c):
+    for values, kind in (("ratings", "cosine"), ("continuous", "cosine"), ("binary", "adjusted"), ("binary", "pearson")):
+        X = synth_urm(400, 200, 0.05, seed=4, values=values)
+        W, sim, _ = _check(X, topK=10, shrink=2, similarity=kind)
+        assert _k1c_info(sim)[0] == 0
+
+
+def test_k1c_sparse_catalogue_auto_and_against_window_kernel(monkeypatch):
+    """230 K columns, sparse counts: chosen without hooks, all columns on the bitmap kernel, same W as the window kernel."""
+    X = synth_urm(20_000, 230_000, 0.0003, seed=42, values="binary")
+    kw = dict(topK=50, shrink=10, similarity="cosine")
+    cols = np.arange(0, X.shape[1], 997)
+    W1, sim1, _ = _check(X, cols=cols, **kw)
+    en, tb, nb, nw = _k1c_info(sim1)
+    assert en == 1 and nb == int((np.diff(X.tocsc().indptr) > 0).sum()) and nb + nw == X.shape[1]  # empty columns: window kernel
+    monkeypatch.setenv("B200REC_K1C", "0")
+    W0, sim0, _ = _check(X, cols=cols, **kw)
+    assert _k1c_info(sim0)[0] == 0
+    assert abs(W1 - W0).nnz == 0  # integer counts: both kernels are exact and deterministic
+
+
+def test_k1c_c1_shape_levels_and_redo(force_k1c):
+    """C1 shape (counts well above 3 everywhere): levels, deep table and -- with the table shrunk to 16 slots -- the redo
+    path through the window kernel; column ranges; ties resolved like the window kernel."""
+    X = synth_urm(10_000, 5_000, 0.01, seed=42, values="binary")
+    kw = dict(topK=200, shrink=100, similarity="cosine")
+    cols = np.arange(0, 5000, 11)
+    W1, sim1, _ = _check(X, cols=cols, **kw)
+    en, tb, nb, nw = _k1c_info(sim1)
+    assert en == 1 and nb > 0
+    import ctypes
+    from recsys2019_deeplearning_evaluation_b200 import _lib
+    _lib.check(_lib.load().b200_sim_debug_k1c(sim1._h, 4, None, None, None, None))
+    W1b = sim1.compute_similarity()
+    en, tb, nb2, nw2 = _k1c_info(sim1)
+    assert tb == 4 and nw2 > nw  # columns were handed back
+    force_k1c.setenv("B200REC_K1C", "0")
+    W0, sim0, _ = _check(X, cols=cols, **kw)
+    assert abs(W1 - W0).nnz == 0 and abs(W1b - W0).nnz == 0
+    force_k1c.delenv("B200REC_K1C")
+    Wp = sim1.compute_similarity(start_col=1000, end_col=1800)
+    assert abs(Wp[:, 1000:1800] - W0[:, 1000:1800]).nnz == 0 and Wp[:, :1000].nnz == 0 and Wp[:, 1800:].nnz == 0
+
+
+def test_k1c_skewed_popularity_and_long_rows(force_k1c):
+    """Popular items (columns of thousands of users: several stage chunks) and users with long profiles (rows of several
+    ring pieces); dense co-occurrence overflows the deep table for the head items -> redo."""
+    X = synth_urm(30_000, 2_000, 0.01, seed=13, values="binary", popularity=1.1)
+    _check(X, cols=np.arange(0, 2000, 13), topK=100, shrink=10, similarity="cosine")
+    Y = synth_urm(300, 4_000, 0.2, seed=5, values="binary")  # rows of ~800 entries = 7 pieces each
+    _check(Y, cols=np.arange(0, 4000, 41), topK=40, shrink=1, similarity="jaccard")
+
+
+def test_k1c_empty_columns_topk_exceeds_candidates(force_k1c):
+    X = synth_urm(200, 120, 0.02, seed=2, values="binary").tolil()
+    X[:, 5] = 0
+    X[:, 77] = 0
+    X = sps.csr_matrix(X, dtype=np.float32)
+    X.eliminate_zeros()
+    W, sim, _ = _check(X, topK=100, shrink=0, similarity="cosine")
+    assert W[:, 5].nnz == 0 and W[5, :].nnz == 0
