@@ -203,7 +203,9 @@ def _ref_worker(conn, X, kind, w):
 
 
 def cpu_baseline_leg(X, budget_cols):
-    """Reference Cython (1 thread, as shipped) on a bounded slice of the same URM, for the b200 arm's JSON."""
+    """Reference Cython (1 thread, as shipped) on a bounded slice of the same URM, for the b200 arm's JSON.
+    Returns (the cpu_baseline dict, the reference's W for those columns, lo, hi): parity_gate() compares the GPU
+    table of the same run against it."""
     from oracle import ref_loader
     mod = ref_loader.load("Compute_Similarity_Cython")
     kind = "reference" if mod is not None else "port"
@@ -222,14 +224,35 @@ def cpu_baseline_leg(X, budget_cols):
     os.dup2(devnull.fileno(), 1)
     try:
         t = time.perf_counter()
-        obj.compute_similarity(start_col=lo, end_col=hi)
+        W_ref = obj.compute_similarity(start_col=lo, end_col=hi)
         dt = time.perf_counter() - t
     finally:
         sys.stdout.flush()
         os.dup2(so, 1)
         os.close(so)
-    return {"value": (hi - lo) / dt, "unit": "rows/s", "cores": 1, "kind": kind,
-            "sample": "columns [%d,%d) of the same URM in %.1fs, 1 thread (the reference is single-threaded); constructor %.1fs not counted" % (lo, hi, dt, ctor)}
+    return ({"value": (hi - lo) / dt, "unit": "rows/s", "cores": 1, "kind": kind,
+             "sample": "columns [%d,%d) of the same URM in %.1fs, 1 thread (the reference is single-threaded); constructor %.1fs not counted" % (lo, hi, dt, ctor)},
+            W_ref, lo, hi)
+
+
+def parity_gate(X, table, W_ref, lo, hi, K, kind):
+    """The timed run's own output against the reference's columns [lo, hi) of the same URM (the checker, not the thing
+    measured): tie-aware index sets + 1e-4 relative values (oracle.similarity_oracle.compare_topk_with_reference);
+    entries that only the GPU holds (ties at the K-th value) are re-evaluated exactly in fp64 from the URM columns."""
+    import scipy.sparse as sps
+    from oracle.similarity_oracle import compare_topk_with_reference, cosine_pair_values
+    idx, val, cnt = (t[lo:hi].cpu().numpy() for t in table)
+    keep = np.arange(idx.shape[1])[None, :] < cnt[:, None]
+    cols = np.broadcast_to(np.arange(lo, hi)[:, None], idx.shape)[keep]
+    n = X.shape[1]
+    G = sps.csc_matrix((val[keep], (idx[keep], cols)), shape=(n, n))
+    t = time.perf_counter()
+    Xc = sps.csc_matrix(X)
+    res = compare_topk_with_reference(G, W_ref, np.arange(lo, hi), K,
+                                      pair_values=lambda jj, cc: cosine_pair_values(Xc, jj, cc, SIM_KW["shrink"]))
+    res.update({"against": "%s Compute_Similarity_Cython, columns [%d,%d) of the timed run's output table" % (kind, lo, hi),
+                "rule": "tie-aware index sets, rtol 1e-4", "seconds": time.perf_counter() - t})
+    return res
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -354,6 +377,7 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    sim_K = sim.K
     sim._dealloc()
     secondary = None
     if world > 1 and not args.no_bpr:
@@ -368,12 +392,20 @@ def run_b200(args, rank, world, local_rank):
             secondary = bpr_leg(args, X)
         except Exception as ex:
             secondary = {"metric": "BPR-MF samples/sec", "error": repr(ex)}
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    cpu, parity = None, None
+    if not args.no_cpu_baseline:
         try:
-            cpu = cpu_baseline_leg(X, args.cpu_cols)
+            # N = 1: the cpu_baseline slice; N > 1: a shorter slice, only for the parity of the gathered table
+            cpu, W_ref, c_lo, c_hi = cpu_baseline_leg(X, args.cpu_cols if world == 1 else max(200, args.cpu_cols // 4))
         except Exception as ex:  # the GPU numbers stand without it
             cpu = {"value": None, "unit": "rows/s", "cores": 1, "kind": "unavailable", "sample": repr(ex)}
+        else:
+            try:
+                parity = parity_gate(X, out, W_ref, c_lo, c_hi, sim_K, cpu["kind"])
+            except Exception as ex:
+                parity = {"ok": False, "error": repr(ex)}
+            if world > 1:
+                cpu = None  # reported at N = 1 only
     nu, ni, dens = CONFIGS[args.workload]
     name, sms, mem = _lib.device_info()
     out = {
@@ -393,6 +425,7 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
         "secondary": secondary,
         "device": name,
     }

@@ -123,12 +123,12 @@ int b200_sim_debug_set_cap(b200_sim_t h, int cap);
  * [6] emit (window kernel); the bitmap kernel reports [1] accumulate  [2] level >= 3  [3] level 2  [4] level 1  [6] emit+clear.  enable!=0 turns counting on for later launches; out8 (nullable) receives and resets the counters. */
 int b200_sim_debug_phase_cycles(b200_sim_t h, int enable, uint64_t* out8);
 
-/* TEST/BENCH HOOK for the bitmap kernel of the binary path (csrc/sim_k1c.cuh; chosen at create time for binary data with
- * many columns, B200REC_K1C=0 disables it): reports whether the handle uses it, the log2 of its deep-table slots and the
- * routing of the last launch (columns sent to the bitmap kernel; columns the window kernel processed, i.e. the dense ones
- * plus those the bitmap kernel handed back).  set_t4bits > 0 shrinks the deep table (columns then overflow and are redone
- * by the window kernel -- the fallback under test). */
-int b200_sim_debug_k1c(b200_sim_t h, int set_t4bits, int* enabled, int* t4bits, int* n_bitmap_cols, int* n_window_cols);
+/* TEST/BENCH HOOK for the 4-bit-counter kernel of the binary path (csrc/sim_k1d.cuh; chosen at create time for binary data
+ * with many columns, B200REC_K1C=0 disables it): reports whether the handle uses it, how many of its CTAs share an SM, and
+ * how the last launch was routed (columns it took / columns the window kernel computed, including the ones handed back
+ * because a counter overflowed).  set_fail_every > 0 makes it hand back every n-th local column (exercises the redo path);
+ * 0 switches that off. */
+int b200_sim_debug_k1c(b200_sim_t h, int set_fail_every, int* enabled, int* ctas_per_sm, int* n_bitmap_cols, int* n_window_cols);
 
 /* duration in milliseconds of the last top-K kernel launched through this handle, measured with CUDA
  * events on the launching stream (bench.py roofline leg) */
@@ -181,6 +181,12 @@ int b200_mf_get_factors(b200_mf_t h, double* user_factors, double* item_factors,
 int b200_mf_device_factors(b200_mf_t h, float** d_user_factors, float** d_item_factors);
 /* device time of the last epoch (sampling kernel + epoch kernel), CUDA events on the launching stream */
 int b200_mf_last_epoch_ms(b200_mf_t h, float* ms);
+/* Multi-GPU exchange of a replicated factor table ("V (item factors) replicated"; the reference has
+ * no distributed path).  n = elements (a multiple of 4), all pointers on the device, fp32.
+ *   snapshot:  own = V - B;  sum = own (the caller all-reduces `sum` in place);  B = V
+ *   apply:     t = sum - own (the other ranks' movement);  V += t (RED.ADD: the trainer may be writing V);  B += t */
+int b200_mf_delta_snapshot_device(const float* d_V, float* d_B, float* d_own, float* d_sum, int64_t n, void* stream);
+int b200_mf_delta_apply_device(float* d_V, float* d_B, const float* d_sum, const float* d_own, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3: SLIM-BPR epochs on a dense / symmetric item-item matrix  (hot path ii)

@@ -219,3 +219,80 @@ def check_topk_against_dense(W, oracle, cols, rtol=1e-4, atol=1e-7):
             if set(top.tolist()) != got:
                 ties += 1
     return ties
+
+
+def cosine_pair_values(Xc, jj, cc, shrink):
+    """fp64 similarity of the column pairs (jj[k], cc[k]) of the CSC matrix Xc, cosine with shrink, normalize=True:
+    dot / (|j| |c| + shrink + 1e-6) (pyx:378-408 for the dot, :170-174 and :484-485 for the normalisation)."""
+    out = np.zeros(len(jj), np.float64)
+    sq = {}
+
+    def col(c):
+        s, e = Xc.indptr[c], Xc.indptr[c + 1]
+        return Xc.indices[s:e], Xc.data[s:e].astype(np.float64)
+
+    for k, (j, c) in enumerate(zip(jj, cc)):
+        ij, vj = col(j)
+        ic, vc = col(c)
+        for t, v in ((j, vj), (c, vc)):
+            if t not in sq:
+                sq[t] = float(np.sqrt((v * v).sum()))
+        _, aj, ac = np.intersect1d(ij, ic, assume_unique=True, return_indices=True)
+        out[k] = float((vj[aj] * vc[ac]).sum()) / (sq[j] * sq[c] + int(shrink) + 1e-6)
+    return out
+
+
+def compare_topk_with_reference(G, R, cols, K, pair_values=None, rtol=1e-4, atol=1e-7, max_pairs=20000):
+    """Tie-aware comparison of two top-K results (scipy sparse, entry [j, c] = similarity of neighbour j to target c):
+    G the result under test, R the reference's (Compute_Similarity_Cython.compute_similarity, pyx:413-611).
+    Per target column in `cols`: the neighbour counts agree; the sorted value lists agree within rtol; common neighbours
+    carry the same value; and the two index sets differ only by neighbours tied (within tolerance) with the K-th value --
+    the reference's pick among equal values is numpy-introselect order (pyx:544-548), ours ascending index.  For the
+    entries only G holds, `pair_values(jj, cc)` (an exact fp64 evaluation) confirms the value G reports.
+    Returns {"cols", "ok", "max_rel", "tie_cols", "tie_pairs_checked", "failures": [...first few...]}."""
+    G, R = sps.csc_matrix(G), sps.csc_matrix(R)
+    fails, max_rel, tie_cols = [], 0.0, 0
+    pj, pc, pv = [], [], []
+    for c in np.asarray(cols):
+        gi, gv = G.indices[G.indptr[c]:G.indptr[c + 1]], G.data[G.indptr[c]:G.indptr[c + 1]].astype(np.float64)
+        ri, rv = R.indices[R.indptr[c]:R.indptr[c + 1]], R.data[R.indptr[c]:R.indptr[c + 1]].astype(np.float64)
+        if len(gi) != len(ri):
+            fails.append("column %d: %d neighbours, reference %d" % (c, len(gi), len(ri)))
+            continue
+        if len(ri) == 0:
+            continue
+        sg, sr = np.sort(gv)[::-1], np.sort(rv)[::-1]
+        rel = np.abs(sg - sr) / np.maximum(np.abs(sr), 1e-30)
+        max_rel = max(max_rel, float(rel.max()))
+        if not np.allclose(sg, sr, rtol=rtol, atol=atol):
+            fails.append("column %d: sorted values differ, max rel %.3e" % (c, rel.max()))
+            continue
+        og, orr = np.argsort(gi), np.argsort(ri)
+        gi, gv, ri, rv = gi[og], gv[og], ri[orr], rv[orr]
+        _, ag, ar = np.intersect1d(gi, ri, assume_unique=True, return_indices=True)
+        if not np.allclose(gv[ag], rv[ar], rtol=rtol, atol=atol):
+            fails.append("column %d: a common neighbour carries a different value" % c)
+            continue
+        if len(ag) == len(gi):
+            continue
+        tie_cols += 1
+        kth = sr[-1]
+        tol = rtol * abs(kth) + atol
+        only_g = np.setdiff1d(np.arange(len(gi)), ag)
+        only_r = np.setdiff1d(np.arange(len(ri)), ar)
+        if len(ri) < K or (np.abs(gv[only_g] - kth) > tol).any() or (np.abs(rv[only_r] - kth) > tol).any():
+            fails.append("column %d: index sets differ beyond ties at the K-th value" % c)
+            continue
+        if len(pj) < max_pairs:
+            pj.extend(gi[only_g].tolist()); pc.extend([int(c)] * len(only_g)); pv.extend(gv[only_g].tolist())
+    checked = 0
+    if pair_values is not None and pj:
+        exact = pair_values(np.asarray(pj), np.asarray(pc))
+        checked = len(pj)
+        bad = ~np.isclose(np.asarray(pv), exact, rtol=rtol, atol=atol)
+        if bad.any():
+            k = int(np.argmax(bad))
+            fails.append("%d tie entries carry a wrong value, e.g. (%d, %d): %.7g vs exact %.7g" % (
+                int(bad.sum()), pj[k], pc[k], pv[k], exact[k]))
+    return {"cols": int(len(cols)), "ok": not fails, "max_rel": max_rel, "tie_cols": tie_cols,
+            "tie_pairs_checked": checked, "failures": fails[:5]}

@@ -53,6 +53,8 @@ SIGNATURES = {
     "b200_mf_get_factors": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_void, c_void]),
     "b200_mf_device_factors": (ctypes.c_int, [c_void, ctypes.POINTER(c_void), ctypes.POINTER(c_void)]),
     "b200_mf_last_epoch_ms": (ctypes.c_int, [c_void, c_float_p]),
+    "b200_mf_delta_snapshot_device": (ctypes.c_int, [c_void, c_void, c_void, c_void, ctypes.c_int64, c_void]),
+    "b200_mf_delta_apply_device": (ctypes.c_int, [c_void, c_void, c_void, c_void, ctypes.c_int64, c_void]),
     "b200_slim_create": (ctypes.c_int, [ctypes.POINTER(c_void), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void, c_void,
                                         ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                         ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]),

@@ -13,10 +13,18 @@
 //     vector RED.ADD into the accumulators), grid sync, phase 2 (one warp per touched row), grid sync.
 //     The sample stream is either replayed on the host with glibc's rand() (bit-compatible with the reference's
 //     libc calls) or drawn on the device with Philox4x32-10.
+//     Without bias terms the same semantics run as a DATAFLOW (mf_dataflow_kernel, the default): the only true
+//     dependences between batches are rows touched again by a later batch (a batch of 1000 touches 3000 of 1.2 M
+//     rows at C5), so instead of two grid-wide barriers per batch every (row, batch) pair carries a precomputed
+//     expected hit count and the batch that touched the row before; a sample waits until exactly that earlier
+//     update is visible, the last sample to hit a row in a batch applies the row's step, and a row hit once in its
+//     batch (the common case) is stepped straight from registers without an accumulator round trip.
 //   * hogwild: no batch barrier -- every warp applies its sample's update immediately (the reference's
 //     batch_size=1 recursion run concurrently; races between warps are the usual Hogwild races).
 // Roofline: HBM; bytes per BPR sample = 6 * f * 4 (three rows read, three accumulator rows RMW).
 #include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -47,6 +55,12 @@ struct Params {
   const int* su; const int* si; const int* sj; const float* sr;  // sample stream of the epoch
   long long n_batches;
   double* pow_out;  // [2] adam powers after the epoch
+  // dataflow mode: per row (users first, then items at n_users + i) the batch whose update is in place / arrivals of the
+  // current batch; per sample slot (sample * slots + k) the batch that touched the row before and the row's hit count in
+  // this batch; per batch the adam bias corrections
+  int *applied, *arrived;
+  const int *slot_prev, *slot_expect;
+  const float *inv1_b, *inv2_b;
 };
 
 struct AdaptCtx {
@@ -305,6 +319,226 @@ __global__ void __launch_bounds__(256) mf_hogwild_kernel(const Params p, long lo
   }
 }
 
+
+// =====================================================================================================================
+// Dataflow mini-batch mode (same arithmetic and semantics as mf_epoch_kernel, no grid-wide barrier).
+//   row ids: user u -> u, item i -> n_users + i.  slot k of sample g: 0 = user, 1 = item i, 2 = item j (BPR).
+//   slot_prev[g*S+k]   = the latest batch < batch(g) of this epoch that touches the row, or -1
+//   slot_expect[g*S+k] = how many samples of batch(g) touch the row
+//   applied[row]       = batch whose step is in place (-1 at epoch start); published with st.release after the row is
+//                        written, read with ld.acquire before the row is read; rows and optimiser state move with
+//                        .cg accesses (L2 only), so no stale L1 line can be observed
+// Progress: warps take samples in increasing order and wait only for steps of earlier batches, each of which is taken by
+// one of that batch's samples; with every warp resident (cooperative launch) the smallest unfinished sample never waits.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// pyx:838-876 on one element with L2-only accesses to the state
+__device__ __forceinline__ float adapt_cg(const AdaptCtx& a, float g, float* c, float* m1, float* m2) {
+  if (a.mode == ADAGRAD) {
+    const float cc = __ldcg(c) + g * g;
+    __stcg(c, cc);
+    return g / (sqrtf(cc) + 1e-8f);
+  } else if (a.mode == RMSPROP) {
+    const float cc = __ldcg(c) * a.gamma + (1.f - a.gamma) * g * g;
+    __stcg(c, cc);
+    return g / (sqrtf(cc) + 1e-8f);
+  } else if (a.mode == ADAM) {
+    const float mm1 = __ldcg(m1) * a.beta1 + (1.f - a.beta1) * g;
+    const float mm2 = __ldcg(m2) * a.beta2 + (1.f - a.beta2) * g * g;
+    __stcg(m1, mm1);
+    __stcg(m2, mm2);
+    return (mm1 * a.inv1) / (sqrtf(mm2 * a.inv2) + 1e-8f);
+  }
+  return g;
+}
+
+// one row's share of a sample: either the row's whole step (it is hit once in this batch) or a contribution to its sum
+struct SlotCtx {
+  float* P; double* acc; float *c, *m1, *m2;  // row base pointers (state pointers may be null)
+  bool direct;
+};
+__device__ __forceinline__ void slot_element(const Params& p, const AdaptCtx& ad, const SlotCtx& s, int q, float old, double term,
+                                             double inv_bs) {
+  if (s.direct) {
+    float g = (float)(term * inv_bs);  // what apply_row computes from a one-term sum
+    g = adapt_cg(ad, g, s.c ? s.c + q : nullptr, s.m1 ? s.m1 + q : nullptr, s.m2 ? s.m2 + q : nullptr);
+    __stcg(s.P + q, old + p.lr * g);
+  } else {
+    atomicAdd(s.acc + q, term);
+  }
+}
+// the step of a row whose sum is complete (pyx:792-832), L2-only accesses
+__device__ __forceinline__ void apply_row_cg(const Params& p, const AdaptCtx& ad, const SlotCtx& s, int lane, double inv_bs) {
+  for (int q = lane; q < p.f; q += 32) {
+    float g = (float)(__ldcg(s.acc + q) * inv_bs);
+    g = adapt_cg(ad, g, s.c ? s.c + q : nullptr, s.m1 ? s.m1 + q : nullptr, s.m2 ? s.m2 + q : nullptr);
+    __stcg(s.P + q, __ldcg(s.P + q) + p.lr * g);
+    __stcg(s.acc + q, 0.0);
+  }
+}
+// after the elements of a slot are written: publish (direct) or count the arrival and, as the last one, take the step
+__device__ __forceinline__ void slot_finish(const Params& p, const AdaptCtx& ad, const SlotCtx& s, int row, int expect, int batch,
+                                            int lane, double inv_bs) {
+  __threadfence();
+  __syncwarp();
+  if (s.direct) {
+    if (lane == 0) st_release(p.applied + row, batch);
+    return;
+  }
+  int last = 0;
+  if (lane == 0) {
+    last = (atomicAdd(p.arrived + row, 1) + 1 == expect) ? 1 : 0;
+    __threadfence();
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  apply_row_cg(p, ad, s, lane, inv_bs);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) {
+    p.arrived[row] = 0;
+    __threadfence();
+    st_release(p.applied + row, batch);
+  }
+}
+
+template <bool BPR>
+__global__ void __launch_bounds__(256) mf_dataflow_kernel(const Params p, long long n_samples) {
+  constexpr int S = BPR ? 3 : 2;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int f = p.f, nU = p.n_users;
+  const double inv_bs = 1.0 / (double)p.batch_size;
+  const bool vec4 = (f & 3) == 0;
+  AdaptCtx ad;
+  ad.mode = p.sgd_mode; ad.gamma = p.gamma; ad.beta1 = p.beta1; ad.beta2 = p.beta2; ad.inv1 = ad.inv2 = 1.f;
+  for (long long g = warp; g < n_samples; g += n_warps) {
+    const int batch = (int)(g / p.batch_size);
+    const int u = p.su[g], i = p.si[g], j = BPR ? p.sj[g] : 0;
+    const int ru = u, ri = nU + i, rj = nU + j;
+    const long long s0 = g * S;
+    const int pu = p.slot_prev[s0], pi = p.slot_prev[s0 + 1], pj = BPR ? p.slot_prev[s0 + 2] : 0;
+    const int eu = p.slot_expect[s0], ei = p.slot_expect[s0 + 1], ej = BPR ? p.slot_expect[s0 + 2] : 0;
+    if (p.sgd_mode == ADAM) { ad.inv1 = p.inv1_b[batch]; ad.inv2 = p.inv2_b[batch]; }
+    // ---- wait for the three rows' previous steps (every lane acquires for itself)
+    {
+      unsigned ns = 20;
+      while (ld_acquire(p.applied + ru) != pu || ld_acquire(p.applied + ri) != pi || (BPR && ld_acquire(p.applied + rj) != pj)) {
+        __nanosleep(ns);
+        if (ns < 640) ns <<= 1;
+      }
+    }
+    float* Uu = p.U + (size_t)u * f;
+    float* Vi = p.V + (size_t)i * f;
+    float* Vj = p.V + (size_t)j * f;
+    // ---- dot product on the frozen parameters
+    float x = 0.f;
+    if (vec4) {
+      for (int q = lane * 4; q < f; q += 128) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(Uu + q)), b = __ldcg(reinterpret_cast<const float4*>(Vi + q));
+        if (BPR) {
+          const float4 c = __ldcg(reinterpret_cast<const float4*>(Vj + q));
+          x += a.x * (b.x - c.x) + a.y * (b.y - c.y) + a.z * (b.z - c.z) + a.w * (b.w - c.w);
+        } else {
+          x += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+      }
+    } else {
+      for (int q = lane; q < f; q += 32) x += BPR ? __ldcg(Uu + q) * (__ldcg(Vi + q) - __ldcg(Vj + q)) : __ldcg(Uu + q) * __ldcg(Vi + q);
+    }
+    x = warp_sum(x);
+    // BPR: sigma = 1 / (1 + e^x), pyx:622; FunkSVD (no bias here): err = r - x, pyx:318
+    const double coef = BPR ? (double)(1.f / (1.f + expf(x))) : (double)(p.sr[g] - x);
+    const size_t ou = (size_t)u * f, oi = (size_t)i * f, oj = (size_t)j * f;
+    SlotCtx su_{Uu, p.accU + ou, p.cU ? p.cU + ou : nullptr, p.m1U ? p.m1U + ou : nullptr, p.m2U ? p.m2U + ou : nullptr, eu == 1};
+    SlotCtx si_{Vi, p.accV + oi, p.cV ? p.cV + oi : nullptr, p.m1V ? p.m1V + oi : nullptr, p.m2V ? p.m2V + oi : nullptr, ei == 1};
+    SlotCtx sj_{Vj, p.accV + oj, p.cV ? p.cV + oj : nullptr, p.m1V ? p.m1V + oj : nullptr, p.m2V ? p.m2V + oj : nullptr, ej == 1};
+    const double rp = (double)p.positive_reg, rn = (double)p.negative_reg, rgu = (double)p.user_reg;
+    // ---- every element: the three terms from the OLD values, then each row's own action
+    for (int q = lane; q < f; q += 32) {
+      const float af = __ldcg(Uu + q), bf = __ldcg(Vi + q), cf = BPR ? __ldcg(Vj + q) : 0.f;
+      const double a = (double)af, b = (double)bf, c = (double)cf;
+      if (BPR) {
+        slot_element(p, ad, si_, q, bf, coef * a - rp * b, inv_bs);        // pyx:633
+        slot_element(p, ad, sj_, q, cf, -coef * a - rn * c, inv_bs);       // pyx:634
+        slot_element(p, ad, su_, q, af, coef * (b - c) - rgu * a, inv_bs);  // pyx:635
+      } else {
+        slot_element(p, ad, si_, q, bf, coef * a - rp * b, inv_bs);   // pyx:349 (positive_reg, not item_reg)
+        slot_element(p, ad, su_, q, af, coef * b - rgu * a, inv_bs);  // pyx:350
+      }
+    }
+    slot_finish(p, ad, si_, ri, ei, batch, lane, inv_bs);
+    if (BPR) slot_finish(p, ad, sj_, rj, ej, batch, lane, inv_bs);
+    slot_finish(p, ad, su_, ru, eu, batch, lane, inv_bs);
+  }
+}
+
+// ---- multi-GPU exchange of a replicated factor table (dist.ShardedBPR): two fused element-wise passes
+// snapshot: d = V - B (this rank's own movement since the last snapshot), D = d (the all-reduce runs in place on D),
+// B = V.  The training kernel may be writing V concurrently (Hogwild): whatever this pass reads is what B records, so
+// d + B_old == B_new exactly and later writes land in the next delta.
+__global__ void mf_delta_snapshot_kernel(const float4* __restrict__ V, float4* __restrict__ B, float4* __restrict__ d,
+                                         float4* __restrict__ D, long long n4) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldcg(V + k), b = B[k];
+    const float4 x = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
+    d[k] = x;
+    D[k] = x;
+    B[k] = v;
+  }
+}
+// apply: t = D - d (the other ranks' movement); V += t with RED.ADD (the training kernel keeps updating V), B += t
+__global__ void mf_delta_apply_kernel(float4* __restrict__ V, float4* __restrict__ B, const float4* __restrict__ D,
+                                      const float4* __restrict__ d, long long n4) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
+    const float4 a = D[k], o = d[k];
+    const float4 t = make_float4(a.x - o.x, a.y - o.y, a.z - o.z, a.w - o.w);
+    red_add4(reinterpret_cast<float*>(V + k), t);
+    float4 b = B[k];
+    b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w;
+    B[k] = b;
+  }
+}
+
+// keys of the (row, batch) pairs of an epoch's sample stream: row << bbits | batch; value = slot id
+template <bool BPR>
+__global__ void mf_slot_keys_kernel(const int* __restrict__ su, const int* __restrict__ si, const int* __restrict__ sj, long long n,
+                                    int n_users, int batch_size, int bbits, unsigned long long* keys, int* vals) {
+  constexpr int S = BPR ? 3 : 2;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const unsigned long long b = (unsigned long long)(g / batch_size);
+  keys[g * S] = ((unsigned long long)su[g] << bbits) | b;
+  keys[g * S + 1] = ((unsigned long long)(n_users + si[g]) << bbits) | b;
+  if (BPR) keys[g * S + 2] = ((unsigned long long)(n_users + sj[g]) << bbits) | b;
+  for (int k = 0; k < S; ++k) vals[g * S + k] = (int)(g * S + k);
+}
+
+// sorted keys -> per slot: previous batch of the row, hit count of the (row, batch) run.  The head of a run walks it.
+__global__ void mf_deps_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ vals, long long m, int bbits,
+                               int* slot_prev, int* slot_expect) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const unsigned long long key = keys[t];
+  if (t > 0 && keys[t - 1] == key) return;
+  int prev = -1;
+  if (t > 0 && (keys[t - 1] >> bbits) == (key >> bbits)) prev = (int)(keys[t - 1] & ((1ull << bbits) - 1ull));
+  long long e = t + 1;
+  while (e < m && keys[e] == key) ++e;
+  const int cnt = (int)(e - t);
+  for (long long k = t; k < e; ++k) {
+    const int slot = vals[k];
+    slot_prev[slot] = prev;
+    slot_expect[slot] = cnt;
+  }
+}
+
 // ---- device sampler: Philox4x32-10, counter = (sample index, draw block), key = (seed, epoch)
 __device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0, unsigned k1) {
   const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -429,6 +663,16 @@ struct b200_mf_s {
   long long samples_last = 0, cap_samples = 0, epoch_samples_override = 0;
   int shard_lo = 0, shard_hi = 0;  // device sampler draws users from [shard_lo, shard_hi) when set (multi-GPU user sharding)
   int grid = 0;
+  int hog_blocks = 8;  // hogwild CTAs per SM; a sharded (multi-GPU) run leaves room for the collective's CTAs
+  // dataflow mode (mf_dataflow_kernel): dependency tables rebuilt from every epoch's sample stream
+  bool dataflow = false;
+  int df_grid = 0, bbits = 1, rbits = 1;
+  DevBuf<int> applied, arrived, slot_prev, slot_expect, vals_a, vals_b;
+  DevBuf<unsigned long long> keys_a, keys_b;
+  DevBuf<unsigned char> sort_tmp;
+  size_t sort_tmp_bytes = 0;
+  DevBuf<float> inv1_b, inv2_b;
+  std::vector<float> h_inv1, h_inv2;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   float* falloc(size_t n, const double* init) {
@@ -572,6 +816,38 @@ int b200_mf_create(b200_mf_t* out, int64_t n_users, int64_t n_items, int64_t nnz
     else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mf_epoch_kernel<false>, 256, 0));
     B200_REQUIRE(per_sm >= 1, "b200_mf_create: epoch kernel does not fit on an SM");
     h->grid = sm_count() * std::min(per_sm, 8);
+    // dataflow mode: the default for the mini-batch semantics without bias terms (the global bias is touched by every
+    // sample, which turns the dependence chain into a barrier per batch: those runs keep the cooperative kernel);
+    // B200REC_MF_DATAFLOW=0 selects the cooperative kernel for A/B runs
+    {
+      const char* e = getenv("B200REC_MF_DATAFLOW");
+      h->dataflow = !p.hogwild && !p.use_bias && !(e && atoi(e) == 0);
+    }
+    if (h->dataflow) {
+      const int S = algorithm == MF_BPR ? 3 : 2;
+      const size_t rows = (size_t)n_users + (size_t)n_items, slots = (size_t)h->cap_samples * S;
+      B200_REQUIRE(slots < (1ull << 31), "b200_mf_create: epoch too long for 32-bit slot ids");
+      h->applied.alloc(rows); h->arrived.alloc(rows);
+      B200_CUDA(cudaMemset(h->arrived.get(), 0, sizeof(int) * rows));
+      h->slot_prev.alloc(slots); h->slot_expect.alloc(slots);
+      h->keys_a.alloc(slots); h->keys_b.alloc(slots); h->vals_a.alloc(slots); h->vals_b.alloc(slots);
+      const long long nb = epoch_batches(h);
+      while ((1ll << h->bbits) < nb + 1) ++h->bbits;
+      while ((1ull << h->rbits) < rows + 1) ++h->rbits;
+      cub::DoubleBuffer<unsigned long long> dk(h->keys_a.get(), h->keys_b.get());
+      cub::DoubleBuffer<int> dv(h->vals_a.get(), h->vals_b.get());
+      B200_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->sort_tmp_bytes, dk, dv, (int)slots, 0, h->bbits + h->rbits));
+      h->sort_tmp.alloc(h->sort_tmp_bytes + 16);
+      if (sgd_mode == ADAM) { h->inv1_b.alloc((size_t)nb); h->inv2_b.alloc((size_t)nb); }
+      p.applied = h->applied.get(); p.arrived = h->arrived.get();
+      p.slot_prev = h->slot_prev.get(); p.slot_expect = h->slot_expect.get();
+      p.inv1_b = h->inv1_b.get(); p.inv2_b = h->inv2_b.get();
+      int per_sm_df = 0;
+      if (algorithm == MF_BPR) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_df, mf_dataflow_kernel<true>, 256, 0));
+      else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_df, mf_dataflow_kernel<false>, 256, 0));
+      B200_REQUIRE(per_sm_df >= 1, "b200_mf_create: dataflow kernel does not fit on an SM");
+      h->df_grid = sm_count() * std::min(per_sm_df, 8);
+    }
     B200_CUDA(cudaEventCreate(&h->ev0));
     B200_CUDA(cudaEventCreate(&h->ev1));
     *out = h;
@@ -612,12 +888,45 @@ int b200_mf_epoch(b200_mf_t h, void* stream) {
       count_launch();
     }
     if (p.hogwild) {
-      mf_hogwild_kernel<<<sm_count() * 8, 256, 0, st>>>(p, n);
+      mf_hogwild_kernel<<<sm_count() * h->hog_blocks, 256, 0, st>>>(p, n);
       B200_CUDA(cudaGetLastError());
       if (p.sgd_mode == ADAM) {  // powers advance once per size-1 batch
         p.b1_pow *= pow((double)p.beta1, (double)n);
         p.b2_pow *= pow((double)p.beta2, (double)n);
       }
+    } else if (h->dataflow) {
+      // dependency tables of this epoch's stream: (row, batch) keys sorted, run heads give hit counts and previous batches
+      const bool bpr = p.algorithm == MF_BPR;
+      const int S = bpr ? 3 : 2;
+      const long long m = n * S;
+      if (bpr) mf_slot_keys_kernel<true><<<div_up(n, 256), 256, 0, st>>>(p.su, p.si, p.sj, n, p.n_users, p.batch_size, h->bbits, h->keys_a.get(), h->vals_a.get());
+      else mf_slot_keys_kernel<false><<<div_up(n, 256), 256, 0, st>>>(p.su, p.si, p.sj, n, p.n_users, p.batch_size, h->bbits, h->keys_a.get(), h->vals_a.get());
+      count_launch();
+      cub::DoubleBuffer<unsigned long long> dk(h->keys_a.get(), h->keys_b.get());
+      cub::DoubleBuffer<int> dv(h->vals_a.get(), h->vals_b.get());
+      size_t tb = h->sort_tmp_bytes;
+      B200_CUDA(cub::DeviceRadixSort::SortPairs(h->sort_tmp.get(), tb, dk, dv, (int)m, 0, h->bbits + h->rbits, st));
+      count_launch();
+      mf_deps_kernel<<<div_up(m, 256), 256, 0, st>>>(dk.Current(), dv.Current(), m, h->bbits, h->slot_prev.get(), h->slot_expect.get());
+      count_launch();
+      B200_CUDA(cudaMemsetAsync(h->applied.get(), 0xFF, sizeof(int) * ((size_t)p.n_users + (size_t)p.n_items), st));  // -1
+      if (p.sgd_mode == ADAM) {  // the powers advance once per batch (pyx:649-652), the same repeated product as the other kernel
+        h->h_inv1.resize((size_t)p.n_batches); h->h_inv2.resize((size_t)p.n_batches);
+        double b1p = p.b1_pow, b2p = p.b2_pow;
+        for (long long b = 0; b < p.n_batches; ++b) {
+          h->h_inv1[(size_t)b] = (float)(1.0 / (1.0 - b1p));
+          h->h_inv2[(size_t)b] = (float)(1.0 / (1.0 - b2p));
+          b1p *= (double)p.beta1; b2p *= (double)p.beta2;
+        }
+        B200_CUDA(cudaMemcpyAsync(h->inv1_b.get(), h->h_inv1.data(), sizeof(float) * (size_t)p.n_batches, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(h->inv2_b.get(), h->h_inv2.data(), sizeof(float) * (size_t)p.n_batches, cudaMemcpyHostToDevice, st));
+        p.b1_pow = b1p; p.b2_pow = b2p;
+      }
+      long long n_arg = n;
+      void* args[] = {(void*)&p, (void*)&n_arg};
+      // cooperative launch only for its co-residency guarantee (the progress argument needs every warp resident)
+      if (bpr) B200_CUDA(cudaLaunchCooperativeKernel((void*)mf_dataflow_kernel<true>, dim3(h->df_grid), dim3(256), args, 0, st));
+      else B200_CUDA(cudaLaunchCooperativeKernel((void*)mf_dataflow_kernel<false>, dim3(h->df_grid), dim3(256), args, 0, st));
     } else {
       void* args[] = {(void*)&p};
       if (p.f % 4 == 0) B200_CUDA(cudaLaunchCooperativeKernel((void*)mf_epoch_kernel<true>, dim3(h->grid), dim3(256), args, 0, st));
@@ -626,7 +935,9 @@ int b200_mf_epoch(b200_mf_t h, void* stream) {
     count_launch();
     B200_CUDA(cudaEventRecord(h->ev1, st));
     h->timed = true;
-    if (!p.hogwild && p.sgd_mode == ADAM) {
+    if (h->dataflow && p.sgd_mode == ADAM) {
+      B200_CUDA(cudaStreamSynchronize(st));  // the host-side inv tables are reused by the next epoch
+    } else if (!p.hogwild && p.sgd_mode == ADAM) {
       double pw[2];
       B200_CUDA(cudaMemcpyAsync(pw, h->pow_out.get(), sizeof(pw), cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaStreamSynchronize(st));
@@ -650,6 +961,7 @@ int b200_mf_set_user_shard(b200_mf_t h, int user_lo, int user_hi, int64_t sample
     h->shard_hi = user_hi;
     h->epoch_samples_override = samples_per_epoch;
     h->seed += 0x9E3779B9u * stream_id;  // decorrelates the ranks' Philox streams
+    h->hog_blocks = 6;  // 1536 of an SM's 2048 threads: the all-reduce kernels of the overlapped exchange fit beside it
   });
 }
 
@@ -696,6 +1008,28 @@ int b200_mf_device_factors(b200_mf_t h, float** d_user_factors, float** d_item_f
     B200_REQUIRE(h != nullptr, "b200_mf_device_factors: NULL handle");
     if (d_user_factors) *d_user_factors = h->p.U;
     if (d_item_factors) *d_item_factors = h->p.V;
+  });
+}
+
+int b200_mf_delta_snapshot_device(const float* d_V, float* d_B, float* d_own, float* d_sum, int64_t n, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(d_V && d_B && d_own && d_sum && n >= 0 && (n & 3) == 0, "b200_mf_delta_snapshot_device: bad argument (n must be a multiple of 4)");
+    if (n == 0) return;
+    mf_delta_snapshot_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(d_V), reinterpret_cast<float4*>(d_B),
+                                                                             reinterpret_cast<float4*>(d_own), reinterpret_cast<float4*>(d_sum), n / 4);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+  });
+}
+
+int b200_mf_delta_apply_device(float* d_V, float* d_B, const float* d_sum, const float* d_own, int64_t n, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(d_V && d_B && d_own && d_sum && n >= 0 && (n & 3) == 0, "b200_mf_delta_apply_device: bad argument (n must be a multiple of 4)");
+    if (n == 0) return;
+    mf_delta_apply_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(d_V), reinterpret_cast<float4*>(d_B),
+                                                                          reinterpret_cast<const float4*>(d_sum), reinterpret_cast<const float4*>(d_own), n / 4);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
   });
 }
 

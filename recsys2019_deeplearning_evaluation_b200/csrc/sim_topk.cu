@@ -100,10 +100,10 @@ struct KParams {
   int eu_mode, eu_norm, eu_signed;
   float eu_div, eu_shrink;
   float* dense_out;  // dense mode (TopK == 0 / full Gram): [n_range, n_cols] row-major, out[target - col_begin, neighbour]
-  // K1-C (sim_k1c.cuh): words per bitmap, ring slots (power of two), log2 of the deep-table slots, norm tiles and their
-  // bounds, the n_win = 1 padded row layout with the CSC-side (row start, row chunks) list, the work items of the launch
-  // (new column, local column, csc begin, csc end), and the list + counter that receive the columns to redo
-  int bm_words, ring_slots, t4bits, ntile;
+  // K1-D (sim_k1d.cuh): 4-bit counter words, key-buffer slots, norm tiles and their bounds, the n_win = 1 padded row
+  // layout with the CSC-side (row start, row chunks) list, the work items of the launch (new column, local column, csc
+  // begin, csc end), the list + counter that receive the columns to redo, and a test hook (every n-th column is handed back)
+  int bm_words, cap_d, fail_every, ntile;
   const float* __restrict__ tbnd;
   const int* __restrict__ csr_idx1;
   const int2* __restrict__ csc_seg;
@@ -967,7 +967,7 @@ __global__ void tile_bounds_kernel(const int2* __restrict__ BN, int n_cols, int 
   tileB[g] = __int_as_float(BN[j].x);
 }
 
-#include "sim_k1c.cuh"
+#include "sim_k1d.cuh"
 
 // ------------------------------------------------------------------------------------------------------
 // preprocessing kernels (constructor work of pyx:147-209, on the device)
@@ -1187,14 +1187,14 @@ struct b200_sim_s {
   DevBuf<int2> csr_ent, csc_ent, BN;
   DevBuf<float> A, tileB;
   int lpu_log2 = 3;
-  // K1-C (binary path, large sparse catalogues): second row layout with one window, CSC-side row locations, norm tile
+  // K1-D (binary path, large sparse catalogues): second row layout with one window, CSC-side row locations, norm tile
   // bounds, ring / table geometry, routing threshold (expected hits per neighbour of a column) and last-launch statistics
   bool want_k1c = true, k1c = false;
   DevBuf<int> csr_idx1, fail;
   DevBuf<int2> csc_seg;
   DevBuf<float> tbnd;
   DevBuf<int4> worklist;
-  int bm_words = 0, ring_slots = 0, t4bits = 0, ntile = 0;
+  int bm_words = 0, cap_d = 0, fail_every = 0, ctas_per_sm = 0, ntile = 0;
   size_t smem1_bytes = 0;
   double k1c_lambda = 0.75;
   int k1c_min_cols = 32768;
@@ -1233,13 +1233,13 @@ sim_kernel_t kernel_for(int formula, bool binary, bool pack) {
   }
 }
 
-sim_kernel_t k1c_kernel_for(int formula) {
+sim_kernel_t k1d_kernel_for(int formula) {
   switch (formula) {
-    case F_PROD: return sim_k1c_kernel<F_PROD>;
-    case F_NONORM: return sim_k1c_kernel<F_NONORM>;
-    case F_JACCARD: return sim_k1c_kernel<F_JACCARD>;
-    case F_DICE: return sim_k1c_kernel<F_DICE>;
-    default: return sim_k1c_kernel<F_TVERSKY>;
+    case F_PROD: return sim_k1d_kernel<F_PROD>;
+    case F_NONORM: return sim_k1d_kernel<F_NONORM>;
+    case F_JACCARD: return sim_k1d_kernel<F_JACCARD>;
+    case F_DICE: return sim_k1d_kernel<F_DICE>;
+    default: return sim_k1d_kernel<F_TVERSKY>;
   }
 }
 
@@ -1475,7 +1475,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
     const bool f_ok_c = h->formula == F_PROD || h->formula == F_NONORM || h->formula == F_JACCARD || h->formula == F_DICE ||
                         (h->formula == F_TVERSKY && h->ta >= 0.f && h->tb >= 0.f);  // decreasing in the neighbour's norm term
     if (h->want_k1c && f_ok_c && nnz > 0 && n_cols >= h->k1c_min_cols) {
-      // K1-C layout: the same rows once more as ONE window -- whole rows padded to 16-byte chunks with the index win1
+      // K1-D layout: the same rows once more as ONE window -- whole rows padded to 16-byte chunks with the index win1
       // (>= n_cols) -- and, per CSC entry, where its user's padded row lives (start, length in 16-byte chunks)
       const int win1 = ((n_cols + 7) / 8) * 8;
       DevBuf<int> sp1((size_t)n_rows * 2), len1((size_t)n_rows + 1), poff1((size_t)n_rows + 1), split1((size_t)n_rows * 2);
@@ -1494,7 +1494,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
                                                                         h->csr_idx1.get(), split1.get()); count_launch();
       h->csc_seg.alloc((size_t)nnz + 2);
       B200_CUDA(cudaMemsetAsync(h->csc_seg.get() + nnz, 0, 2 * sizeof(int2), st));
-      k1c_csc_seg_kernel<<<GRID1D, 256, 0, st>>>(h->csc_idx.get(), split1.get(), nnz, h->csc_seg.get()); count_launch();
+      k1d_csc_seg_kernel<<<GRID1D, 256, 0, st>>>(h->csc_idx.get(), split1.get(), nnz, h->csc_seg.get()); count_launch();
       B200_CUDA(cudaStreamSynchronize(st));
     }
     h->csr_idx = std::move(idx_pad);
@@ -1517,27 +1517,34 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   if (!h->binary) h->csr_idx.release();  // the AoS copy carries the indices
   h->counter.alloc(1);
   h->order.alloc((size_t)n_cols);
-  // ---- K1-C geometry and eligibility (sim_k1c.cuh)
+  // ---- K1-D geometry and eligibility (sim_k1d.cuh)
   h->k1c = false;
   if (h->csc_seg.n > 0) {
     const int win1 = ((n_cols + 7) / 8) * 8;
-    h->ntile = (n_cols + (1 << C_TILE_LOG2) - 1) >> C_TILE_LOG2;
-    h->bm_words = (((win1 + 32 + 31) / 32) + 3) / 4 * 4;
-    auto total_bytes = [&](int slots, int t4bits) {
-      return (long long)slots * (C_PIECE_BYTES + 16 + 16) + 2ll * (C_STAGE + 2) * 8 + 3ll * h->bm_words * 4 + (8ll << t4bits) +
-             (long long)h->cap_alloc * 8 + (long long)SBINS * 4 + ((long long)h->ntile + 1) * 4 + 16 + 8 + 128;
-    };
-    const long long avail = (long long)max_smem - (long long)sizeof(Shared) - (long long)sizeof(K1CShared) - 256;
-    int slots = 0, t4 = 0;
-    for (int tb4 = 12; tb4 >= 9 && !slots; --tb4)      // deep table: 4096 .. 512 slots
-      for (int sl = 256; sl >= 64 && !slots; sl >>= 1)  // ring: 128 KB .. 32 KB
-        if (total_bytes(sl, tb4) <= avail) { slots = sl; t4 = tb4; }
-    if (slots) {
-      h->ring_slots = slots;
-      h->t4bits = t4;
-      h->smem1_bytes = (size_t)total_bytes(slots, t4);
+    h->ntile = (n_cols + (1 << D_TILE_LOG2) - 1) >> D_TILE_LOG2;
+    h->bm_words = ((win1 / 8 + 1) + 3) / 4 * 4;
+    const long long fixed = (long long)h->bm_words * 4 + ((long long)h->ntile + 1) * 4 + (long long)h->ntile * 4 + 32;
+    // two CTAs per SM when both fit (each CTA also pays its static shared memory and the 1 KB the hardware reserves)
+    cudaFuncAttributes fa{};
+    B200_CUDA(cudaFuncGetAttributes(&fa, k1d_kernel_for(h->formula)));
+    int dev = 0, sm_total = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    const long long need_keys = (long long)h->K + (1ll << D_TILE_LOG2) + 128;  // a pruned buffer always takes one more tile
+    for (int ctas = 2; ctas >= 1 && !h->k1c; --ctas) {
+      long long avail = (long long)sm_total / ctas - (long long)fa.sharedSizeBytes - 1024;
+      avail = std::min<long long>(avail, (long long)max_smem - (long long)fa.sharedSizeBytes);
+      const long long keys = std::min<long long>((avail - fixed) / 8, 8 * D_THREADS);
+      if (keys >= need_keys) {
+        h->ctas_per_sm = ctas;
+        h->cap_d = (int)keys;
+        h->smem1_bytes = (size_t)(fixed + keys * 8);
+        h->k1c = true;
+      }
+    }
+    if (h->k1c) {
       h->tbnd.alloc((size_t)h->ntile + 1);
-      k1c_tile_bounds_kernel<<<div_up(h->ntile + 1, 128), 128, 0, st>>>(h->BN.get(), n_cols, h->ntile, h->tbnd.get()); count_launch();
+      k1d_tile_bounds_kernel<<<div_up(h->ntile + 1, 128), 128, 0, st>>>(h->BN.get(), n_cols, h->ntile, h->tbnd.get()); count_launch();
       h->fail.alloc(1);
       h->worklist.alloc((size_t)n_cols);
       h->h_old2new.resize((size_t)n_cols);
@@ -1545,8 +1552,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
       B200_CUDA(cudaMemcpyAsync(h->h_old2new.data(), h->old2new.get(), sizeof(int) * (size_t)n_cols, cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaMemcpyAsync(h->h_csc_ptr.data(), h->csc_ptr.get(), sizeof(int) * ((size_t)n_cols + 1), cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaStreamSynchronize(st));
-      B200_CUDA(cudaFuncSetAttribute(k1c_kernel_for(h->formula), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem1_bytes));
-      h->k1c = true;
+      B200_CUDA(cudaFuncSetAttribute(k1d_kernel_for(h->formula), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem1_bytes));
     }
   }
   if (!h->k1c) { h->csr_idx1.release(); h->csc_seg.release(); }
@@ -1573,7 +1579,7 @@ int b200_sim_create(b200_sim_t* out, int64_t n_rows, int64_t n_cols, int64_t nnz
     B200_REQUIRE(h_indptr && (nnz == 0 || (h_indices && h_data)), "b200_sim_create: NULL input array");
     h = new b200_sim_s();
     h->allow_pack = getenv("B200REC_NO_PACK") == nullptr;  // test hook: force 32-bit counters on the binary path
-    // K1-C routing: on by default for binary data with >= k1c_min_cols columns; B200REC_K1C=0 disables it, the other two
+    // K1-D routing: on by default for binary data with >= k1c_min_cols columns; B200REC_K1C=0 disables it, the other two
     // variables are test hooks (small matrices, forced overflow -> redo path)
     if (const char* e = getenv("B200REC_K1C")) h->want_k1c = atoi(e) != 0;
     if (const char* e = getenv("B200REC_K1C_LAMBDA")) h->k1c_lambda = atof(e);
@@ -1671,9 +1677,9 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
                         cudaStream_t st) {
   const int n_range = end_col - start_col;
   const bool use_k1c = h->k1c && d_dense == nullptr;
-  // Routing + longest-processing-time-first order of the local columns (cached per range).  With K1-C the columns whose
-  // expected hits per neighbour (gathered entries / n_cols) stay below k1c_lambda go to the bitmap kernel (`worklist`);
-  // the rest -- and whatever the bitmap kernel hands back -- go to the window kernel (`order`).
+  // Routing + longest-processing-time-first order of the local columns (cached per range).  With K1-D the columns whose
+  // expected hits per neighbour (gathered entries / n_cols) stay below k1c_lambda go to the nibble-counter kernel (`worklist`);
+  // the rest -- and whatever that kernel hands back -- go to the window kernel (`order`).
   if (h->order_lo != start_col || h->order_hi != end_col) {
     const unsigned long long* w = h->h_work.data() + start_col;
     std::vector<int> sparse;
@@ -1723,18 +1729,18 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   p.eu_shrink = h->shrink;
   p.dense_out = d_dense;
   p.prof = h->prof_on ? h->prof.get() : nullptr;
-  p.bm_words = h->bm_words; p.ring_slots = h->ring_slots; p.t4bits = h->t4bits; p.ntile = h->ntile; p.tbnd = h->tbnd.get();
+  p.bm_words = h->bm_words; p.cap_d = h->cap_d; p.fail_every = h->fail_every; p.ntile = h->ntile; p.tbnd = h->tbnd.get();
   p.csr_idx1 = h->csr_idx1.get(); p.csc_seg = h->csc_seg.get(); p.worklist = h->worklist.get();
   p.redo = h->order.get(); p.fail = h->fail.get();
   p.n_range_dev = nullptr;
   B200_CUDA(cudaEventRecord(h->ev0, st));
   if (n_sparse > 0) {
-    // bitmap kernel first; columns whose deep table overflows are appended to the window kernel's list, whose length
+    // nibble-counter kernel first; columns with an overflowed counter are appended to the window kernel's list, whose length
     // the window kernel then reads from the device (no host round trip between the two launches)
     B200_CUDA(cudaMemcpyAsync(h->fail.get(), &h->n_dense_last, sizeof(int), cudaMemcpyHostToDevice, st));
     KParams q = p;
     q.n_range = n_sparse;
-    k1c_kernel_for(h->formula)<<<std::min(n_sparse, h->n_sm), THREADS, h->smem1_bytes, st>>>(q);
+    k1d_kernel_for(h->formula)<<<std::min(n_sparse, h->n_sm * h->ctas_per_sm), D_THREADS, h->smem1_bytes, st>>>(q);
     B200_CUDA(cudaGetLastError());
     count_launch();
     B200_CUDA(cudaMemsetAsync(h->counter.get(), 0, sizeof(int), st));
@@ -1816,19 +1822,16 @@ int b200_sim_debug_phase_cycles(b200_sim_t h, int enable, uint64_t* out8) {
   });
 }
 
-int b200_sim_debug_k1c(b200_sim_t h, int set_t4bits, int* enabled, int* t4bits, int* n_bitmap_cols, int* n_window_cols) {
+int b200_sim_debug_k1c(b200_sim_t h, int set_fail_every, int* enabled, int* ctas_per_sm, int* n_bitmap_cols, int* n_window_cols) {
   return guarded([&] {
     B200_REQUIRE(h != nullptr, "b200_sim_debug_k1c: NULL handle");
-    if (set_t4bits > 0 && h->k1c) {
-      B200_REQUIRE(set_t4bits >= 4 && set_t4bits <= h->t4bits, "b200_sim_debug_k1c: t4bits must be in [4, %d]", h->t4bits);
-      h->t4bits = set_t4bits;  // the allocation keeps its size; a smaller deep table only overflows earlier
-    }
+    if (set_fail_every >= 0 && h->k1c) h->fail_every = set_fail_every;  // 0 = off; n: every n-th local column is handed back
     if (enabled) *enabled = h->k1c ? 1 : 0;
-    if (t4bits) *t4bits = h->k1c ? h->t4bits : 0;
+    if (ctas_per_sm) *ctas_per_sm = h->k1c ? h->ctas_per_sm : 0;
     if (n_bitmap_cols) *n_bitmap_cols = h->n_sparse_last;  // routing of the last launch
     if (n_window_cols) {
       *n_window_cols = h->n_dense_last;
-      if (h->k1c && h->n_sparse_last > 0) {  // the bitmap kernel's redo count is on the device
+      if (h->k1c && h->n_sparse_last > 0) {  // the nibble kernel's redo count is on the device
         B200_CUDA(cudaDeviceSynchronize());
         B200_CUDA(cudaMemcpy(n_window_cols, h->fail.get(), sizeof(int), cudaMemcpyDeviceToHost));
       }

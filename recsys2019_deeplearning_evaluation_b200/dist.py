@@ -74,13 +74,18 @@ def compute_similarity_sharded(sim, group=None, assemble=True):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# K2 data parallelism: user-sharded Hogwild BPR-MF with a replicated item-factor table.
-# Rank r draws its samples from users [lo_r, hi_r) only, so user rows are private; the item factors are replicated and
-# after every epoch the ranks' item-factor DELTAS are summed over NCCL:  V <- V_prev + sum_r (V_r - V_prev)
-# (every rank's updates count once, the Hogwild reading of "all updates are applied").
+# K2 data parallelism: user-sharded Hogwild BPR-MF with a replicated item-factor table (SURVEY.md 8(e)).
+# Rank r draws its samples from users [lo_r, hi_r) only, so user rows are private.  The item factors are replicated; what
+# the ranks exchange is each rank's own MOVEMENT of the table since its last snapshot:
+#     snapshot k:  own_k = V - B,  B = V          (fused pass, csrc/mf_sgd.cu mf_delta_snapshot_kernel)
+#     all-reduce:  sum_k = sum_r own_k            (NCCL, asynchronous, on a side stream)
+#     apply k:     V += sum_k - own_k,  B += ...  (fused pass with RED.ADD: the trainer keeps writing V meanwhile)
+# The apply of exchange k runs when exchange k + 1 starts, i.e. one epoch later: the collective is hidden behind the next
+# epoch's training kernel and every update of every rank reaches every replica exactly once (bounded staleness: one
+# epoch -- the Hogwild reading of "all updates are applied"; flush() drains the pipeline).
 
 def sync_replicated_delta(V, V_prev, group=None):
-    """In place: V <- V_prev + all_reduce_sum(V - V_prev); V_prev <- V.  Works on CPU tensors (gloo) and CUDA (NCCL)."""
+    """Blocking form: V <- V_prev + all_reduce_sum(V - V_prev); V_prev <- V.  CPU tensors (gloo) and CUDA (NCCL)."""
     import torch.distributed as dist
     delta = V - V_prev
     dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
@@ -89,13 +94,94 @@ def sync_replicated_delta(V, V_prev, group=None):
     return V
 
 
-class ShardedBPR:
-    """One rank of a user-sharded Hogwild BPR-MF run (MatrixFactorization_Cython_Epoch semantics per sample)."""
+class ReplicatedDeltaExchange:
+    """Overlapped exchange of one replicated fp32 table (see the protocol above).  `exchange()` is called after a
+    training epoch has been enqueued on the current stream; it never blocks the host or the training stream."""
 
-    def __init__(self, URM, group=None, **mf_kwargs):
+    def __init__(self, V, group=None):
+        import torch
+        self.V, self.group = V, group
+        self.B = V.clone()
+        self.own = torch.zeros_like(V)
+        self.sum = torch.zeros_like(V)
+        self.work = None
+        self.cuda = V.is_cuda
+        self.comm = torch.cuda.Stream(device=V.device) if self.cuda else None
+        assert V.numel() % 4 == 0 or not self.cuda, "the fused exchange kernels move float4 elements"
+
+    def _snapshot(self):
+        if self.cuda:
+            import ctypes
+            import torch
+            from . import _lib
+            _lib.check(_lib.load().b200_mf_delta_snapshot_device(self.V.data_ptr(), self.B.data_ptr(), self.own.data_ptr(), self.sum.data_ptr(),
+                                                                 self.V.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        else:  # gloo tests of the protocol (host logic only)
+            self.own.copy_(self.V - self.B)
+            self.sum.copy_(self.own)
+            self.B.copy_(self.V)
+
+    def _apply(self):
+        if self.cuda:
+            import ctypes
+            import torch
+            from . import _lib
+            _lib.check(_lib.load().b200_mf_delta_apply_device(self.V.data_ptr(), self.B.data_ptr(), self.sum.data_ptr(), self.own.data_ptr(),
+                                                              self.V.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        else:
+            t = self.sum - self.own
+            self.V.add_(t)
+            self.B.add_(t)
+
+    def _step(self):
+        import torch.distributed as dist
+        if self.work is not None:
+            self.work.wait()  # CUDA: the current (side) stream waits for the collective; CPU: blocks
+            self._apply()
+        self._snapshot()
+        self.work = dist.all_reduce(self.sum, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def exchange(self):
+        if not self.cuda:
+            self._step()
+            return
+        import torch
+        ev = torch.cuda.Event()
+        ev.record()  # the epoch just enqueued on the training stream
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ev)
+            self._step()
+
+    def flush(self):
+        """Drains the pipeline: afterwards V holds every rank's movement up to the last exchange()."""
+        if self.work is None:
+            return
+        if not self.cuda:
+            self.work.wait()
+            self._apply()
+            self.work = None
+            return
+        import torch
+        with torch.cuda.stream(self.comm):
+            self.work.wait()
+            self._apply()
+        self.work = None
+        torch.cuda.current_stream().wait_stream(self.comm)
+
+
+class ShardedBPR:
+    """One rank of a user-sharded Hogwild BPR-MF run (MatrixFactorization_Cython_Epoch semantics per sample).
+    scaling="strong": the reference's epoch ((n_users / bs + 1) * bs samples) is split over the ranks;
+    scaling="weak": every rank draws a full epoch's worth of samples from its own user shard per step."""
+
+    def __init__(self, URM, group=None, scaling="strong", overlap=True, **mf_kwargs):
         import torch.distributed as dist
         from .mf_epoch import MatrixFactorization_Cython_Epoch
-        self.group = group
+        if mf_kwargs.get("random_seed") is None:
+            # every rank draws its initial factors from its own numpy RNG: without a common seed the replicas of the item
+            # table start different and only deltas are exchanged, so they would never agree
+            raise ValueError("ShardedBPR: random_seed is required (the ranks must start from identical factors)")
+        self.group, self.overlap = group, overlap
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         n_users = URM.shape[0]
         bounds = balanced_ranges(np.diff(URM.indptr), self.world)  # equal interaction mass per rank
@@ -104,17 +190,22 @@ class ShardedBPR:
         mf_kwargs.update(sampler="philox", hogwild=True)
         self.epoch_obj = MatrixFactorization_Cython_Epoch(URM, **mf_kwargs)  # same seed -> identical initial factors on every rank
         bs = self.epoch_obj.batch_size
-        total = (n_users // bs + 1) * bs  # the reference's epoch length, split over the ranks
-        self.samples_per_rank = max(bs, (total // self.world // bs) * bs)
+        total = (n_users // bs + 1) * bs  # the reference's epoch length
+        self.samples_per_rank = total if scaling == "weak" else max(bs, (total // self.world // bs) * bs)
         self.epoch_obj.set_user_shard(self.lo, self.hi, self.samples_per_rank, stream_id=self.rank)
         self.U, self.V = self.epoch_obj.device_factors()
-        self.V_prev = self.V.clone()
         self.U0 = self.U.clone()
+        self.xchg = ReplicatedDeltaExchange(self.V.view(-1), group)
 
     def epoch(self):
         self.epoch_obj.epochIteration_Cython()
-        sync_replicated_delta(self.V, self.V_prev, self.group)
+        self.xchg.exchange()
+        if not self.overlap:
+            self.xchg.flush()
         return self.samples_per_rank * self.world
+
+    def flush(self):
+        self.xchg.flush()
 
     def gather_user_factors(self):
         """Every rank ends with the full user-factor table (rows outside a rank's shard never moved there)."""

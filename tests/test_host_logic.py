@@ -115,6 +115,51 @@ def test_sync_replicated_delta_gloo_world2():
         assert np.allclose(V, want) and np.allclose(Vp, want)
 
 
+def _exchange_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from recsys2019_deeplearning_evaluation_b200.dist import ReplicatedDeltaExchange
+    V = torch.zeros(8, dtype=torch.float32)
+    x = ReplicatedDeltaExchange(V)
+    seen = []
+    for epoch in range(3):
+        V[rank] += 1.0            # a private cell per rank ...
+        V[4] += 0.25 * (rank + 1)  # ... and a shared one
+        x.exchange()
+        seen.append(V.numpy().copy())
+    x.flush()
+    q.put((rank, seen, V.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_overlapped_delta_exchange_gloo_world2():
+    """dist.ReplicatedDeltaExchange: the other rank's movement of epoch k becomes visible when exchange k + 1 starts (one
+    epoch of staleness), and after flush() both replicas hold every movement exactly once."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.zeros(8, np.float32)
+    want[0] = want[1] = 3.0
+    want[4] = 3 * 0.25 * (1 + 2)
+    for rank, seen, V in res:
+        assert np.allclose(V, want), (rank, V)
+        other = 1 - rank
+        # after exchange k (0-based) the replica holds its own k + 1 movements and the other rank's first k
+        for k, s_ in enumerate(seen):
+            assert np.isclose(s_[rank], k + 1) and np.isclose(s_[other], k), (rank, k, s_)
+
+
 def _owned_rows_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist

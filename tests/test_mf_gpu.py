@@ -34,9 +34,13 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("dataflow", ["1", "0"])
 @pytest.mark.parametrize("algo,kw", CASES)
-def test_glibc_stream_parity(algo, kw):
-    """Same seed => same replayed libc sample stream => factors agree with the reference semantics."""
+def test_glibc_stream_parity(algo, kw, dataflow, monkeypatch):
+    """Same seed => same replayed libc sample stream => factors agree with the reference semantics.  Both mini-batch
+    kernels: the dataflow kernel (default; the bias cases fall back to the cooperative one by design) and the
+    cooperative two-barriers-per-batch kernel."""
+    monkeypatch.setenv("B200REC_MF_DATAFLOW", dataflow)
     X = synth_urm(300, 120, 0.08, seed=3, values="ratings")
     common = dict(algorithm_name=algo, learning_rate=0.05, random_seed=42, **kw)
     g, o = _cls()(X, **common), MFOracle(X, **common)
@@ -69,6 +73,22 @@ def test_minibatch_mode_is_run_to_run_deterministic():
         else:
             for a, b in zip(got, first):
                 assert np.allclose(a, b, rtol=1e-6, atol=1e-8), float(np.abs(a - b).max())
+
+
+def test_dataflow_kernel_under_heavy_row_sharing():
+    """Few rows, large batches: almost every (row, batch) pair is hit many times, so the accumulate-and-last-arriver path,
+    the waits on the previous batch and the per-row arrival counters all run hot (the C5 shape exercises almost only the
+    hit-once fast path)."""
+    X = synth_urm(40, 12, 0.4, seed=8, values="ratings")
+    for algo, kw in (("MF_BPR", dict(sgd_mode="adam", batch_size=64, n_factors=8, user_reg=1e-3, positive_reg=1e-3, negative_reg=1e-3)),
+                     ("FUNK_SVD", dict(sgd_mode="adagrad", batch_size=97, n_factors=33, negative_interactions_quota=0.4)),
+                     ("MF_BPR", dict(sgd_mode="sgd", batch_size=5, n_factors=128))):
+        common = dict(algorithm_name=algo, learning_rate=0.05, random_seed=13, **kw)
+        g, o = _cls()(X, **common), MFOracle(X, **common)
+        for _ in range(4):
+            g.epochIteration_Cython()
+            o.epochIteration_Cython()
+        _compare(g, o)
 
 
 @pytest.mark.parametrize("algo", ["MF_BPR", "FUNK_SVD"])

@@ -177,32 +177,32 @@ def test_binary_counter_widths(monkeypatch):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# K1-C: the bitmap kernel of the binary path (csrc/sim_k1c.cuh).  It is chosen by itself for binary data with >= 32768
-# columns; the environment hooks route small matrices through it as well.
+# K1-D: the 4-bit-counter kernel of the binary path (csrc/sim_k1d.cuh).  It is chosen by itself for binary data with
+# >= 32768 columns; the environment hooks route small matrices through it as well.
 
 def _k1c_info(sim):
     import ctypes
     from recsys2019_deeplearning_evaluation_b200 import _lib
-    en, tb, nb, nw = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
-    _lib.check(_lib.load().b200_sim_debug_k1c(sim._h, 0, ctypes.byref(en), ctypes.byref(tb), ctypes.byref(nb), ctypes.byref(nw)))
-    return en.value, tb.value, nb.value, nw.value
+    en, ctas, nb, nw = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(_lib.load().b200_sim_debug_k1c(sim._h, -1, ctypes.byref(en), ctypes.byref(ctas), ctypes.byref(nb), ctypes.byref(nw)))
+    return en.value, ctas.value, nb.value, nw.value
 
 
 @pytest.fixture
 def force_k1c(monkeypatch):
     monkeypatch.setenv("B200REC_K1C_MINCOLS", "1")
-    monkeypatch.setenv("B200REC_K1C_LAMBDA", "1e9")  # every non-empty column goes to the bitmap kernel first
+    monkeypatch.setenv("B200REC_K1C_LAMBDA", "1e9")  # every non-empty column goes to the nibble kernel first
     yield monkeypatch
 
 
 @pytest.mark.parametrize("kind", ["cosine", "asymmetric", "jaccard", "tanimoto", "dice", "tversky"])
 def test_k1c_kinds_small_forced(force_k1c, kind):
-    """Every formula the bitmap kernel serves, on a small binary matrix whose counts run deep (deep table + levels)."""
+    """Every formula the nibble kernel serves, on a small binary matrix whose counts reach all three levels."""
     X = synth_urm(700, 300, 0.04, seed=3, values="binary")
     W, sim, _ = _check(X, topK=25, shrink=7, normalize=True, similarity=kind, asymmetric_alpha=0.3, tversky_alpha=0.7,
                        tversky_beta=1.3)
-    en, tb, nb, nw = _k1c_info(sim)
-    assert en == 1 and nb > 0
+    en, ctas, nb, nw = _k1c_info(sim)
+    assert en == 1 and nb > 0 and ctas == 2
 
 
 def test_k1c_not_used_for_valued_or_signed_data(force_k1c):
@@ -213,13 +213,15 @@ def test_k1c_not_used_for_valued_or_signed_data(force_k1c):
 
 
 def test_k1c_sparse_catalogue_auto_and_against_window_kernel(monkeypatch):
-    """230 K columns, sparse counts: chosen without hooks, all columns on the bitmap kernel, same W as the window kernel."""
+    """230 K columns, sparse counts, columns of a handful of users: chosen without hooks, all non-empty columns on the
+    nibble kernel (one CTA per SM: 115 KB of counters), same W as the window kernel."""
     X = synth_urm(20_000, 230_000, 0.0003, seed=42, values="binary")
     kw = dict(topK=50, shrink=10, similarity="cosine")
     cols = np.arange(0, X.shape[1], 997)
     W1, sim1, _ = _check(X, cols=cols, **kw)
-    en, tb, nb, nw = _k1c_info(sim1)
-    assert en == 1 and nb == int((np.diff(X.tocsc().indptr) > 0).sum()) and nb + nw == X.shape[1]  # empty columns: window kernel
+    en, ctas, nb, nw = _k1c_info(sim1)
+    assert en == 1 and ctas == 1
+    assert nb == int((np.diff(X.tocsc().indptr) > 0).sum()) and nb + nw == X.shape[1]  # empty columns: window kernel
     monkeypatch.setenv("B200REC_K1C", "0")
     W0, sim0, _ = _check(X, cols=cols, **kw)
     assert _k1c_info(sim0)[0] == 0
@@ -227,20 +229,21 @@ def test_k1c_sparse_catalogue_auto_and_against_window_kernel(monkeypatch):
 
 
 def test_k1c_c1_shape_levels_and_redo(force_k1c):
-    """C1 shape (counts well above 3 everywhere): levels, deep table and -- with the table shrunk to 16 slots -- the redo
-    path through the window kernel; column ranges; ties resolved like the window kernel."""
+    """C1 shape (counts around 1, a good share >= 3): all three levels, the chunked pushes; with the test hook every 4th
+    column is handed back through the redo list to the window kernel; column ranges; ties resolved like the window kernel."""
     X = synth_urm(10_000, 5_000, 0.01, seed=42, values="binary")
     kw = dict(topK=200, shrink=100, similarity="cosine")
     cols = np.arange(0, 5000, 11)
     W1, sim1, _ = _check(X, cols=cols, **kw)
-    en, tb, nb, nw = _k1c_info(sim1)
+    en, ctas, nb, nw = _k1c_info(sim1)
     assert en == 1 and nb > 0
     import ctypes
     from recsys2019_deeplearning_evaluation_b200 import _lib
     _lib.check(_lib.load().b200_sim_debug_k1c(sim1._h, 4, None, None, None, None))
     W1b = sim1.compute_similarity()
-    en, tb, nb2, nw2 = _k1c_info(sim1)
-    assert tb == 4 and nw2 > nw  # columns were handed back
+    en, ctas, nb2, nw2 = _k1c_info(sim1)
+    assert nw2 >= nw + nb // 4  # columns were handed back
+    _lib.check(_lib.load().b200_sim_debug_k1c(sim1._h, 0, None, None, None, None))
     force_k1c.setenv("B200REC_K1C", "0")
     W0, sim0, _ = _check(X, cols=cols, **kw)
     assert abs(W1 - W0).nnz == 0 and abs(W1b - W0).nnz == 0
@@ -249,13 +252,26 @@ def test_k1c_c1_shape_levels_and_redo(force_k1c):
     assert abs(Wp[:, 1000:1800] - W0[:, 1000:1800]).nnz == 0 and Wp[:, :1000].nnz == 0 and Wp[:, 1800:].nnz == 0
 
 
-def test_k1c_skewed_popularity_and_long_rows(force_k1c):
-    """Popular items (columns of thousands of users: several stage chunks) and users with long profiles (rows of several
-    ring pieces); dense co-occurrence overflows the deep table for the head items -> redo."""
-    X = synth_urm(30_000, 2_000, 0.01, seed=13, values="binary", popularity=1.1)
-    _check(X, cols=np.arange(0, 2000, 13), topK=100, shrink=10, similarity="cosine")
-    Y = synth_urm(300, 4_000, 0.2, seed=5, values="binary")  # rows of ~800 entries = 7 pieces each
+def test_k1c_counter_overflow_is_detected_and_redone(force_k1c):
+    """Dense co-occurrence: nearly every pair of columns shares far more than 15 users, so 4-bit counters overflow in every
+    column; the nibble checksum catches it and the window kernel recomputes the column."""
+    X = synth_urm(2000, 100, 0.3, seed=6, values="binary")
+    W, sim, _ = _check(X, topK=20, shrink=3, similarity="cosine")
+    en, ctas, nb, nw = _k1c_info(sim)
+    assert en == 1 and nb == 100 and nw == 100
+    # a mixed case: a few popular columns overflow, the long tail does not
+    Y = synth_urm(30_000, 2_000, 0.01, seed=13, values="binary", popularity=1.1)
+    W, sim, _ = _check(Y, cols=np.arange(0, 2000, 13), topK=100, shrink=10, similarity="cosine")
+    en, ctas, nb, nw = _k1c_info(sim)
+    assert 0 < nw < 2000
+
+
+def test_k1c_long_rows_and_short_columns(force_k1c):
+    """Users with long profiles (rows of several 512-byte pieces) and columns of one or two users."""
+    Y = synth_urm(300, 4_000, 0.2, seed=5, values="binary")  # rows of ~800 entries
     _check(Y, cols=np.arange(0, 4000, 41), topK=40, shrink=1, similarity="jaccard")
+    Z = synth_urm(500, 3_000, 0.002, seed=5, values="binary")  # columns of ~1 user, rows of ~6 entries
+    _check(Z, topK=10, shrink=0, similarity="cosine")
 
 
 def test_k1c_empty_columns_topk_exceeds_candidates(force_k1c):

@@ -29,8 +29,8 @@ out = (ctypes.c_uint64 * 8)()
 _lib.check(L.b200_sim_debug_phase_cycles(sim._h, 0, out))
 cyc = np.array(list(out), dtype=np.float64)
 en, tb, nb, nw = (ctypes.c_int32() for _ in range(4))
-_lib.check(L.b200_sim_debug_k1c(sim._h, 0, ctypes.byref(en), ctypes.byref(tb), ctypes.byref(nb), ctypes.byref(nw)))
-print("bitmap kernel: enabled=%d t4bits=%d bitmap cols=%d window cols (dense + redo)=%d" % (en.value, tb.value, nb.value, nw.value), flush=True)
-names = ["stage", "mac", "bootstrap|lvl3", "scan|lvl2", "eval|lvl1", "select", "emit", "-"]
+_lib.check(L.b200_sim_debug_k1c(sim._h, -1, ctypes.byref(en), ctypes.byref(tb), ctypes.byref(nb), ctypes.byref(nw)))
+print("nibble kernel: enabled=%d ctas/SM=%d its cols=%d window cols (dense + redo)=%d" % (en.value, tb.value, nb.value, nw.value), flush=True)
+names = ["stage", "mac|gather", "bootstrap|sweep", "scan|lvl3", "eval|lvl2", "select|lvl1", "emit|select+emit", "-"]
 print("phase cycles per column: " + "  ".join("%s=%.0f" % (n, c / X.shape[1]) for n, c in zip(names, cyc)) + "  total=%.0f (kernel %.3f ms)" % (cyc.sum() / X.shape[1], sim.last_kernel_ms()), flush=True)
 t = time.time(); W = sim.table_to_csr(tab); print("to_csr %.3fs nnz=%d" % (time.time() - t, W.nnz), flush=True)
