@@ -277,7 +277,7 @@ def run_b200(args, rank, world, local_rank):
     from recsys2019_deeplearning_evaluation_b200.synth import synth_config, CONFIGS
     from recsys2019_deeplearning_evaluation_b200.similarity import Compute_Similarity_Cython, topk_table_to_csr
     from recsys2019_deeplearning_evaluation_b200 import _lib
-    from recsys2019_deeplearning_evaluation_b200.dist import balanced_ranges, allgather_topk_tables
+    from recsys2019_deeplearning_evaluation_b200.dist import balanced_ranges, allgather_topk_tables, SymmetricTopKTable
     assert torch.cuda.is_available(), "bench.py --impl b200 needs CUDA (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     t0 = time.time()
@@ -296,7 +296,26 @@ def run_b200(args, rank, world, local_rank):
     bounds = balanced_ranges(sim.column_work(), world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
 
+    # N > 1: the full table lives in symmetric memory and the kernel of every rank stores its rows into every rank's copy
+    # (dist.SymmetricTopKTable); NCCL all-gathers of the ranks' slabs are the fallback when symmetric memory cannot be set up
+    table, gather = None, "1 GPU"
+    if world > 1:
+        try:
+            if args.gather == "nccl":
+                raise RuntimeError("--gather nccl")
+            table = SymmetricTopKTable(n_items, sim.K)
+            gather = "kernel stores every finished row into all %d ranks' tables over NVLink (symmetric memory) + barrier" % world
+        except Exception as ex:
+            log("[rank %d] symmetric-memory table unavailable (%r): NCCL all-gather" % (rank, ex))
+            gather = "NCCL all-gather of [n_items/N, K] idx/val/cnt slabs"
+        flag = torch.tensor([1 if table is not None else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            table = None
+
     def step():
+        if table is not None:
+            return table.fill(sim, lo, hi)
         tab = sim.compute_topk_device(lo, hi)
         if world > 1:
             return allgather_topk_tables(tab.idx, tab.val, tab.cnt, bounds)
@@ -339,43 +358,60 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / 1e9 / (kernel_avg_ms * 1e-3)
     traffic = ncu_traffic_per_launch(args.workload) if world == 1 else None
+    import ctypes
+    en, ctas, nb, nw = (ctypes.c_int32() for _ in range(4))
+    _lib.check(_lib.load().b200_sim_debug_k1c(sim._h, -1, ctypes.byref(en), ctypes.byref(ctas), ctypes.byref(nb), ctypes.byref(nw)))
+    kname = ("sim_k1d_kernel (4-bit counters, %d CTAs/SM): %d columns; sim_topk_kernel (window kernel): %d columns" % (
+        ctas.value, nb.value - (nw.value - (hi - lo - nb.value)), nw.value)) if en.value else "sim_topk_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "sim_topk_kernel", "kernel_ms": kernel_avg_ms,
+                "traffic": traffic, "kernel": kname, "kernel_ms": kernel_avg_ms,
                 "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                 "bytes_model": "%d B x %d gathered row entries + CSR/CSC once + 8 B x K x columns" % (bpe, ent)}
 
-    # ---- e2e arm: host scipy CSR in -> scipy CSR out through the reference-facing class
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    # ---- e2e arm: host scipy CSR in -> scipy CSR out through the reference-facing class; inputs in page-locked memory (the
+    # contract's case) and in ordinary pageable numpy arrays (what a caller's scipy matrix is)
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
     h2d = X.data.nbytes + X.indices.nbytes + X.indptr.nbytes
     d2h = 0
-    e2e_times = []
-    for it in range(e2e_steps + 1):  # first pass is a warm-up
-        barrier()
-        t = time.perf_counter()
-        s2 = Compute_Similarity_Cython(Xp, **SIM_KW)
-        torch.cuda.synchronize()
-        t_create = time.perf_counter() - t
-        tab = s2.compute_topk_device(lo, hi)
-        if world > 1:
-            gi, gv, gc = allgather_topk_tables(tab.idx, tab.val, tab.cnt, bounds)
-        else:
-            gi, gv, gc = tab.idx, tab.val, tab.cnt
-        torch.cuda.synchronize()
-        t_kernel = time.perf_counter() - t - t_create
-        if rank == 0:
-            W = topk_table_to_csr(n_items, s2.K, gi.contiguous(), gv.contiguous(), gc.contiguous())
-            d2h = W.data.nbytes + W.indices.nbytes + W.indptr.nbytes
-        barrier()
-        dt = time.perf_counter() - t
-        e2e_parts = {"create_h2d_s": t_create, "kernel_gather_s": t_kernel, "csr_assembly_d2h_s": dt - t_create - t_kernel}
-        s2._dealloc()
-        if it > 0:
-            e2e_times.append(dt)
-    e2e_s = float(np.mean(e2e_times))
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+
+    def e2e_arm(Xin):
+        nonlocal d2h
+        times, parts = [], []
+        for it in range(e2e_steps + 1):  # first pass is a warm-up
+            barrier()
+            t = time.perf_counter()
+            s2 = Compute_Similarity_Cython(Xin, **SIM_KW)
+            torch.cuda.synchronize()
+            t_create = time.perf_counter() - t
+            if table is not None:
+                gi, gv, gc = table.fill(s2, lo, hi)
+            else:
+                tab = s2.compute_topk_device(lo, hi)
+                if world > 1:
+                    gi, gv, gc = allgather_topk_tables(tab.idx, tab.val, tab.cnt, bounds)
+                else:
+                    gi, gv, gc = tab.idx, tab.val, tab.cnt
+            torch.cuda.synchronize()
+            t_kernel = time.perf_counter() - t - t_create
+            if rank == 0:
+                W = topk_table_to_csr(n_items, s2.K, gi.contiguous(), gv.contiguous(), gc.contiguous())
+                d2h = W.data.nbytes + W.indices.nbytes + W.indptr.nbytes
+            barrier()
+            dt = time.perf_counter() - t
+            s2._dealloc()
+            if it > 0:
+                times.append(dt)
+                parts.append({"create_h2d_s": t_create, "kernel_gather_s": t_kernel, "csr_assembly_d2h_s": dt - t_create - t_kernel})
+        if world > 1:  # every sample: max over ranks
+            tt = torch.tensor(times, device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            times = [float(x) for x in tt.tolist()]
+        k = int(np.argsort(times)[len(times) // 2])
+        return {"seconds_median": times[k], "seconds_min": min(times), "seconds_all": times, "breakdown_median_fit": parts[k]}
+
+    e2e_pinned = e2e_arm(Xp)
+    e2e_pageable = e2e_arm(X)
+    e2e_s = e2e_pinned["seconds_median"]
 
     sim_K = sim.K
     sim._dealloc()
@@ -406,6 +442,12 @@ def run_b200(args, rank, world, local_rank):
                 parity = {"ok": False, "error": repr(ex)}
             if world > 1:
                 cpu = None  # reported at N = 1 only
+    tensor = None
+    if world == 1 and not args.no_tensor:
+        try:
+            tensor = tensor_leg(args)
+        except Exception as ex:
+            tensor = {"error": repr(ex)}
     nu, ni, dens = CONFIGS[args.workload]
     name, sms, mem = _lib.device_info()
     out = {
@@ -416,52 +458,63 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": "%s ItemKNN cosine topK=200 shrink=100 on %dx%d density %.4g %s URM" % (
             args.workload, nu, ni, dens, args.values),
             "windows": sim.n_windows, "binary_path": sim.binary_path,
-            "parallelism": "item-sharded x%d + NCCL all-gather of [n_items/N, K] idx/val" % world if world > 1 else "1 GPU",
+            "parallelism": ("item-sharded x%d; " % world + gather) if world > 1 else "1 GPU",
             "timing": "inputs (CSR+CSC %.2f GB) larger than the 126 MB L2; no explicit flush" % (2 * bpe * X.nnz / 1e9)},
         "clocks": clocks,
         "e2e": {"value": n_items / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "seconds_per_fit": e2e_s, "steps": e2e_steps, "breakdown_last_fit": e2e_parts,
-                "what": "Compute_Similarity_Cython(host scipy CSR in pinned memory).compute_similarity() -> scipy CSR"},
+                "seconds_per_fit": e2e_s, "steps": e2e_steps, "pinned_inputs": e2e_pinned,
+                "pageable_inputs": dict(e2e_pageable, value=n_items / e2e_pageable["seconds_median"]),
+                "what": "Compute_Similarity_Cython(host scipy CSR).compute_similarity() -> scipy CSR; value = median fit with the three "
+                        "input arrays in page-locked memory, pageable_inputs = the same with ordinary numpy arrays"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "parity": parity,
         "secondary": secondary,
+        "hot_path_iii": tensor,
         "device": name,
     }
     emit_json(out)
 
 
 def bpr_leg_sharded(args, X, rank, world):
-    """N > 1: user-sharded Hogwild BPR-MF (dist.ShardedBPR): every rank samples its own user range, item factors are
-    replicated and their deltas summed with one NCCL all-reduce per epoch.  The epoch keeps the reference's length
-    ((n_users / 1000 + 1) * 1000 samples in total), so this is strong scaling; time = max over ranks incl. the all-reduce."""
+    """N > 1: user-sharded Hogwild BPR-MF (dist.ShardedBPR): every rank samples its own user range, the item factors are
+    replicated and every rank's movement of the table is exchanged once per epoch with an all-reduce that runs on a side
+    stream behind the next epoch's training kernel (one epoch of staleness).  Two runs: "weak" -- every rank draws a full
+    reference epoch ((n_users / 1000 + 1) * 1000 samples) per step, the data-parallel reading of samples/sec -- and
+    "strong" -- the reference epoch split over the ranks.  Time = device events, max over ranks, pipeline flushed inside."""
     import torch
     import torch.distributed as dist
     from recsys2019_deeplearning_evaluation_b200.dist import ShardedBPR
     f = 128
-    tr = ShardedBPR(X, n_factors=f, batch_size=1000, learning_rate=1e-3, random_seed=42, sgd_mode="sgd")
-    for _ in range(3):
-        tr.epoch()
-    torch.cuda.synchronize(); dist.barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    steps = max(5, args.steps)
-    ev0.record()
-    n = 0
-    for _ in range(steps):
-        n += tr.epoch()
-    ev1.record()
-    torch.cuda.synchronize(); dist.barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    peak, peak_src = measured_peaks()
-    return {"metric": "BPR-MF samples/sec", "unit": "samples/s", "value": n / (ms * 1e-3), "ms_per_epoch": ms / steps,
-            "samples_per_epoch": n // steps,
+    out = {}
+    for scaling in ("weak", "strong"):
+        tr = ShardedBPR(X, scaling=scaling, n_factors=f, batch_size=1000, learning_rate=1e-3, random_seed=42, sgd_mode="sgd")
+        for _ in range(3):
+            tr.epoch()
+        tr.flush()
+        torch.cuda.synchronize(); dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = max(10, args.steps)
+        ev0.record()
+        n = 0
+        for _ in range(steps):
+            n += tr.epoch()
+        tr.flush()
+        ev1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[scaling] = {"value": n / (ms * 1e-3), "ms_per_step": ms / steps, "samples_per_step": n // steps}
+        del tr
+        torch.cuda.empty_cache()
+    return {"metric": "BPR-MF samples/sec", "unit": "samples/s", "value": out["weak"]["value"], "scaling": "weak",
+            "ms_per_epoch": out["weak"]["ms_per_step"], "samples_per_epoch": out["weak"]["samples_per_step"],
+            "strong_scaling": out["strong"],
             "config": {"workload": "%s MF_BPR n_factors=%d sgd lr=1e-3" % (args.workload, f),
-                       "parallelism": "user-sharded hogwild x%d, item factors replicated, NCCL all-reduce of the item-factor deltas (%.0f MB) per epoch" % (
-                           world, X.shape[1] * f * 4 / 1e6)},
-            "scaling": "strong"}
+                       "parallelism": "user-sharded hogwild x%d, item factors replicated, one NCCL all-reduce of the ranks' item-factor movement (%.0f MB) per epoch, overlapped with the next epoch" % (
+                           world, X.shape[1] * f * 4 / 1e6)}}
 
 
 def bpr_leg(args, X):
@@ -499,6 +552,30 @@ def bpr_leg(args, X):
                                "roofline": {"bound": "hbm", "achieved": n * 6 * f * 4 / 1e9 / dev, "peak": peak, "unit": "GB/s",
                                             "frac": n * 6 * f * 4 / 1e9 / dev / peak, "peak_source": peak_src}}
         m._dealloc()
+    if not args.no_cpu_baseline:
+        # parity of the reference-semantics mode at the benchmarked shape: one epoch of the dataflow kernel on a device-drawn
+        # stream, the same stream and initial factors replayed through the C oracle (itself pinned to the compiled reference)
+        try:
+            from oracle.sgd_oracle import MFOracle
+            kw = dict(n_factors=f, algorithm_name="MF_BPR", batch_size=1000, learning_rate=1e-3, random_seed=7, sgd_mode="sgd",
+                      user_reg=1e-4, positive_reg=1e-4, negative_reg=1e-4)
+            t = time.perf_counter()
+            g = MatrixFactorization_Cython_Epoch(X, sampler="philox", **kw)
+            init = (g.get_USER_factors(), g.get_ITEM_factors())
+            g.epochIteration_Cython()
+            o = MFOracle(X, init_factors=init, samples=g.get_samples(), **kw)
+            o.epochIteration_Cython()
+            U, V = g.get_USER_factors(), g.get_ITEM_factors()
+            ok = bool(np.allclose(U, o.get_USER_factors(), rtol=1e-4, atol=2e-6) and np.allclose(V, o.get_ITEM_factors(), rtol=1e-4, atol=2e-6))
+            moved = float(np.abs(V - init[1]).max())
+            res["parity"] = {"ok": ok, "max_abs_diff": float(max(np.abs(U - o.get_USER_factors()).max(), np.abs(V - o.get_ITEM_factors()).max())),
+                             "max_abs_movement": moved, "samples": int(g.samples_last_epoch()),
+                             "against": "oracle/sgd_oracle.c mf_epoch on the epoch's own (u, i, j) stream, rtol 1e-4 atol 2e-6",
+                             "seconds": time.perf_counter() - t}
+            g._dealloc()
+            del o, init, U, V
+        except Exception as ex:
+            res["parity"] = {"ok": False, "error": repr(ex)}
     res["value"] = res["modes"]["hogwild_philox"]["value"]
     res["reference_semantics_value"] = res["modes"]["minibatch_bs1000_philox"]["value"]
     if not args.no_cpu_baseline:
@@ -517,6 +594,68 @@ def bpr_leg(args, X):
     return res
 
 
+def tensor_leg(args):
+    """Hot path (iii) as BASELINE.json configs[3] writes it: IALS with 256 factors and EASE_R on the Netflix-shape synthetic
+    URM (C4, 480 K x 17.7 K, binary), one GPU.  Flops per SURVEY.md 8(d): IALS epoch = sum over rows of 2 len f^2 (Gram of the
+    gathered factor rows) + (2/3) f^3 + 2 f^2 (Cholesky + two triangular solves); EASE = 2 sum_u len_u^2 (sparse Gram) + n^3
+    (Cholesky + inverse from the factor).  Roofline bound: tensor (dense contraction); peak = the measured sustained bf16
+    throughput (MEASURED_PEAKS.json), the denominator the contract names -- the kernels compute in 3xTF32 / fp64."""
+    import torch
+    from recsys2019_deeplearning_evaluation_b200.synth import synth_config, CONFIGS
+    from recsys2019_deeplearning_evaluation_b200 import recommenders as R
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak_tf, peak_src = (float(json.load(open(pk))["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)") \
+        if os.path.exists(pk) else (1500.0, "fallback (B200_PROFILING.md)")
+    t0 = time.time()
+    X = synth_config("C4", values="binary")
+    nu, ni = X.shape
+    log("[tensor leg] C4 URM %s nnz=%d generated in %.1fs" % (X.shape, X.nnz, time.time() - t0))
+    res = {"config": {"workload": "C4 (configs[3]): IALS num_factors=256 alpha=1 reg=1e-3 linear, EASE_R l2_norm=1e3 on %dx%d density %.4g binary URM" % CONFIGS["C4"]},
+           "peak_tflops": peak_tf, "peak_source": peak_src}
+    f = 256
+    try:
+        np.random.seed(42)
+        rec = R.IALSRecommender(X, verbose=False)
+        rec.fit(epochs=1, num_factors=f, alpha=1.0, reg=1e-3)  # builds the device state and runs the first epoch (warm-up)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rec._run_epoch(1)
+        ev1.record()
+        torch.cuda.synchronize()
+        sec = ev0.elapsed_time(ev1) * 1e-3
+        flops = float(2 * 2 * f * f * X.nnz + (nu + ni) * (2.0 * f ** 3 / 3.0 + 2.0 * f * f))
+        res["ials"] = {"metric": "IALS row-solves/sec", "value": (nu + ni) / sec, "unit": "rows/s", "seconds_per_epoch": sec, "n_factors": f,
+                       "roofline": {"bound": "tensor", "achieved": flops / sec / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                                    "frac": flops / sec / 1e12 / peak_tf, "flops_per_epoch": flops},
+                       "path": getattr(rec, "last_path", None)}
+        del rec
+    except Exception as ex:
+        res["ials"] = {"error": repr(ex)}
+    torch.cuda.empty_cache()
+    try:
+        ease = R.EASE_R_Recommender(X, verbose=False)
+        secs = []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            ease.fit(topK=None, l2_norm=1e3, verbose=False)
+            torch.cuda.synchronize()
+            secs.append(time.perf_counter() - t)
+        lens = np.diff(X.indptr).astype(np.float64)
+        flops = float(2.0 * (lens ** 2).sum() + float(ni) ** 3)
+        sec = min(secs)
+        res["ease"] = {"metric": "EASE_R fit seconds", "value": sec, "unit": "s", "higher_is_better": False, "seconds_all": secs,
+                       "what": "EASE_R_Recommender(host URM).fit(): H2D, Gram (similarity kernel, dense mode), blocked Cholesky inverse on tcgen05 (3xTF32), B on the device",
+                       "roofline": {"bound": "tensor", "achieved": flops / sec / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                                    "frac": flops / sec / 1e12 / peak_tf, "flops_per_fit": flops}}
+        del ease
+    except Exception as ex:
+        res["ease"] = {"error": repr(ex)}
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -525,12 +664,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C5", help="C1..C5 (synth.CONFIGS); the metric is quoted on C5")
     ap.add_argument("--values", default="binary", choices=["binary", "ratings", "continuous"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-cols", type=int, default=2000, help="columns in the CPU-baseline slice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bpr", action="store_true", help="skip the BPR-MF samples/sec leg")
+    ap.add_argument("--no-tensor", action="store_true", help="skip the C4 IALS / EASE_R leg (hot path iii)")
     ap.add_argument("--ref-workers", type=int, default=64, help="worker processes of the reference arm (capped by the host core count)")
     ap.add_argument("--ref-slice", type=int, default=250)
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: how the ranks' rows reach every rank")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

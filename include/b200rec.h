@@ -100,6 +100,14 @@ int b200_sim_info(b200_sim_t h, int* K, int* n_windows, int* window_cells, int* 
 int b200_sim_compute_device(b200_sim_t h, int start_col, int end_col, int32_t* d_idx, float* d_val,
                             int32_t* d_cnt, void* stream);
 int b200_sim_compute(b200_sim_t h, int start_col, int end_col, int32_t* h_idx, float* h_val, int32_t* h_cnt);
+/* Multi-GPU, item-sharded: like b200_sim_compute_device for the columns [start_col, end_col) this rank
+ * owns, but every finished column is written into n_tables FULL tables -- d_tables[0] the local one, the others the peers'
+ * copies of the same allocation, mapped into this process (symmetric memory over NVLink / NVSwitch) -- by the CTA that
+ * computed it, so the kernel is the all-gather and no collective follows it (a barrier across the ranks does).
+ * Each table is one int32 allocation: idx rows [n_columns, K] at idx_offset, val rows (fp32 bits) at val_offset, cnt
+ * [n_columns] at cnt_offset (offsets in 4-byte elements); row = ORIGINAL column index.  n_tables <= 8. */
+int b200_sim_compute_peers_device(b200_sim_t h, int start_col, int end_col, int n_tables, void* const* d_tables,
+                                  int64_t idx_offset, int64_t val_offset, int64_t cnt_offset, void* stream);
 /* Dense output (TopK == 0, pyx:510-513,597-599; and the full Gram EASE_R asks for with topK = n_items,
  * EASE_R/EASE_R_Recommender.py:55-56): d_out is [end_col - start_col, n_cols] row-major fp32,
  * d_out[target - start_col, neighbour] = W[neighbour, target]; zero where the columns share no row. */
@@ -210,6 +218,21 @@ int b200_slim_get_samples(b200_slim_t h, int32_t* u, int32_t* i, int32_t* j);
  * pyx:1363-1372), row-major fp32, to a host buffer and/or a device buffer (either may be NULL) */
 int b200_slim_get_S_dense(b200_slim_t h, float* h_out, float* d_out);
 int b200_slim_last_epoch_ms(b200_slim_t h, float* ms);
+/* Column-sharded S for catalogues whose dense S does not fit one GPU (the reference's answer to that is
+ * the tree-sparse mode, pyx:509-1031): this handle owns S[:, col_lo:col_hi) as an [n_items, col_hi - col_lo] slab (full
+ * matrix, not the triangular storage).  Every rank creates one with the SAME random_seed and draws the same Philox sample
+ * stream (n_users samples per epoch, pyx:231).  A step over samples [first, first + n_batch) of the epoch:
+ *   partial: d_x[n] = sum over this rank's columns of S[i, s] - S[j, s], s in the user's profile   (pyx:242-255)
+ *   (the caller adds the ranks' d_x: one all-reduce of n_batch floats)
+ *   apply:   gradient from the summed x (pyx:258-263), update of the cells this rank owns            (pyx:266-304)
+ * n_batch = 1 is the reference's recursion exactly; the apply that completes the epoch advances it. */
+int b200_slim_create_sharded(b200_slim_t* out, int64_t n_users, int64_t n_items, int64_t nnz, const int32_t* h_indptr,
+                             const int32_t* h_indices, float learning_rate, float li_reg, float lj_reg, int sgd_mode,
+                             float gamma, float beta_1, float beta_2, uint32_t random_seed, int col_lo, int col_hi);
+int b200_slim_shard_partial_device(b200_slim_t h, int64_t first, int n_batch, float* d_x, void* stream);
+int b200_slim_shard_apply_device(b200_slim_t h, int64_t first, int n_batch, const float* d_x_sum, void* stream);
+/* the slab on the device and its column range */
+int b200_slim_shard_device(b200_slim_t h, float** d_S, int* col_lo, int* col_hi);
 
 /* ------------------------------------------------------------------------------------------------
  * K1b: top-K along the rows / columns of a dense fp32 n x n matrix on the device
@@ -221,6 +244,10 @@ int b200_slim_last_epoch_ms(b200_slim_t h, float* ms);
 enum b200_topk_mode { B200_TOPK_NONZERO = 0, B200_TOPK_ZEROS_OUTRANK = 1 };
 int b200_dense_topk_device(const float* d_matrix, int n, int K, int along_columns, int mode, int32_t* d_idx,
                            float* d_val, int32_t* d_cnt, void* stream);
+/* mode 0 over the lines of a rectangular dense matrix (line l starts at l * stride_line, its cells are stride_inner apart);
+ * reported positions are cell index + index_offset -- the per-row top-K of one column slab of a sharded matrix */
+int b200_dense_topk_rect_device(const float* d_matrix, int n_lines, int n_inner, int64_t stride_line, int64_t stride_inner,
+                                int index_offset, int K, int mode, int32_t* d_idx, float* d_val, int32_t* d_cnt, void* stream);
 /* the same selection over the lines of a compressed sparse n x n matrix on the device (CSC columns or CSR rows):
  * line l holds entries d_ptr[l]..d_ptr[l+1] with positions d_line_idx[] and values d_vals[] */
 int b200_sparse_topk_device(int n, const int32_t* d_ptr, const int32_t* d_line_idx, const float* d_vals, int K,

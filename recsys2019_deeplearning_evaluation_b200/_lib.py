@@ -29,6 +29,8 @@ SIGNATURES = {
     "b200_sim_destroy": (ctypes.c_int, [c_void]),
     "b200_sim_info": (ctypes.c_int, [c_void, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "b200_sim_compute_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void]),
+    "b200_sim_compute_peers_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_void), ctypes.c_int64,
+                                                     ctypes.c_int64, ctypes.c_int64, c_void]),
     "b200_sim_compute_dense_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, c_void, c_void]),
     "b200_sim_compute": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
     "b200_topk_table_to_csr_count": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_void, c_i64_p, c_void]),
@@ -63,6 +65,14 @@ SIGNATURES = {
     "b200_slim_get_samples": (ctypes.c_int, [c_void, c_void, c_void, c_void]),
     "b200_slim_get_S_dense": (ctypes.c_int, [c_void, c_void, c_void]),
     "b200_slim_last_epoch_ms": (ctypes.c_int, [c_void, c_float_p]),
+    "b200_slim_create_sharded": (ctypes.c_int, [ctypes.POINTER(c_void), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void, c_void,
+                                                ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                                ctypes.c_float, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]),
+    "b200_slim_shard_partial_device": (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int, c_void, c_void]),
+    "b200_slim_shard_apply_device": (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int, c_void, c_void]),
+    "b200_slim_shard_device": (ctypes.c_int, [c_void, ctypes.POINTER(c_void), c_int_p, c_int_p]),
+    "b200_dense_topk_rect_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_int, c_void, c_void, c_void, c_void]),
     "b200_dense_topk_device": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void]),
     "b200_sparse_topk_device": (ctypes.c_int, [ctypes.c_int, c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void]),
     "b200_score_spmm_device": (ctypes.c_int, [c_void, ctypes.c_int, c_void, c_void, c_void, c_void, c_void, c_void, ctypes.c_int, c_void, c_void]),

@@ -32,7 +32,7 @@ template <bool SPARSE>
 __global__ void __launch_bounds__(THREADS) topk_lines_kernel(const float* __restrict__ M, const int* __restrict__ ptr,
                                                              const int* __restrict__ sidx, int n_lines, int n_inner_dense,
                                                              long long stride_line, long long stride_inner, int K, int mode,
-                                                             int* out_idx, float* out_val, int* out_cnt) {
+                                                             int* out_idx, float* out_val, int* out_cnt, int idx_off = 0) {
   __shared__ int hist[BINS];
   __shared__ int s_digit, s_need, s_cnt, s_npos, s_nneg;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(THREADS) topk_lines_kernel(const float* __rest
         for (int q = tid; q < n_inner; q += THREADS) {
           const float v = L[(long long)q * stride_inner];
           if (v != 0.f) {
-            const u64 key = (((u64)orderable(v)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)(SPARSE ? LI[q] : q));
+            const u64 key = (((u64)orderable(v)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)(SPARSE ? LI[q] : q + idx_off));
             if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> sh) & ((1u << nb) - 1))], 1);
           }
         }
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(THREADS) topk_lines_kernel(const float* __rest
       for (int q = tid; q < n_inner; q += THREADS) {
         const float v = L[(long long)q * stride_inner];
         if (v != 0.f) {
-          const int qi = SPARSE ? LI[q] : q;
+          const int qi = SPARSE ? LI[q] : q + idx_off;
           const u64 key = (((u64)orderable(v)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)qi);
           if (key >= thr) {
             const int pos = atomicAdd(&s_cnt, 1);
@@ -140,6 +140,19 @@ int b200_dense_topk_device(const float* d_matrix, int n, int K, int along_column
     cudaStream_t st = (cudaStream_t)stream;
     const long long sl = along_columns ? 1 : n, si = along_columns ? n : 1;
     dtk::topk_lines_kernel<false><<<std::min(n, sm_count() * 8), dtk::THREADS, 0, st>>>(d_matrix, nullptr, nullptr, n, n, sl, si, K, mode, d_idx, d_val, d_cnt);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+  });
+}
+
+int b200_dense_topk_rect_device(const float* d_matrix, int n_lines, int n_inner, int64_t stride_line, int64_t stride_inner, int index_offset,
+                                int K, int mode, int32_t* d_idx, float* d_val, int32_t* d_cnt, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(d_matrix && d_idx && d_val && d_cnt, "b200_dense_topk_rect: NULL argument");
+    B200_REQUIRE(n_lines > 0 && n_inner > 0 && K > 0, "b200_dense_topk_rect: bad shape");
+    B200_REQUIRE(mode == 0, "b200_dense_topk_rect: only the non-zero mode (the zeros of the other shards are not visible here)");
+    dtk::topk_lines_kernel<false><<<std::min(n_lines, sm_count() * 8), dtk::THREADS, 0, (cudaStream_t)stream>>>(
+        d_matrix, nullptr, nullptr, n_lines, n_inner, (long long)stride_line, (long long)stride_inner, K, mode, d_idx, d_val, d_cnt, index_offset);
     B200_CUDA(cudaGetLastError());
     count_launch();
   });

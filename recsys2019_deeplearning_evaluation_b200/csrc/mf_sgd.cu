@@ -330,12 +330,15 @@ __global__ void __launch_bounds__(256) mf_hogwild_kernel(const Params p, long lo
 //                        .cg accesses (L2 only), so no stale L1 line can be observed
 // Progress: warps take samples in increasing order and wait only for steps of earlier batches, each of which is taken by
 // one of that batch's samples; with every warp resident (cooperative launch) the smallest unfinished sample never waits.
-__device__ __forceinline__ int ld_acquire(const int* p) {
+__device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// Ordering: a sample spins on its rows' `applied` words with relaxed loads and then executes ONE fence (acquire side) before
+// it reads the rows; after its last write it executes ONE fence (release side) and then publishes with relaxed stores /
+// the arrival atomics.  fence + relaxed access is the PTX release / acquire pattern; one fence serves all three rows.
 
 // pyx:838-876 on one element with L2-only accesses to the state
 __device__ __forceinline__ float adapt_cg(const AdaptCtx& a, float g, float* c, float* m1, float* m2) {
@@ -362,15 +365,16 @@ struct SlotCtx {
   float* P; double* acc; float *c, *m1, *m2;  // row base pointers (state pointers may be null)
   bool direct;
 };
-__device__ __forceinline__ void slot_element(const Params& p, const AdaptCtx& ad, const SlotCtx& s, int q, float old, double term,
-                                             double inv_bs) {
+// returns the element's new value when the slot steps directly (the caller stores it), `old` otherwise
+__device__ __forceinline__ float slot_element(const Params& p, const AdaptCtx& ad, const SlotCtx& s, int q, float old, double term,
+                                              double inv_bs) {
   if (s.direct) {
     float g = (float)(term * inv_bs);  // what apply_row computes from a one-term sum
     g = adapt_cg(ad, g, s.c ? s.c + q : nullptr, s.m1 ? s.m1 + q : nullptr, s.m2 ? s.m2 + q : nullptr);
-    __stcg(s.P + q, old + p.lr * g);
-  } else {
-    atomicAdd(s.acc + q, term);
+    return old + p.lr * g;
   }
+  atomicAdd(s.acc + q, term);
+  return old;
 }
 // the step of a row whose sum is complete (pyx:792-832), L2-only accesses
 __device__ __forceinline__ void apply_row_cg(const Params& p, const AdaptCtx& ad, const SlotCtx& s, int lane, double inv_bs) {
@@ -381,43 +385,41 @@ __device__ __forceinline__ void apply_row_cg(const Params& p, const AdaptCtx& ad
     __stcg(s.acc + q, 0.0);
   }
 }
-// after the elements of a slot are written: publish (direct) or count the arrival and, as the last one, take the step
-__device__ __forceinline__ void slot_finish(const Params& p, const AdaptCtx& ad, const SlotCtx& s, int row, int expect, int batch,
-                                            int lane, double inv_bs) {
-  __threadfence();
-  __syncwarp();
+// after the release fence: publish a directly stepped row, or count the arrival at a shared row and, as the last sample
+// to arrive, take the row's step
+__device__ __forceinline__ void slot_publish(const Params& p, const AdaptCtx& ad, const SlotCtx& s, int row, int expect, int batch,
+                                             int lane, double inv_bs) {
   if (s.direct) {
-    if (lane == 0) st_release(p.applied + row, batch);
+    if (lane == 0) st_relaxed(p.applied + row, batch);
     return;
   }
   int last = 0;
-  if (lane == 0) {
-    last = (atomicAdd(p.arrived + row, 1) + 1 == expect) ? 1 : 0;
-    __threadfence();
-  }
+  if (lane == 0) last = (atomicAdd(p.arrived + row, 1) + 1 == expect) ? 1 : 0;
   last = __shfl_sync(0xffffffffu, last, 0);
   if (!last) return;
+  __threadfence();  // acquire side of the arrival counter: every contribution to the sum is visible
   apply_row_cg(p, ad, s, lane, inv_bs);
   __threadfence();
   __syncwarp();
   if (lane == 0) {
     p.arrived[row] = 0;
     __threadfence();
-    st_release(p.applied + row, batch);
+    st_relaxed(p.applied + row, batch);
   }
 }
 
-template <bool BPR>
-__global__ void __launch_bounds__(256) mf_dataflow_kernel(const Params p, long long n_samples) {
+// ONE4: n_factors is a multiple of 4 and at most 128 -- every lane owns one float4 of each row, read once
+template <bool BPR, bool ONE4>
+__global__ void __launch_bounds__(256, 3) mf_dataflow_kernel(const Params p, long long n_samples) {
   constexpr int S = BPR ? 3 : 2;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int f = p.f, nU = p.n_users;
   const double inv_bs = 1.0 / (double)p.batch_size;
-  const bool vec4 = (f & 3) == 0;
   AdaptCtx ad;
   ad.mode = p.sgd_mode; ad.gamma = p.gamma; ad.beta1 = p.beta1; ad.beta2 = p.beta2; ad.inv1 = ad.inv2 = 1.f;
+  const double rp = (double)p.positive_reg, rn = (double)p.negative_reg, rgu = (double)p.user_reg;
   for (long long g = warp; g < n_samples; g += n_warps) {
     const int batch = (int)(g / p.batch_size);
     const int u = p.su[g], i = p.si[g], j = BPR ? p.sj[g] : 0;
@@ -426,56 +428,88 @@ __global__ void __launch_bounds__(256) mf_dataflow_kernel(const Params p, long l
     const int pu = p.slot_prev[s0], pi = p.slot_prev[s0 + 1], pj = BPR ? p.slot_prev[s0 + 2] : 0;
     const int eu = p.slot_expect[s0], ei = p.slot_expect[s0 + 1], ej = BPR ? p.slot_expect[s0 + 2] : 0;
     if (p.sgd_mode == ADAM) { ad.inv1 = p.inv1_b[batch]; ad.inv2 = p.inv2_b[batch]; }
-    // ---- wait for the three rows' previous steps (every lane acquires for itself)
+    // ---- wait for the three rows' previous steps
     {
       unsigned ns = 20;
-      while (ld_acquire(p.applied + ru) != pu || ld_acquire(p.applied + ri) != pi || (BPR && ld_acquire(p.applied + rj) != pj)) {
+      for (;;) {
+        const int vu = ld_relaxed(p.applied + ru), vi = ld_relaxed(p.applied + ri), vj = BPR ? ld_relaxed(p.applied + rj) : pj;
+        if (vu == pu && vi == pi && vj == pj) break;
         __nanosleep(ns);
         if (ns < 640) ns <<= 1;
       }
+      __threadfence();
     }
     float* Uu = p.U + (size_t)u * f;
     float* Vi = p.V + (size_t)i * f;
     float* Vj = p.V + (size_t)j * f;
-    // ---- dot product on the frozen parameters
-    float x = 0.f;
-    if (vec4) {
-      for (int q = lane * 4; q < f; q += 128) {
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(Uu + q)), b = __ldcg(reinterpret_cast<const float4*>(Vi + q));
-        if (BPR) {
-          const float4 c = __ldcg(reinterpret_cast<const float4*>(Vj + q));
-          x += a.x * (b.x - c.x) + a.y * (b.y - c.y) + a.z * (b.z - c.z) + a.w * (b.w - c.w);
-        } else {
-          x += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-        }
-      }
-    } else {
-      for (int q = lane; q < f; q += 32) x += BPR ? __ldcg(Uu + q) * (__ldcg(Vi + q) - __ldcg(Vj + q)) : __ldcg(Uu + q) * __ldcg(Vi + q);
-    }
-    x = warp_sum(x);
-    // BPR: sigma = 1 / (1 + e^x), pyx:622; FunkSVD (no bias here): err = r - x, pyx:318
-    const double coef = BPR ? (double)(1.f / (1.f + expf(x))) : (double)(p.sr[g] - x);
     const size_t ou = (size_t)u * f, oi = (size_t)i * f, oj = (size_t)j * f;
     SlotCtx su_{Uu, p.accU + ou, p.cU ? p.cU + ou : nullptr, p.m1U ? p.m1U + ou : nullptr, p.m2U ? p.m2U + ou : nullptr, eu == 1};
     SlotCtx si_{Vi, p.accV + oi, p.cV ? p.cV + oi : nullptr, p.m1V ? p.m1V + oi : nullptr, p.m2V ? p.m2V + oi : nullptr, ei == 1};
     SlotCtx sj_{Vj, p.accV + oj, p.cV ? p.cV + oj : nullptr, p.m1V ? p.m1V + oj : nullptr, p.m2V ? p.m2V + oj : nullptr, ej == 1};
-    const double rp = (double)p.positive_reg, rn = (double)p.negative_reg, rgu = (double)p.user_reg;
-    // ---- every element: the three terms from the OLD values, then each row's own action
-    for (int q = lane; q < f; q += 32) {
-      const float af = __ldcg(Uu + q), bf = __ldcg(Vi + q), cf = BPR ? __ldcg(Vj + q) : 0.f;
-      const double a = (double)af, b = (double)bf, c = (double)cf;
-      if (BPR) {
-        slot_element(p, ad, si_, q, bf, coef * a - rp * b, inv_bs);        // pyx:633
-        slot_element(p, ad, sj_, q, cf, -coef * a - rn * c, inv_bs);       // pyx:634
-        slot_element(p, ad, su_, q, af, coef * (b - c) - rgu * a, inv_bs);  // pyx:635
-      } else {
-        slot_element(p, ad, si_, q, bf, coef * a - rp * b, inv_bs);   // pyx:349 (positive_reg, not item_reg)
-        slot_element(p, ad, su_, q, af, coef * b - rgu * a, inv_bs);  // pyx:350
+    if (ONE4) {
+      const int q = lane * 4;
+      const bool on = q < f;
+      float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, c4 = a4;
+      if (on) {
+        a4 = __ldcg(reinterpret_cast<const float4*>(Uu + q));
+        b4 = __ldcg(reinterpret_cast<const float4*>(Vi + q));
+        if (BPR) c4 = __ldcg(reinterpret_cast<const float4*>(Vj + q));
+      }
+      float x = BPR ? a4.x * (b4.x - c4.x) + a4.y * (b4.y - c4.y) + a4.z * (b4.z - c4.z) + a4.w * (b4.w - c4.w)
+                    : a4.x * b4.x + a4.y * b4.y + a4.z * b4.z + a4.w * b4.w;
+      x = warp_sum(x);
+      // BPR: sigma = 1 / (1 + e^x), pyx:622; FunkSVD (no bias here): err = r - x, pyx:318
+      const double coef = BPR ? (double)(1.f / (1.f + expf(x))) : (double)(p.sr[g] - x);
+      if (on) {
+        const float af[4] = {a4.x, a4.y, a4.z, a4.w}, bf[4] = {b4.x, b4.y, b4.z, b4.w}, cf[4] = {c4.x, c4.y, c4.z, c4.w};
+        float na[4], nb[4], nc[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double a = (double)af[e], b = (double)bf[e], c = (double)cf[e];
+          if (BPR) {
+            nb[e] = slot_element(p, ad, si_, q + e, bf[e], coef * a - rp * b, inv_bs);         // pyx:633
+            nc[e] = slot_element(p, ad, sj_, q + e, cf[e], -coef * a - rn * c, inv_bs);        // pyx:634
+            na[e] = slot_element(p, ad, su_, q + e, af[e], coef * (b - c) - rgu * a, inv_bs);  // pyx:635
+          } else {
+            nb[e] = slot_element(p, ad, si_, q + e, bf[e], coef * a - rp * b, inv_bs);   // pyx:349 (positive_reg, not item_reg)
+            na[e] = slot_element(p, ad, su_, q + e, af[e], coef * b - rgu * a, inv_bs);  // pyx:350
+            nc[e] = 0.f;
+          }
+        }
+        if (si_.direct) __stcg(reinterpret_cast<float4*>(Vi + q), make_float4(nb[0], nb[1], nb[2], nb[3]));
+        if (BPR && sj_.direct) __stcg(reinterpret_cast<float4*>(Vj + q), make_float4(nc[0], nc[1], nc[2], nc[3]));
+        if (su_.direct) __stcg(reinterpret_cast<float4*>(Uu + q), make_float4(na[0], na[1], na[2], na[3]));
+      }
+    } else {
+      float x = 0.f;
+      for (int q = lane; q < f; q += 32) x += BPR ? __ldcg(Uu + q) * (__ldcg(Vi + q) - __ldcg(Vj + q)) : __ldcg(Uu + q) * __ldcg(Vi + q);
+      x = warp_sum(x);
+      const double coef = BPR ? (double)(1.f / (1.f + expf(x))) : (double)(p.sr[g] - x);
+      // every element: the terms from the OLD values, then each row's own action
+      for (int q = lane; q < f; q += 32) {
+        const float af = __ldcg(Uu + q), bf = __ldcg(Vi + q), cf = BPR ? __ldcg(Vj + q) : 0.f;
+        const double a = (double)af, b = (double)bf, c = (double)cf;
+        if (BPR) {
+          const float nb = slot_element(p, ad, si_, q, bf, coef * a - rp * b, inv_bs);
+          const float nc = slot_element(p, ad, sj_, q, cf, -coef * a - rn * c, inv_bs);
+          const float na = slot_element(p, ad, su_, q, af, coef * (b - c) - rgu * a, inv_bs);
+          if (si_.direct) __stcg(Vi + q, nb);
+          if (sj_.direct) __stcg(Vj + q, nc);
+          if (su_.direct) __stcg(Uu + q, na);
+        } else {
+          const float nb = slot_element(p, ad, si_, q, bf, coef * a - rp * b, inv_bs);
+          const float na = slot_element(p, ad, su_, q, af, coef * b - rgu * a, inv_bs);
+          if (si_.direct) __stcg(Vi + q, nb);
+          if (su_.direct) __stcg(Uu + q, na);
+        }
       }
     }
-    slot_finish(p, ad, si_, ri, ei, batch, lane, inv_bs);
-    if (BPR) slot_finish(p, ad, sj_, rj, ej, batch, lane, inv_bs);
-    slot_finish(p, ad, su_, ru, eu, batch, lane, inv_bs);
+    // ---- one release fence for all rows, then publish / arrive
+    __threadfence();
+    __syncwarp();
+    slot_publish(p, ad, si_, ri, ei, batch, lane, inv_bs);
+    if (BPR) slot_publish(p, ad, sj_, rj, ej, batch, lane, inv_bs);
+    slot_publish(p, ad, su_, ru, eu, batch, lane, inv_bs);
   }
 }
 
@@ -691,6 +725,12 @@ struct b200_mf_s {
 
 namespace {
 
+const void* dataflow_kernel_for(bool bpr, int f) {
+  const bool one4 = (f % 4) == 0 && f <= 128;
+  if (bpr) return one4 ? (const void*)mf_dataflow_kernel<true, true> : (const void*)mf_dataflow_kernel<true, false>;
+  return one4 ? (const void*)mf_dataflow_kernel<false, true> : (const void*)mf_dataflow_kernel<false, false>;
+}
+
 long long epoch_batches(const b200_mf_s* h) {
   // pyx:586 (BPR: n_users / batch_size + 1) and pyx:292 (FunkSVD: nnz / batch_size + 1)
   return (h->p.algorithm == MF_BPR ? (long long)h->p.n_users : h->nnz) / h->p.batch_size + 1;
@@ -843,8 +883,7 @@ int b200_mf_create(b200_mf_t* out, int64_t n_users, int64_t n_items, int64_t nnz
       p.slot_prev = h->slot_prev.get(); p.slot_expect = h->slot_expect.get();
       p.inv1_b = h->inv1_b.get(); p.inv2_b = h->inv2_b.get();
       int per_sm_df = 0;
-      if (algorithm == MF_BPR) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_df, mf_dataflow_kernel<true>, 256, 0));
-      else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_df, mf_dataflow_kernel<false>, 256, 0));
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_df, dataflow_kernel_for(algorithm == MF_BPR, n_factors), 256, 0));
       B200_REQUIRE(per_sm_df >= 1, "b200_mf_create: dataflow kernel does not fit on an SM");
       h->df_grid = sm_count() * std::min(per_sm_df, 8);
     }
@@ -925,8 +964,7 @@ int b200_mf_epoch(b200_mf_t h, void* stream) {
       long long n_arg = n;
       void* args[] = {(void*)&p, (void*)&n_arg};
       // cooperative launch only for its co-residency guarantee (the progress argument needs every warp resident)
-      if (bpr) B200_CUDA(cudaLaunchCooperativeKernel((void*)mf_dataflow_kernel<true>, dim3(h->df_grid), dim3(256), args, 0, st));
-      else B200_CUDA(cudaLaunchCooperativeKernel((void*)mf_dataflow_kernel<false>, dim3(h->df_grid), dim3(256), args, 0, st));
+      B200_CUDA(cudaLaunchCooperativeKernel(dataflow_kernel_for(bpr, p.f), dim3(h->df_grid), dim3(256), args, 0, st));
     } else {
       void* args[] = {(void*)&p};
       if (p.f % 4 == 0) B200_CUDA(cudaLaunchCooperativeKernel((void*)mf_epoch_kernel<true>, dim3(h->grid), dim3(256), args, 0, st));

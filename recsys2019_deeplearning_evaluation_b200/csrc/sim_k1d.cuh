@@ -37,8 +37,8 @@ constexpr int D_TILE_LOG2 = 10;  // norm tile: 1024 neighbours = 128 counter wor
 
 struct K1DShared {
   int item, nbuf, cnt, adds, nibsum, tstop, chunk_end, chunk_cnt;
-  int need, digit, bincnt;
-  u64 prefix;
+  int need, digit, bincnt, ncand, expect;
+  u64 kor, kand;
   int hist[256];
 };
 
@@ -61,16 +61,29 @@ __device__ u64 d_select(u64* buf, int n, int K, K1DShared* ds, int* n_out) {
   const int tid = threadIdx.x;
   __syncthreads();
   if (n <= K) { *n_out = n; return 0ull; }
-  u64 prefix = 0ull;
+  // digits above the highest bit in which two keys differ are the same for every key: start below them
+  {
+    if (tid == 0) { ds->kor = 0ull; ds->kand = ~0ull; }
+    __syncthreads();
+    u64 o = 0ull, a = ~0ull;
+    for (int q = tid; q < n; q += D_THREADS) { const u64 k = buf[q]; o |= k; a &= k; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { o |= __shfl_xor_sync(0xffffffffu, o, off); a &= __shfl_xor_sync(0xffffffffu, a, off); }
+    if ((tid & 31) == 0) { atomicOr(&ds->kor, o); atomicAnd(&ds->kand, a); }
+    __syncthreads();
+  }
+  const u64 diff = ds->kor ^ ds->kand;
+  int pass = diff ? (63 - __clzll((long long)diff)) >> 3 : 0;
+  u64 prefix = pass < 7 ? (ds->kor >> ((pass + 1) * 8)) << ((pass + 1) * 8) : 0ull;
   int need = K;
-  int pass = 7;
+  const int one = n > 0 ? 1 : 0;  // a run-time 1: a literal makes ptxas emit ATOMS.POPC.INC inside a loop that peels one address per trip
   for (; pass >= 0; --pass) {
     const int shift = pass * 8;
     if (tid < 256) ds->hist[tid] = 0;
     __syncthreads();
     for (int q = tid; q < n; q += D_THREADS) {
       const u64 k = buf[q];
-      if (pass == 7 || (k >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&ds->hist[(int)((k >> shift) & 255ull)], 1);
+      if (pass == 7 || (k >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&ds->hist[(int)((k >> shift) & 255ull)], one);
     }
     __syncthreads();
     if (tid < 32) {  // one warp: bins 255 .. 0, eight per lane, highest bins in lane 0
@@ -137,7 +150,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) { ds.item = atomicAdd(p.counter, 1); ds.nbuf = 0; ds.adds = 0; ds.nibsum = 0; }
+    if (tid == 0) { ds.item = atomicAdd(p.counter, 1); ds.nbuf = 0; ds.adds = 0; ds.nibsum = 0; ds.ncand = 0; }
     __syncthreads();
     const int item = ds.item;
     if (item >= p.n_range) break;
@@ -146,12 +159,15 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
     const size_t out_base = (size_t)lc * K;
     const float Ai = p.A[col];
 
-    // ---------------- gather + count
-    int adds = 0;
+    // ---------------- gather: one fire-and-forget shared atomic per gathered entry, nothing else per entry
+    int expect = 0;  // increments this warp's rows must produce: per row 4 * chunks - padding - 1 (the diagonal, pyx:396)
     for (int k0 = cs + warp * 32; k0 < ce; k0 += D_WARPS * 32) {
       const int nrows = min(32, ce - k0);
       int2 seg = make_int2(0, 0);
-      if (lane < nrows) seg = __ldg(p.csc_seg + k0 + lane);
+      if (lane < nrows) {
+        seg = __ldg(p.csc_seg + k0 + lane);
+        expect += 4 * (seg.y >> 2) - (seg.y & 3) - 1;
+      }
       for (int r0 = 0; r0 < nrows; r0 += D_ROWS) {
         int4 v[D_ROWS];
         int rs[D_ROWS], rn[D_ROWS];
@@ -159,45 +175,68 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
         for (int q = 0; q < D_ROWS; ++q) {
           const int r = r0 + q;
           rs[q] = __shfl_sync(0xffffffffu, seg.x, r & 31);
-          rn[q] = r < nrows ? __shfl_sync(0xffffffffu, seg.y, r & 31) : 0;
-          v[q] = make_int4(-1, -1, -1, -1);
+          rn[q] = r < nrows ? (__shfl_sync(0xffffffffu, seg.y, r & 31) >> 2) : 0;
           if (lane < rn[q]) v[q] = __ldg(reinterpret_cast<const int4*>(p.csr_idx1) + (size_t)rs[q] + lane);
         }
 #pragma unroll
         for (int q = 0; q < D_ROWS; ++q) {
           int c0 = 0;
           for (;;) {
-            const int jj[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+            if (c0 + lane < rn[q]) {
+              const int jj[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int j = jj[c];
-              if ((unsigned)j < (unsigned)p.n_cols && j != col) {  // row padding; the diagonal (pyx:396)
-                atomicAdd(&acc[j >> 3], 1u << ((j & 7) << 2));
-                ++adds;
+              for (int c = 0; c < 4; ++c) {
+                const int j = jj[c];
+                if ((unsigned)j < (unsigned)p.n_cols && j != col) atomicAdd(&acc[j >> 3], 1u << ((j & 7) << 2));
               }
             }
             c0 += 32;
             if (c0 >= rn[q]) break;  // rows longer than 32 chunks (128 entries): next 512 bytes
-            v[q] = make_int4(-1, -1, -1, -1);
             if (c0 + lane < rn[q]) v[q] = __ldg(reinterpret_cast<const int4*>(p.csr_idx1) + (size_t)rs[q] + c0 + lane);
           }
         }
       }
     }
-    adds = __reduce_add_sync(0xffffffffu, adds);
-    if (lane == 0 && adds) atomicAdd(&ds.adds, adds);
+    expect = __reduce_add_sync(0xffffffffu, expect);
+    if (lane == 0 && expect) atomicAdd(&ds.adds, expect);
     __syncthreads();
     PROF_MARK(1);
 
-    // ---------------- sweep: nibble checksum, cells with count >= 3 per norm tile
+    // ---------------- one sweep (128-bit loads): nibble checksum, cells with count >= 3 per norm tile, and the cells themselves
+    // as packed (neighbour << 4 | count) candidates while they fit the key buffer
     {
       int ns = 0;
-      for (int i = tid; i < Wr; i += D_THREADS) {
-        const unsigned w = acc[i];
-        if (!w) continue;
-        ns += nib_sum(w);
-        const int c3 = __popc(nib_ge3(w));
-        if (c3) atomicAdd(&tcnt[i >> (D_TILE_LOG2 - 3)], c3);
+      unsigned* cand = reinterpret_cast<unsigned*>(buf);
+      const int cand_cap = p.cap_d;
+      const uint4* acc4 = reinterpret_cast<const uint4*>(acc);
+      for (int i4 = tid; i4 < ((Wr + 3) >> 2); i4 += D_THREADS) {
+        const uint4 w4 = acc4[i4];
+        if (!(w4.x | w4.y | w4.z | w4.w)) continue;
+        const unsigned ww[4] = {w4.x, w4.y, w4.z, w4.w};
+        unsigned bytes = 0u, any = 0u, m[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          bytes += (ww[e] & 0x0F0F0F0Fu) + ((ww[e] >> 4) & 0x0F0F0F0Fu);  // every byte <= 4 * 30
+          m[e] = nib_ge3(ww[e]);
+          any |= m[e];
+        }
+        ns += (int)__dp4a(bytes, 0x01010101u, 0u);
+        if (any) {
+          const int c3 = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+          atomicAdd(&tcnt[(i4 * 4) >> (D_TILE_LOG2 - 3)], c3);  // the four words of a vector lie in one tile
+          int pos = atomicAdd(&ds.ncand, c3);
+          if (pos + c3 <= cand_cap) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              unsigned mm = m[e];
+              while (mm) {
+                const int q = (__ffs(mm) - 1) >> 2;
+                mm &= mm - 1;
+                cand[pos++] = ((unsigned)((i4 * 4 + e) * 8 + q) << 4) | ((ww[e] >> (q << 2)) & 15u);
+              }
+            }
+          }
+        }
       }
       ns = __reduce_add_sync(0xffffffffu, ns);
       if (lane == 0 && ns) atomicAdd(&ds.nibsum, ns);
@@ -207,7 +246,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
     if (ds.nibsum != ds.adds || forced) {
       // a counter overflowed: the window kernel redoes this column; leave clean state behind
       __syncthreads();
-      if (tid == 0) { p.redo[atomicAdd(p.fail, 1)] = lc; p.out_cnt[lc] = 0; }
+      if (tid == 0) p.redo[atomicAdd(p.fail, 1)] = lc;
       for (int i = tid; i < (W >> 2); i += D_THREADS) reinterpret_cast<int4*>(acc)[i] = make_int4(0, 0, 0, 0);
       for (int i = tid; i < ntile; i += D_THREADS) tcnt[i] = 0;
       continue;
@@ -216,8 +255,39 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
 
     u64 thr = 0ull;  // keys below it cannot be among the K best
     int n_have = 0;  // block-uniform copy of ds.nbuf between pushes
+    const int n3 = ds.ncand;
+    const bool collected = n3 <= p.cap_d;  // every count >= 3 cell sits in the buffer as a packed candidate
+    if (collected) {
+      // all candidates at once: the norm-term gathers of a column are one round trip, not one per sweep step
+      const unsigned* cand = reinterpret_cast<const unsigned*>(buf);
+      u64 keys[4];  // cap_d <= 4 * D_THREADS on this path (host)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int t = q * D_THREADS + tid;
+        keys[q] = 0ull;
+        if (t < n3) {
+          const unsigned cd = cand[t];
+          const int2 bn = __ldg(p.BN + (cd >> 4));
+          const float sv = sim_value<F>(p, (float)(cd & 15u), Ai, __int_as_float(bn.x));
+          if (sv > 0.f) keys[q] = (((u64)__float_as_uint(sv)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)bn.y);
+        }
+      }
+      __syncthreads();  // every packed candidate has been read: the keys may overwrite them
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (keys[q]) buf[atomicAdd(&ds.nbuf, 1)] = keys[q];
+      for (int i = tid; i < ntile; i += D_THREADS) tcnt[i] = 0;
+      __syncthreads();
+      n_have = ds.nbuf;
+      if (n_have >= K) {
+        // every key has count >= 3 and a norm term <= the largest one: that similarity is a floor of the K-th best
+        const float fl = sim_value<F>(p, 3.f, Ai, tbs[ntile]) * (1.f - 1e-6f);
+        if (fl > 0.f) thr = ((u64)__float_as_uint(fl)) << 32;
+      }
+      PROF_MARK(3);
+    }
 #pragma unroll 1
-    for (int level = 3; level >= 1; --level) {
+    for (int level = collected ? 2 : 3; level >= 1; --level) {
       int t_end = ntile;
       if (level < 3) {
         // exactly-`level` cells reach the floor only in the leading norm tiles (tbs[t] = smallest norm term of tile t)
@@ -231,6 +301,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
             if (!(sim_value<F>(p, (float)level, Ai, tbs[t]) >= tsim)) atomicMin(&ds.tstop, t);
           __syncthreads();
           t_end = ds.tstop;
+          __syncthreads();  // everyone has read it before thread 0 of the next level resets it
         }
         if (t_end == 0) continue;
         // cells of this level per allowed tile
@@ -314,14 +385,12 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
     }
     for (int t = tid; t < n_have; t += D_THREADS) {
       const u64 k64 = buf[t];
-      p.out_idx[out_base + t] = (int)(0xFFFFFFFFu - (unsigned)k64);
-      p.out_val[out_base + t] = __uint_as_float((unsigned)(k64 >> 32));
+      emit_entry(p, out_base + t, (int)(0xFFFFFFFFu - (unsigned)k64), __uint_as_float((unsigned)(k64 >> 32)));
     }
     for (int t = n_have + tid; t < K; t += D_THREADS) {
-      p.out_idx[out_base + t] = -1;
-      p.out_val[out_base + t] = 0.f;
+      emit_entry(p, out_base + t, -1, 0.f);
     }
-    if (tid == 0) p.out_cnt[lc] = n_have;
+    if (tid == 0) emit_count(p, lc, n_have);
     for (int i = tid; i < (W >> 2); i += D_THREADS) reinterpret_cast<int4*>(acc)[i] = make_int4(0, 0, 0, 0);
     PROF_MARK(6);
   }
@@ -334,11 +403,14 @@ __global__ void k1d_tile_bounds_kernel(const int2* __restrict__ BN, int n_cols, 
   tb[t] = __int_as_float(BN[min(t << D_TILE_LOG2, n_cols - 1)].x);
 }
 
-// csc_seg[q] = where the padded single-window row of CSC entry q's user lives: (start, length) in 16-byte chunks
-__global__ void k1d_csc_seg_kernel(const int* __restrict__ csc_idx, const int* __restrict__ split1, long long nnz, int2* seg) {
+// csc_seg[q] = where the padded single-window row of CSC entry q's user lives: x = start in 16-byte chunks,
+// y = chunks << 2 | padding entries in the last chunk (0..3)
+__global__ void k1d_csc_seg_kernel(const int* __restrict__ csc_idx, const int* __restrict__ split1, const int* __restrict__ csr_ptr,
+                                   long long nnz, int2* seg) {
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nnz; q += (long long)gridDim.x * blockDim.x) {
     const int u = csc_idx[q];
     const int s = split1[2 * (size_t)u], e = split1[2 * (size_t)u + 1];
-    seg[q] = make_int2(s >> 2, (e - s) >> 2);
+    const int len = csr_ptr[u + 1] - csr_ptr[u];
+    seg[q] = make_int2(s >> 2, (((e - s) >> 2) << 2) | ((e - s) - len));
   }
 }

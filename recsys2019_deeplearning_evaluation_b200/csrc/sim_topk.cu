@@ -67,6 +67,7 @@ constexpr int UB = B200_UB;      // 128-bit loads in flight per lane
 // column's CSC entries -> row-segment bounds and issue L2 prefetches for those row segments, so that the next column's
 // stage and accumulate phases find their three dependent levels of data in L2 instead of DRAM.
 constexpr int MAXTILES = 16;
+#define B200_MAX_PEERS 8  // output tables one launch can write: the local one + up to 7 peers of an 8-GPU box
 
 enum Formula { F_PROD = 0, F_NONORM = 1, F_JACCARD = 2, F_DICE = 3, F_TVERSKY = 4, F_SCALE = 5, F_EUCLID = 6 };
 
@@ -91,9 +92,13 @@ struct KParams {
   int col_begin, n_range;            // original numbering
   const int* __restrict__ order;     // processing order of local columns (descending work), or nullptr
   int* counter;
-  int* out_idx;
-  float* out_val;
-  int* out_cnt;
+  // output tables [columns of the range, K] idx / val and [columns] cnt: n_out copies -- the local one first, then (multi-GPU,
+  // b200_sim_compute_peers_device) the same rows of every peer's table, written straight over NVLink by the CTA that
+  // finished the column, so that no collective follows the kernel
+  int n_out;
+  int* o_idx[B200_MAX_PEERS];
+  float* o_val[B200_MAX_PEERS];
+  int* o_cnt[B200_MAX_PEERS];
   int signed_data;
   // euclidean (Compute_Similarity_Euclidean.py): distance -> similarity mode 0 exp / 1 lin / 2 log, normalize,
   // divisor of normalize_avg_row (n_rows, or 1), shrink as a float, and whether stored values can be negative
@@ -113,6 +118,15 @@ struct KParams {
   const int* n_range_dev;  // window kernel: the number of columns to process is read from here when set
   unsigned long long* prof;  // optional [8] per-phase cycle counters (thread 0 of every CTA), test/bench hook
 };
+
+__device__ __forceinline__ void emit_entry(const KParams& p, size_t pos, int idx, float val) {
+#pragma unroll 1
+  for (int r = 0; r < p.n_out; ++r) { p.o_idx[r][pos] = idx; p.o_val[r][pos] = val; }
+}
+__device__ __forceinline__ void emit_count(const KParams& p, int row, int n) {
+#pragma unroll 1
+  for (int r = 0; r < p.n_out; ++r) p.o_cnt[r][row] = n;
+}
 
 template <int F>
 __device__ __forceinline__ float sim_value(const KParams& p, float d, float a, float b) {
@@ -881,8 +895,7 @@ __device__ void process_column(const KParams& p, int col, int target, int out_ba
 #if B200_GUESS
     if (!NEG) atomicMin(&sh->kmin, hi);
 #endif
-    p.out_idx[(size_t)out_base + t] = (int)(0xFFFFFFFFu - (unsigned)k);
-    p.out_val[(size_t)out_base + t] = __uint_as_float(NEG ? ~hi : hi);
+    emit_entry(p, (size_t)out_base + t, (int)(0xFFFFFFFFu - (unsigned)k), __uint_as_float(NEG ? ~hi : hi));
   }
   *n_emitted = nbuf;
   __syncthreads();
@@ -949,10 +962,9 @@ __global__ void __launch_bounds__(THREADS, 1) sim_topk_kernel(const KParams p) {
       }
     }
     for (int t = n_out + tid; t < p.K; t += THREADS) {
-      p.out_idx[(size_t)out_base_row * p.K + t] = -1;
-      p.out_val[(size_t)out_base_row * p.K + t] = 0.f;
+      emit_entry(p, (size_t)out_base_row * p.K + t, -1, 0.f);
     }
-    if (tid == 0) p.out_cnt[out_base_row] = n_out;
+    if (tid == 0) emit_count(p, out_base_row, n_out);
     __syncthreads();
   }
 }
@@ -1494,7 +1506,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
                                                                         h->csr_idx1.get(), split1.get()); count_launch();
       h->csc_seg.alloc((size_t)nnz + 2);
       B200_CUDA(cudaMemsetAsync(h->csc_seg.get() + nnz, 0, 2 * sizeof(int2), st));
-      k1d_csc_seg_kernel<<<GRID1D, 256, 0, st>>>(h->csc_idx.get(), split1.get(), nnz, h->csc_seg.get()); count_launch();
+      k1d_csc_seg_kernel<<<GRID1D, 256, 0, st>>>(h->csc_idx.get(), split1.get(), h->csr_ptr.get(), nnz, h->csc_seg.get()); count_launch();
       B200_CUDA(cudaStreamSynchronize(st));
     }
     h->csr_idx = std::move(idx_pad);
@@ -1534,7 +1546,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
     for (int ctas = 2; ctas >= 1 && !h->k1c; --ctas) {
       long long avail = (long long)sm_total / ctas - (long long)fa.sharedSizeBytes - 1024;
       avail = std::min<long long>(avail, (long long)max_smem - (long long)fa.sharedSizeBytes);
-      const long long keys = std::min<long long>((avail - fixed) / 8, 8 * D_THREADS);
+      const long long keys = std::min<long long>((avail - fixed) / 8, 4 * D_THREADS);
       if (keys >= need_keys) {
         h->ctas_per_sm = ctas;
         h->cap_d = (int)keys;
@@ -1553,6 +1565,9 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
       B200_CUDA(cudaMemcpyAsync(h->h_csc_ptr.data(), h->csc_ptr.get(), sizeof(int) * ((size_t)n_cols + 1), cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaStreamSynchronize(st));
       B200_CUDA(cudaFuncSetAttribute(k1d_kernel_for(h->formula), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem1_bytes));
+      // the whole unified L1 / shared array as shared memory: without it the driver sizes the carve-out for ONE block and the
+      // second CTA of an SM never becomes resident
+      B200_CUDA(cudaFuncSetAttribute(k1d_kernel_for(h->formula), cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     }
   }
   if (!h->k1c) { h->csr_idx1.release(); h->csc_seg.release(); }
@@ -1673,8 +1688,10 @@ int b200_sim_info(b200_sim_t h, int* K, int* n_windows, int* window_cells, int* 
   });
 }
 
+struct PeerOut { int* idx; float* val; int* cnt; };
+
 static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx, float* d_val, int32_t* d_cnt, float* d_dense,
-                        cudaStream_t st) {
+                        cudaStream_t st, const PeerOut* peers = nullptr, int n_peers = 0) {
   const int n_range = end_col - start_col;
   const bool use_k1c = h->k1c && d_dense == nullptr;
   // Routing + longest-processing-time-first order of the local columns (cached per range).  With K1-D the columns whose
@@ -1722,7 +1739,9 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   p.col_begin = start_col; p.n_range = n_dense;
   p.order = h->order.get();
   p.counter = h->counter.get();
-  p.out_idx = d_idx; p.out_val = d_val; p.out_cnt = d_cnt;
+  p.n_out = 1 + n_peers;
+  p.o_idx[0] = d_idx; p.o_val[0] = d_val; p.o_cnt[0] = d_cnt;
+  for (int r = 0; r < n_peers; ++r) { p.o_idx[1 + r] = peers[r].idx; p.o_val[1 + r] = peers[r].val; p.o_cnt[1 + r] = peers[r].cnt; }
   p.signed_data = (h->signed_data && h->formula != F_EUCLID) ? 1 : 0;  // euclidean similarities are never negative
   p.eu_mode = h->eu_mode; p.eu_norm = h->eu_norm; p.eu_signed = h->signed_data ? 1 : 0;
   p.eu_div = h->eu_avg ? (float)h->n_rows : 1.f;
@@ -1765,6 +1784,27 @@ int b200_sim_compute_device(b200_sim_t h, int start_col, int end_col, int32_t* d
     if (end_col == start_col) return;
     B200_REQUIRE(d_idx && d_val && d_cnt, "b200_sim_compute: NULL output");
     launch_topk(h, start_col, end_col, d_idx, d_val, d_cnt, nullptr, (cudaStream_t)stream);
+  });
+}
+
+int b200_sim_compute_peers_device(b200_sim_t h, int start_col, int end_col, int n_tables, void* const* d_tables, int64_t idx_offset,
+                                  int64_t val_offset, int64_t cnt_offset, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr, "b200_sim_compute_peers: NULL handle");
+    B200_REQUIRE(0 <= start_col && start_col <= end_col && end_col <= h->n_cols, "b200_sim_compute_peers: bad column range [%d,%d)",
+                 start_col, end_col);
+    B200_REQUIRE(n_tables >= 1 && n_tables <= B200_MAX_PEERS && d_tables != nullptr, "b200_sim_compute_peers: 1..%d tables", B200_MAX_PEERS);
+    if (end_col == start_col) return;
+    PeerOut out[B200_MAX_PEERS];
+    for (int r = 0; r < n_tables; ++r) {
+      B200_REQUIRE(d_tables[r] != nullptr, "b200_sim_compute_peers: NULL table");
+      int32_t* base = reinterpret_cast<int32_t*>(d_tables[r]);
+      // rows are addressed by GLOBAL column: the range's first row sits at start_col
+      out[r].idx = base + idx_offset + (int64_t)start_col * h->K;
+      out[r].val = reinterpret_cast<float*>(base + val_offset) + (int64_t)start_col * h->K;
+      out[r].cnt = base + cnt_offset + start_col;
+    }
+    launch_topk(h, start_col, end_col, out[0].idx, out[0].val, out[0].cnt, nullptr, (cudaStream_t)stream, out + 1, n_tables - 1);
   });
 }
 

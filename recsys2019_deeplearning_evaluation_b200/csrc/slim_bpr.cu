@@ -137,6 +137,73 @@ __global__ void __launch_bounds__(256) slim_hogwild_kernel(const Params p) {
   }
 }
 
+// ---- column-sharded S: this rank holds S[:, lo:hi) as an [n_items, width] slab.  Every rank draws the
+// same samples (counter-based Philox: same seed, epoch and sample index); a step handles a batch of them against the frozen
+// S: each rank sums the cells of its own columns into a partial x_uij per sample, the ranks' partials are added by ONE
+// all-reduce of a [batch] vector, and every rank then updates the cells it owns.  batch = 1 is the reference's recursion
+// (pyx:231-312) exactly; larger batches trade staleness inside the batch for fewer exchanges.
+struct ShardParams {
+  Params p;
+  int lo, hi, width;
+  long long first;  // index of the batch's first sample within the epoch
+  int n_batch;
+};
+
+__global__ void __launch_bounds__(256) slim_shard_partial_kernel(const ShardParams sp, float* __restrict__ x_out) {
+  const Params& p = sp.p;
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int n_warps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  for (int n = warp; n < sp.n_batch; n += n_warps) {
+    const long long g = sp.first + n;
+    const int u = p.su[g], i = p.si[g], j = p.sj[g];
+    const int s = p.indptr[u], e = p.indptr[u + 1];
+    const float* Si = p.S + (size_t)i * sp.width - sp.lo;
+    const float* Sj = p.S + (size_t)j * sp.width - sp.lo;
+    float x = 0.f;
+    for (int k = s + lane; k < e; k += 32) {
+      const int sn = p.indices[k];
+      if (sn >= sp.lo && sn < sp.hi) x += Si[sn] - Sj[sn];  // pyx:242-255, this rank's columns
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    if (lane == 0) x_out[n] = x;
+  }
+}
+
+__global__ void __launch_bounds__(256) slim_shard_apply_kernel(const ShardParams sp, const float* __restrict__ x_sum) {
+  const Params& p = sp.p;
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int n_warps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  for (int n = warp; n < sp.n_batch; n += n_warps) {
+    const long long g = sp.first + n;
+    const int u = p.su[g], i = p.si[g], j = p.sj[g];
+    const int s = p.indptr[u], e = p.indptr[u + 1];
+    const float gr = 1.f / (1.f + expf(x_sum[n]));  // pyx:258
+    float gi = gr, gj = gr;
+    if (p.sgd_mode != SGD) {
+      float inv1 = 1.f, inv2 = 1.f;
+      if (p.sgd_mode == ADAM) {  // the powers advance once per sample (pyx:309-312)
+        inv1 = (float)(1.0 / (1.0 - p.b1_pow * pow((double)p.beta1, (double)g)));
+        inv2 = (float)(1.0 / (1.0 - p.b2_pow * pow((double)p.beta2, (double)g)));
+      }
+      // the per-item state is replicated: every rank applies the same gradients to it (i first, then j, pyx:262-263)
+      if (lane == 0) { gi = adapt_item(p, gr, i, inv1, inv2); gj = adapt_item(p, gr, j, inv1, inv2); }
+      gi = __shfl_sync(0xffffffffu, gi, 0);
+      gj = __shfl_sync(0xffffffffu, gj, 0);
+    }
+    float* Si = p.S + (size_t)i * sp.width - sp.lo;
+    float* Sj = p.S + (size_t)j * sp.width - sp.lo;
+    for (int k = s + lane; k < e; k += 32) {
+      const int sn = p.indices[k];
+      if (sn < sp.lo || sn >= sp.hi) continue;
+      if (sn != i) atomicAdd(Si + sn, p.lr * (gi - p.li_reg * Si[sn]));   // pyx:266-283
+      if (sn != j) atomicAdd(Sj + sn, -p.lr * (gj - p.lj_reg * Sj[sn]));  // pyx:285-304
+    }
+  }
+}
+
 // expands the stored matrix into the full n x n view get_S returns before its top-K (diagonal zeroed, pyx:345-355;
 // symmetric mode mirrors the lower triangle, pyx:1363-1372)
 __global__ void slim_full_kernel(const float* __restrict__ S, int n, int symmetric, float* out) {
@@ -237,6 +304,8 @@ struct b200_slim_s {
   DevBuf<double> pow_out;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  int shard_lo = 0, shard_hi = 0;  // column-sharded handle (b200_slim_create_sharded): S is [n_items, shard_hi - shard_lo]
+  long long drawn_epoch = -1;      // the epoch whose sample stream is in su / si / sj
 };
 
 extern "C" {
@@ -290,6 +359,100 @@ int b200_slim_create(b200_slim_t* out, int64_t n_users, int64_t n_items, int64_t
   return rc;
 }
 
+int b200_slim_create_sharded(b200_slim_t* out, int64_t n_users, int64_t n_items, int64_t nnz, const int32_t* h_indptr,
+                             const int32_t* h_indices, float learning_rate, float li_reg, float lj_reg, int sgd_mode, float gamma,
+                             float beta_1, float beta_2, uint32_t random_seed, int col_lo, int col_hi) {
+  if (out) *out = nullptr;
+  b200_slim_s* h = nullptr;
+  int rc = guarded([&] {
+    B200_REQUIRE(out && h_indptr && (nnz == 0 || h_indices), "b200_slim_create_sharded: NULL argument");
+    B200_REQUIRE(n_users > 0 && n_items > 0 && nnz >= 0 && nnz < (1ll << 31) - 1, "b200_slim_create_sharded: bad shape");
+    B200_REQUIRE(sgd_mode >= SGD && sgd_mode <= ADAM, "b200_slim_create_sharded: unknown sgd_mode %d", sgd_mode);
+    B200_REQUIRE(0 <= col_lo && col_lo < col_hi && col_hi <= n_items, "b200_slim_create_sharded: bad column range [%d,%d)", col_lo, col_hi);
+    h = new b200_slim_s();
+    Params& p = h->p;
+    p.n_users = (int)n_users; p.n_items = (int)n_items; p.symmetric = 0; p.sgd_mode = sgd_mode;
+    p.lr = learning_rate; p.li_reg = li_reg; p.lj_reg = lj_reg; p.gamma = gamma; p.beta1 = beta_1; p.beta2 = beta_2;
+    p.b1_pow = beta_1; p.b2_pow = beta_2;
+    h->sampler = 1; h->hogwild = 1;
+    h->seed = random_seed;
+    h->shard_lo = col_lo; h->shard_hi = col_hi;
+    h->d_indptr.alloc((size_t)n_users + 1);
+    h->d_indices.alloc((size_t)std::max<int64_t>(nnz, 1));
+    B200_CUDA(cudaMemcpy(h->d_indptr.get(), h_indptr, sizeof(int) * ((size_t)n_users + 1), cudaMemcpyHostToDevice));
+    if (nnz) B200_CUDA(cudaMemcpy(h->d_indices.get(), h_indices, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
+    p.indptr = h->d_indptr.get(); p.indices = h->d_indices.get();
+    const size_t cells = (size_t)n_items * (size_t)(col_hi - col_lo);
+    h->S.alloc(cells);
+    B200_CUDA(cudaMemset(h->S.get(), 0, cells * sizeof(float)));
+    p.S = h->S.get();
+    if (sgd_mode == ADAGRAD || sgd_mode == RMSPROP) {
+      h->c.alloc((size_t)n_items); B200_CUDA(cudaMemset(h->c.get(), 0, sizeof(float) * (size_t)n_items)); p.c = h->c.get();
+    } else if (sgd_mode == ADAM) {
+      h->m1.alloc((size_t)n_items); h->m2.alloc((size_t)n_items);
+      B200_CUDA(cudaMemset(h->m1.get(), 0, sizeof(float) * (size_t)n_items));
+      B200_CUDA(cudaMemset(h->m2.get(), 0, sizeof(float) * (size_t)n_items));
+      p.m1 = h->m1.get(); p.m2 = h->m2.get();
+    }
+    h->su.alloc((size_t)n_users); h->si.alloc((size_t)n_users); h->sj.alloc((size_t)n_users);
+    p.su = h->su.get(); p.si = h->si.get(); p.sj = h->sj.get();
+    h->pow_out.alloc(2);
+    p.pow_out = h->pow_out.get();
+    B200_CUDA(cudaEventCreate(&h->ev0));
+    B200_CUDA(cudaEventCreate(&h->ev1));
+    *out = h;
+  });
+  if (rc != B200_OK && h) delete h;
+  return rc;
+}
+
+int b200_slim_shard_partial_device(b200_slim_t h, int64_t first, int n_batch, float* d_x, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(h && d_x && h->shard_hi > h->shard_lo, "b200_slim_shard_partial: not a sharded handle");
+    B200_REQUIRE(first >= 0 && n_batch > 0 && first + n_batch <= h->p.n_users, "b200_slim_shard_partial: batch [%lld, +%d) outside the epoch",
+                 (long long)first, n_batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->drawn_epoch != (long long)h->epoch) {  // the epoch's whole stream, identical on every rank
+      slim_sample_kernel<<<div_up(h->p.n_users, 256), 256, 0, st>>>(h->p.indptr, h->p.indices, h->p.n_users, h->p.n_items, h->p.n_users,
+                                                                  h->seed, h->epoch, h->su.get(), h->si.get(), h->sj.get());
+      count_launch();
+      h->drawn_epoch = (long long)h->epoch;
+    }
+    ShardParams sp{h->p, h->shard_lo, h->shard_hi, h->shard_hi - h->shard_lo, (long long)first, n_batch};
+    slim_shard_partial_kernel<<<std::min<int>(div_up(n_batch, 8), sm_count() * 8), 256, 0, st>>>(sp, d_x);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+  });
+}
+
+int b200_slim_shard_apply_device(b200_slim_t h, int64_t first, int n_batch, const float* d_x_sum, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(h && d_x_sum && h->shard_hi > h->shard_lo, "b200_slim_shard_apply: not a sharded handle");
+    B200_REQUIRE(first >= 0 && n_batch > 0 && first + n_batch <= h->p.n_users && h->drawn_epoch == (long long)h->epoch,
+                 "b200_slim_shard_apply: no partial step for this batch");
+    ShardParams sp{h->p, h->shard_lo, h->shard_hi, h->shard_hi - h->shard_lo, (long long)first, n_batch};
+    slim_shard_apply_kernel<<<std::min<int>(div_up(n_batch, 8), sm_count() * 8), 256, 0, (cudaStream_t)stream>>>(sp, d_x_sum);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+    if (first + n_batch == h->p.n_users) {  // the epoch is complete
+      if (h->p.sgd_mode == ADAM) {
+        h->p.b1_pow *= pow((double)h->p.beta1, (double)h->p.n_users);
+        h->p.b2_pow *= pow((double)h->p.beta2, (double)h->p.n_users);
+      }
+      h->epoch += 1;
+    }
+  });
+}
+
+int b200_slim_shard_device(b200_slim_t h, float** d_S, int* col_lo, int* col_hi) {
+  return guarded([&] {
+    B200_REQUIRE(h && h->shard_hi > h->shard_lo, "b200_slim_shard_device: not a sharded handle");
+    if (d_S) *d_S = h->p.S;
+    if (col_lo) *col_lo = h->shard_lo;
+    if (col_hi) *col_hi = h->shard_hi;
+  });
+}
+
 int b200_slim_destroy(b200_slim_t h) {
   if (!h) return B200_OK;
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -301,6 +464,7 @@ int b200_slim_destroy(b200_slim_t h) {
 int b200_slim_epoch(b200_slim_t h, void* stream) {
   return guarded([&] {
     B200_REQUIRE(h != nullptr, "b200_slim_epoch: NULL handle");
+    B200_REQUIRE(h->shard_hi == 0, "b200_slim_epoch: a column-sharded handle steps through b200_slim_shard_partial / _apply");
     cudaStream_t st = (cudaStream_t)stream;
     Params& p = h->p;
     const long long n = p.n_users;  // pyx:231: n_users samples per epoch
@@ -371,6 +535,7 @@ int b200_slim_get_samples(b200_slim_t h, int32_t* u, int32_t* i, int32_t* j) {
 int b200_slim_get_S_dense(b200_slim_t h, float* h_out, float* d_out) {
   return guarded([&] {
     B200_REQUIRE(h && (h_out || d_out), "b200_slim_get_S_dense: NULL argument");
+    B200_REQUIRE(h->shard_hi == 0, "b200_slim_get_S_dense: a column-sharded handle exposes its slab through b200_slim_shard_device");
     const int n = h->p.n_items;
     const size_t cells = (size_t)n * n;
     DevBuf<float> tmp;

@@ -57,17 +57,64 @@ def allgather_topk_tables(idx, val, cnt, bounds, group=None):
     return g_idx[keep], g_val[keep], g_cnt[keep]
 
 
-def compute_similarity_sharded(sim, group=None, assemble=True):
+class SymmetricTopKTable:
+    """The full [n_columns, K] idx / val + [n_columns] cnt table of an item-sharded similarity run, allocated once per rank as
+    symmetric memory (torch.distributed._symmetric_memory: every rank's copy is mapped into every other rank's address space
+    over NVLink / NVSwitch).  `fill(sim, lo, hi)` runs the similarity kernel on this rank's columns with EVERY rank's copy as
+    an output table: the CTA that finishes a column stores its row into all the tables, so the kernel itself is the all-gather
+    (b200_sim_compute_peers_device) and the only collective left is the barrier that says every rank's kernel has finished."""
+
+    MAX_WORLD = 8  # output tables one kernel launch can address (include/b200rec.h)
+
+    def __init__(self, n_columns, K, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > self.MAX_WORLD:
+            raise ValueError("SymmetricTopKTable: at most %d ranks" % self.MAX_WORLD)
+        self.n, self.K = int(n_columns), int(K)
+        self.off_idx, self.off_val, self.off_cnt = 0, self.n * self.K, 2 * self.n * self.K
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm.empty((2 * self.n * self.K + self.n,), dtype=torch.int32, device=dev)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        self.tables = [ptrs[self.rank]] + [ptrs[r] for r in range(self.world) if r != self.rank]  # the local copy first
+        self.idx = self.buf[:self.off_val].view(self.n, self.K)
+        self.val = self.buf[self.off_val:self.off_cnt].view(torch.float32).view(self.n, self.K)
+        self.cnt = self.buf[self.off_cnt:]
+
+    def fill(self, sim, lo, hi):
+        """Every rank calls this with its own column range; returns once the launches are enqueued on the current stream
+        (the closing barrier is stream-ordered too): afterwards idx / val / cnt hold every rank's rows."""
+        import ctypes
+        import torch
+        from . import _lib
+        self.hdl.barrier(channel=0)  # nobody is still reading the previous fill of its copy
+        arr = (ctypes.c_void_p * len(self.tables))(*self.tables)
+        _lib.check(_lib.load().b200_sim_compute_peers_device(sim._h, int(lo), int(hi), len(self.tables), arr, self.off_idx, self.off_val,
+                                                             self.off_cnt, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.hdl.barrier(channel=1)  # every rank's kernel (and with it its stores into this copy) has finished
+        return self.idx, self.val, self.cnt
+
+
+def compute_similarity_sharded(sim, group=None, assemble=True, table=None):
     """Item-sharded compute_similarity: every rank holds the same `sim` (Compute_Similarity_Cython built from the
-    replicated URM).  Returns the scipy CSR W (on every rank) or, with assemble=False, the gathered device table."""
+    replicated URM).  Returns the scipy CSR W (on every rank) or, with assemble=False, the full device table.
+    With a SymmetricTopKTable the kernel writes every rank's copy directly (no collective); without one the ranks' slabs are
+    exchanged with NCCL all-gathers."""
     import torch.distributed as dist
     from .similarity import topk_table_to_csr
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     bounds = balanced_ranges(sim.column_work(), world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    tab = sim.compute_topk_device(lo, hi)
-    g_idx, g_val, g_cnt = allgather_topk_tables(tab.idx, tab.val, tab.cnt, bounds, group)
+    if table is not None:
+        g_idx, g_val, g_cnt = table.fill(sim, lo, hi)
+    else:
+        tab = sim.compute_topk_device(lo, hi)
+        g_idx, g_val, g_cnt = allgather_topk_tables(tab.idx, tab.val, tab.cnt, bounds, group)
     if not assemble:
         return g_idx, g_val, g_cnt
     return topk_table_to_csr(sim.n_columns, sim.K, g_idx.contiguous(), g_val.contiguous(), g_cnt.contiguous())
@@ -268,3 +315,154 @@ def make_sharded_ials(group=None):
             self._half_sharded(self._d_warm_items, self._d_Ct, self._d_U, self._d_V)
 
     return ShardedIALSRecommender
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K3 model parallelism: SLIM-BPR with S sharded by columns.  At 200 K items the dense S is 160 GB: no
+# single GPU holds it (the reference trains such catalogues in its tree-sparse mode, SLIM_BPR_Cython_Epoch.pyx:509-1031).
+# Rank g owns S[:, cols_g]; every rank walks the SAME sample stream (counter-based Philox, common seed); per batch each rank
+# sums its own cells into a partial x_uij per sample, ONE all-reduce of the [batch] vector adds the partials, and every
+# rank updates the cells it owns (csrc/slim_bpr.cu slim_shard_*_kernel).  batch_size = 1 is the reference's recursion.
+
+class ShardedSLIM_BPR:
+    """One rank of a column-sharded SLIM-BPR run.  Mirrors the epoch API of SLIM_BPR_Cython_Epoch (epochIteration_Cython,
+    get_S); the full, non-symmetric S is trained (the triangular storage of symmetric=True does not shard by columns)."""
+
+    _MODE = {"sgd": 0, "adagrad": 1, "rmsprop": 2, "adam": 3}
+
+    def __init__(self, URM_mask, group=None, batch_size=8192, learning_rate=0.01, li_reg=0.0, lj_reg=0.0, topK=150, symmetric=False,
+                 random_seed=None, sgd_mode="adam", gamma=0.995, beta_1=0.9, beta_2=0.999, col_range=None, world_rank=None):
+        import ctypes
+        import scipy.sparse as sps
+        import torch
+        from . import _lib
+        if symmetric:
+            raise NotImplementedError("ShardedSLIM_BPR trains the full S; symmetric=True (triangular storage) is single-GPU only")
+        if random_seed is None:
+            raise ValueError("ShardedSLIM_BPR: random_seed is required (every rank must draw the same sample stream)")
+        if sgd_mode not in self._MODE:
+            raise ValueError("SLIM_BPR_Cython_Epoch: sgd_mode '{}' not recognized".format(sgd_mode))
+        self._lib = _lib.load()
+        self.group = group
+        if world_rank is None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        else:  # explicit placement (tests run several shards in one process and add the partial sums themselves)
+            self.world, self.rank = world_rank
+        X = sps.csr_matrix(URM_mask, dtype=np.float32)
+        if not X.has_sorted_indices:
+            X = X.sorted_indices()
+        self.n_users, self.n_items = X.shape
+        self.topK = min(int(topK), self.n_items)
+        self.batch_size = int(batch_size)
+        if col_range is None:
+            b = np.linspace(0, self.n_items, self.world + 1).astype(np.int64)
+            col_range = (int(b[self.rank]), int(b[self.rank + 1]))
+        self.lo, self.hi = col_range
+        self._h = ctypes.c_void_p()
+        indptr = np.ascontiguousarray(X.indptr, np.int32)
+        indices = np.ascontiguousarray(X.indices, np.int32)
+        _lib.check(self._lib.b200_slim_create_sharded(
+            ctypes.byref(self._h), self.n_users, self.n_items, X.nnz, _lib.ptr(indptr), _lib.ptr(indices), float(learning_rate),
+            float(li_reg), float(lj_reg), self._MODE[sgd_mode], float(gamma), float(beta_1), float(beta_2),
+            int(random_seed) & 0xFFFFFFFF, self.lo, self.hi))
+        self._x = torch.empty(max(1, min(self.batch_size, self.n_users)), dtype=torch.float32, device="cuda")
+
+    def _stream(self):
+        import ctypes
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def partial(self, first, n):
+        from . import _lib
+        _lib.check(self._lib.b200_slim_shard_partial_device(self._h, int(first), int(n), self._x.data_ptr(), self._stream()))
+        return self._x[:n]
+
+    def apply(self, first, n, x_sum):
+        from . import _lib
+        _lib.check(self._lib.b200_slim_shard_apply_device(self._h, int(first), int(n), x_sum.data_ptr(), self._stream()))
+
+    def epochIteration_Cython(self):
+        """n_users samples (pyx:231) in batches; returns the number of samples."""
+        import torch.distributed as dist
+        for first in range(0, self.n_users, self.batch_size):
+            n = min(self.batch_size, self.n_users - first)
+            x = self.partial(first, n)
+            if self.world > 1:
+                dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
+            self.apply(first, n, x)
+        return self.n_users
+
+    def slab(self):
+        """This rank's [n_items, hi - lo] columns of S as a torch CUDA tensor aliasing the trainer's memory."""
+        import ctypes
+        import torch
+        from . import _lib
+        ptr = ctypes.c_void_p()
+        _lib.check(self._lib.b200_slim_shard_device(self._h, ctypes.byref(ptr), None, None))
+
+        class _Arr:
+            def __init__(s, p, shape):
+                s.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (p, False), "version": 3, "strides": None}
+
+        return torch.as_tensor(_Arr(ptr.value, (self.n_items, self.hi - self.lo)), device=torch.device("cuda", torch.cuda.current_device()))
+
+    def local_row_topk(self):
+        """[n_items, K] idx (global column) / val candidates of every row from this rank's columns (K largest non-zero)."""
+        import torch
+        from . import _lib
+        K, w = self.topK, self.hi - self.lo
+        dev = torch.device("cuda", torch.cuda.current_device())
+        idx = torch.empty((self.n_items, K), dtype=torch.int32, device=dev)
+        val = torch.empty((self.n_items, K), dtype=torch.float32, device=dev)
+        cnt = torch.empty((self.n_items,), dtype=torch.int32, device=dev)
+        _lib.check(self._lib.b200_dense_topk_rect_device(self.slab().data_ptr(), self.n_items, w, w, 1, self.lo, K, 0, idx.data_ptr(),
+                                                         val.data_ptr(), cnt.data_ptr(), self._stream()))
+        return idx, val
+
+    @staticmethod
+    def merge_row_topk(cands, n_items, K):
+        """cands: list of (idx, val) [n_items, K] tables of the shards -> scipy CSR with the K largest non-zero cells per row
+        (the dense branch of get_S: similarityMatrixTopK(S.T).T, pyx:371,386)."""
+        import scipy.sparse as sps
+        import torch
+        from . import _lib
+        from .similarity import topk_table_to_csr
+        idx = torch.cat([c[0] for c in cands], dim=1).contiguous()
+        val = torch.cat([c[1] for c in cands], dim=1).contiguous()
+        m = idx.shape[1]
+        ptr = (torch.arange(n_items + 1, dtype=torch.int64, device=idx.device) * m).to(torch.int32)
+        oi = torch.empty((n_items, K), dtype=torch.int32, device=idx.device)
+        ov = torch.empty((n_items, K), dtype=torch.float32, device=idx.device)
+        oc = torch.empty((n_items,), dtype=torch.int32, device=idx.device)
+        import ctypes
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().b200_sparse_topk_device(n_items, ptr.data_ptr(), idx.data_ptr(), val.data_ptr(), K, 0, oi.data_ptr(),
+                                                       ov.data_ptr(), oc.data_ptr(), st))
+        T = topk_table_to_csr(n_items, K, oi, ov, oc)  # T[column, row]: the transpose
+        return sps.csc_matrix((T.data, T.indices, T.indptr), shape=(n_items, n_items)).tocsr()
+
+    def get_S(self):
+        """Row top-K of the full S on every rank: local candidates, one all-gather of the [n_items, K] tables, merge."""
+        import torch
+        import torch.distributed as dist
+        idx, val = self.local_row_topk()
+        if self.world == 1:
+            return self.merge_row_topk([(idx, val)], self.n_items, self.topK)
+        gi = [torch.empty_like(idx) for _ in range(self.world)]
+        gv = [torch.empty_like(val) for _ in range(self.world)]
+        dist.all_gather(gi, idx, group=self.group)
+        dist.all_gather(gv, val, group=self.group)
+        return self.merge_row_topk(list(zip(gi, gv)), self.n_items, self.topK)
+
+    def _dealloc(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.b200_slim_destroy(self._h)
+            import ctypes
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self._dealloc()
+        except Exception:
+            pass

@@ -25,9 +25,11 @@ def loss(U, V):
 
 
 tr = ShardedBPR(X, **kw)
-l0 = loss(tr.U0.cpu().numpy().astype(np.float64), tr.V_prev.cpu().numpy().astype(np.float64))
+l0 = loss(tr.U0.cpu().numpy().astype(np.float64), tr.V.cpu().numpy().astype(np.float64))
 for _ in range(60):
     tr.epoch()
+tr.flush()
+torch.cuda.synchronize()
 U = tr.gather_user_factors().cpu().numpy().astype(np.float64)
 V = tr.V.cpu().numpy().astype(np.float64)
 ls = loss(U, V)
