@@ -26,6 +26,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <stdlib.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -636,6 +638,93 @@ __global__ void mf_sample_kernel(const int* __restrict__ indptr, const int* __re
   if (algorithm == FUNK_SVD) sr[g] = r;
 }
 
+
+// =====================================================================================================================
+// glibc stream on the device.  The reference draws its samples with libc rand() (sampleBPR_Cython pyx:943-987,
+// sampleMSE_Cython :881-938): a sequential recurrence feeding rejection loops, so sample g's first draw depends on how many
+// draws every earlier sample consumed.  The raw stream itself is cheap to produce in order (1 ns per draw on the host);
+// what made the host replay slow (160 ms per C5 epoch) are the dependent memory lookups of the acceptance rules.  Here:
+//   1. the host appends raw draws to a pinned buffer and uploads them;
+//   2. glibc_len_kernel: for EVERY position p of the buffer, how many draws a sample STARTING at p would consume;
+//   3. pointer doubling: J_0[p] = p + len[p], J_{k+1} = J_k o J_k, so that any number of samples can be skipped at once;
+//   4. glibc_emit_kernel: sample g starts where the binary expansion of g leads from position 0; it is re-evaluated there
+//      and written out.  The number of draws the epoch consumed tells the host where the next epoch's stream begins.
+// Bit-identical to the host replay (same draws, same rules); tests compare the two.
+struct GlibcView {
+  const int* __restrict__ raw; int R;  // draws raw[0 .. R)
+  const int* __restrict__ indptr; const int* __restrict__ indices; const float* __restrict__ data;
+  int n_users, n_items, algorithm; float quota;
+};
+
+// the sample starting at raw position p: returns the position after its last draw (> R when the buffer ran out)
+__device__ __forceinline__ int glibc_sample_at(const GlibcView& v, int p, int* u_out, int* i_out, int* j_out, float* r_out) {
+  int q = p;
+  int u = 0, s = 0, n = 0;
+  for (;;) {  // pyx:952-960 / :890-898: users with an empty or a full profile are redrawn
+    if (q >= v.R) return v.R + 1;
+    u = v.raw[q++] % v.n_users;
+    s = v.indptr[u];
+    n = v.indptr[u + 1] - s;
+    if (n != 0 && n != v.n_items) break;
+  }
+  bool positive = true;
+  if (v.algorithm == FUNK_SVD && v.quota != 0.f) {  // pyx:901
+    if (q >= v.R) return v.R + 1;
+    positive = (double)v.raw[q++] <= (double)v.quota * 2147483647.0;
+  }
+  int item = -1;
+  float r = 0.f;
+  if (v.algorithm == MF_BPR || positive) {
+    if (q >= v.R) return v.R + 1;
+    const int k = v.raw[q++] % n;
+    item = v.indices[s + k];
+    if (v.algorithm == FUNK_SVD) r = v.data[s + k];
+  }
+  if (v.algorithm == MF_BPR || !positive) {
+    int neg;
+    for (;;) {
+      if (q >= v.R) return v.R + 1;
+      neg = v.raw[q++] % v.n_items;
+      int lo = 0, hi = n;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (v.indices[s + mid] < neg) lo = mid + 1; else hi = mid; }
+      if (lo == n || v.indices[s + lo] != neg) break;
+    }
+    if (v.algorithm == MF_BPR) { if (j_out) *j_out = neg; } else { item = neg; r = 0.f; }
+  }
+  if (u_out) *u_out = u;
+  if (i_out) *i_out = item;
+  if (r_out) *r_out = r;
+  return q;
+}
+
+__global__ void glibc_len_kernel(const GlibcView v, int* __restrict__ nxt) {  // nxt[p] = start of the following sample; nxt[R] = R
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > v.R) return;
+  nxt[p] = p == v.R ? v.R : min(glibc_sample_at(v, p, nullptr, nullptr, nullptr, nullptr), v.R);
+}
+
+__global__ void glibc_double_kernel(const int* __restrict__ jk, int R, int* __restrict__ jk1) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p <= R) jk1[p] = jk[jk[p]];
+}
+
+// sample g: follow the binary expansion of g through the jump tables (tables[k] = J_k, (R + 1) ints each), evaluate, store
+__global__ void glibc_emit_kernel(const GlibcView v, const int* __restrict__ tables, int levels, long long n_samples, int* su, int* si,
+                                  int* sj, float* sr, int* consumed) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_samples) return;
+  int p = 0;
+  for (int k = 0; k < levels; ++k)
+    if ((g >> k) & 1) p = tables[(size_t)k * (v.R + 1) + p];
+  int u = 0, i = 0, j = 0;
+  float r = 0.f;
+  const int q = p < v.R ? glibc_sample_at(v, p, &u, &i, &j, &r) : v.R + 1;
+  su[g] = u; si[g] = i;
+  if (v.algorithm == MF_BPR) sj[g] = j; else sr[g] = r;
+  if (q > v.R) atomicMax(consumed, 0x7FFFFFFF);  // the buffer ran out somewhere: the host extends it and repeats
+  else if (g == n_samples - 1) atomicMax(consumed, q);
+}
+
 // host replay of glibc srand()/rand() (TYPE_3 additive feedback, r[i] = r[i-31] + r[i-3], 310 discarded, >> 1)
 struct GlibcRand {
   int32_t r[31];
@@ -697,6 +786,13 @@ struct b200_mf_s {
   long long samples_last = 0, cap_samples = 0, epoch_samples_override = 0;
   int shard_lo = 0, shard_hi = 0;  // device sampler draws users from [shard_lo, shard_hi) when set (multi-GPU user sharding)
   int grid = 0;
+  // device-side replay of the glibc stream (glibc_*_kernel): pinned raw draws with the unread tail of the previous epoch in
+  // front, their device copy, the jump tables, the consumed-draw counter
+  bool glibc_device = true;
+  int* h_raw = nullptr;            // pinned
+  long long raw_cap = 0, raw_have = 0;  // capacity / draws currently in h_raw (all unread)
+  DevBuf<int> d_raw, d_tables, d_consumed;
+  long long tables_cap = 0;
   int hog_blocks = 8;  // hogwild CTAs per SM; a sharded (multi-GPU) run leaves room for the collective's CTAs
   // dataflow mode (mf_dataflow_kernel): dependency tables rebuilt from every epoch's sample stream
   bool dataflow = false;
@@ -774,6 +870,57 @@ void host_samples(b200_mf_s* h, long long n) {
   }
 }
 
+
+// The epoch's n samples from the glibc stream, resolved on the device (see glibc_len_kernel).  Synchronises the stream once
+// (the host must know how many draws were consumed before it can continue the stream).
+void glibc_device_samples(b200_mf_s* h, long long n, cudaStream_t st) {
+  const Params& p = h->p;
+  const int per = 3;  // draws of a sample without rejections (user, positive | quota, negative | item)
+  int levels = 1;
+  while ((1ll << levels) < n) ++levels;
+  long long want = n * per + n / 16 + 4096;
+  for (int attempt = 0;; ++attempt) {
+    B200_REQUIRE(attempt < 8 && want < (1ll << 30), "b200_mf_epoch: the glibc replay buffer does not converge (degenerate URM?)");
+    if (want > h->raw_cap) {
+      int* fresh = nullptr;
+      B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&fresh), sizeof(int) * (size_t)want));
+      if (h->raw_have) memcpy(fresh, h->h_raw, sizeof(int) * (size_t)h->raw_have);
+      if (h->h_raw) cudaFreeHost(h->h_raw);
+      h->h_raw = fresh;
+      h->raw_cap = want;
+      h->d_raw.alloc((size_t)want);
+    }
+    for (long long q = h->raw_have; q < want; ++q) h->h_raw[q] = h->rng.next();
+    h->raw_have = want;
+    const int R = (int)want;
+    if ((long long)levels * (R + 1) > h->tables_cap) {
+      h->tables_cap = (long long)levels * (R + 1);
+      h->d_tables.alloc((size_t)h->tables_cap);
+    }
+    if (h->d_consumed.n == 0) h->d_consumed.alloc(1);
+    B200_CUDA(cudaMemcpyAsync(h->d_raw.get(), h->h_raw, sizeof(int) * (size_t)R, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemsetAsync(h->d_consumed.get(), 0, sizeof(int), st));
+    GlibcView v{h->d_raw.get(), R, h->d_indptr.get(), h->d_indices.get(), h->d_data.get(), p.n_users, p.n_items, p.algorithm, h->quota};
+    int* T = h->d_tables.get();
+    glibc_len_kernel<<<div_up(R + 1, 256), 256, 0, st>>>(v, T);
+    for (int k = 0; k + 1 < levels; ++k)
+      glibc_double_kernel<<<div_up(R + 1, 256), 256, 0, st>>>(T + (size_t)k * (R + 1), R, T + (size_t)(k + 1) * (R + 1));
+    glibc_emit_kernel<<<div_up(n, 256), 256, 0, st>>>(v, T, levels, n, h->su.get(), h->si.get(), h->sj.get(), h->sr.get(), h->d_consumed.get());
+    B200_CUDA(cudaGetLastError());
+    count_launch(levels + 1);
+    int consumed = 0;
+    B200_CUDA(cudaMemcpyAsync(&consumed, h->d_consumed.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (consumed != 0x7FFFFFFF && consumed <= R) {
+      // the unread tail opens the next epoch's stream
+      h->raw_have = R - consumed;
+      if (h->raw_have) memmove(h->h_raw, h->h_raw + consumed, sizeof(int) * (size_t)h->raw_have);
+      return;
+    }
+    want = want + want / 2;  // many rejections (dense profiles): a longer buffer, same draws in front
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -805,6 +952,7 @@ int b200_mf_create(b200_mf_t* out, int64_t n_users, int64_t n_items, int64_t nnz
     h->sampler = sampler;
     h->seed = has_seed ? random_seed : 1u;
     h->rng.seed(h->seed);
+    if (const char* e = getenv("B200REC_GLIBC_HOST")) h->glibc_device = atoi(e) == 0;  // 1: the sequential host replay (A/B, tests)
     h->h_indptr.assign(h_indptr, h_indptr + n_users + 1);
     h->h_indices.assign(h_indices, h_indices + nnz);
     if (algorithm == FUNK_SVD) h->h_data.assign(h_data, h_data + nnz);
@@ -899,6 +1047,7 @@ int b200_mf_destroy(b200_mf_t h) {
   if (!h) return B200_OK;
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->h_raw) cudaFreeHost(h->h_raw);
   delete h;
   return B200_OK;
 }
@@ -911,7 +1060,9 @@ int b200_mf_epoch(b200_mf_t h, void* stream) {
     p.n_batches = epoch_batches(h);
     if (h->epoch_samples_override > 0) p.n_batches = std::max<long long>(1, h->epoch_samples_override / p.batch_size);
     const long long n = p.n_batches * p.batch_size;
-    if (h->sampler == 0) {
+    if (h->sampler == 0 && h->glibc_device && n * 4 + 65536 < (1ll << 30)) {
+      glibc_device_samples(h, n, st);
+    } else if (h->sampler == 0) {
       host_samples(h, n);
       B200_CUDA(cudaMemcpyAsync(h->su.get(), h->hs_u.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
       B200_CUDA(cudaMemcpyAsync(h->si.get(), h->hs_i.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -981,7 +1132,7 @@ int b200_mf_epoch(b200_mf_t h, void* stream) {
       B200_CUDA(cudaStreamSynchronize(st));
       p.b1_pow = pw[0];
       p.b2_pow = pw[1];
-    } else if (h->sampler == 0) {
+    } else if (h->sampler == 0 && !(h->glibc_device && n * 4 + 65536 < (1ll << 30))) {
       B200_CUDA(cudaStreamSynchronize(st));  // the host sample vectors are reused by the next epoch
     }
     h->samples_last = n;

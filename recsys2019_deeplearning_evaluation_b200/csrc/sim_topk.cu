@@ -1502,7 +1502,20 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
       B200_CUDA(cudaMemcpyAsync(&total1, poff1.get() + n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaStreamSynchronize(st));
       h->csr_idx1.alloc((size_t)total1 + 8);
-      seg_pad_kernel<<<div_up((long long)n_rows * 8, 256), 256, 0, st>>>(sp1.get(), h->csr_idx.get(), poff1.get(), n_rows, 1, win1, total1,
+      // bank-spread layout (sim_k1d.cuh): the rows of this private copy are ordered by (j & 31, j >> 5) instead of j
+      DevBuf<int> perm_a((size_t)nnz), perm_b((size_t)nnz);
+      k1d_perm_kernel<<<GRID1D, 256, 0, st>>>(h->csr_idx.get(), nnz, perm_a.get(), 1); count_launch();
+      {
+        size_t tbs = 0;
+        B200_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tbs, perm_a.get(), perm_b.get(), (long long)nnz, (long long)n_rows,
+                                                     h->csr_ptr.get(), h->csr_ptr.get() + 1, st));
+        DevBuf<unsigned char> tmps(tbs + 16);
+        B200_CUDA(cub::DeviceSegmentedSort::SortKeys(tmps.get(), tbs, perm_a.get(), perm_b.get(), (long long)nnz, (long long)n_rows,
+                                                     h->csr_ptr.get(), h->csr_ptr.get() + 1, st)); count_launch();
+        B200_CUDA(cudaStreamSynchronize(st));
+      }
+      k1d_perm_kernel<<<GRID1D, 256, 0, st>>>(perm_b.get(), nnz, perm_a.get(), 0); count_launch();
+      seg_pad_kernel<<<div_up((long long)n_rows * 8, 256), 256, 0, st>>>(sp1.get(), perm_a.get(), poff1.get(), n_rows, 1, win1, total1,
                                                                         h->csr_idx1.get(), split1.get()); count_launch();
       h->csc_seg.alloc((size_t)nnz + 2);
       B200_CUDA(cudaMemsetAsync(h->csc_seg.get() + nnz, 0, 2 * sizeof(int2), st));
@@ -1534,7 +1547,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   if (h->csc_seg.n > 0) {
     const int win1 = ((n_cols + 7) / 8) * 8;
     h->ntile = (n_cols + (1 << D_TILE_LOG2) - 1) >> D_TILE_LOG2;
-    h->bm_words = ((win1 / 8 + 1) + 3) / 4 * 4;
+    h->bm_words = (((n_cols - 1) >> 8) + 1) << 5;  // bank-spread layout: 32 words per 256 neighbours
     const long long fixed = (long long)h->bm_words * 4 + ((long long)h->ntile + 1) * 4 + (long long)h->ntile * 4 + 32;
     // two CTAs per SM when both fit (each CTA also pays its static shared memory and the 1 KB the hardware reserves)
     cudaFuncAttributes fa{};

@@ -171,6 +171,27 @@ __global__ void __launch_bounds__(256) slim_shard_partial_kernel(const ShardPara
   }
 }
 
+// the adaptive scale of one gradient from the item's state AS OF THE START OF THE BATCH plus this sample's own contribution
+// (pyx:395-433 without the store); with one sample per batch this is the reference's value exactly
+__device__ __forceinline__ float adapt_item_frozen(const Params& p, float g, int item, float inv1, float inv2) {
+  if (p.sgd_mode == ADAGRAD) return g / (sqrtf(p.c[item] + g * g) + 1e-8f);
+  if (p.sgd_mode == RMSPROP) return g / (sqrtf(p.c[item] * p.gamma + (1.f - p.gamma) * g * g) + 1e-8f);
+  if (p.sgd_mode == ADAM) {
+    const float a = p.m1[item] * p.beta1 + (1.f - p.beta1) * g;
+    const float b = p.m2[item] * p.beta2 + (1.f - p.beta2) * g * g;
+    return (a * inv1) / (sqrtf(b * inv2) + 1e-8f);
+  }
+  return g;
+}
+
+__device__ __forceinline__ void ema_atomic(float* addr, float decay, float add) {  // *addr = *addr * decay + add, atomically
+  int old = __float_as_int(*addr), assumed;
+  do {
+    assumed = old;
+    old = atomicCAS(reinterpret_cast<int*>(addr), assumed, __float_as_int(__int_as_float(assumed) * decay + add));
+  } while (assumed != old);
+}
+
 __global__ void __launch_bounds__(256) slim_shard_apply_kernel(const ShardParams sp, const float* __restrict__ x_sum) {
   const Params& p = sp.p;
   const int lane = threadIdx.x & 31;
@@ -188,8 +209,8 @@ __global__ void __launch_bounds__(256) slim_shard_apply_kernel(const ShardParams
         inv1 = (float)(1.0 / (1.0 - p.b1_pow * pow((double)p.beta1, (double)g)));
         inv2 = (float)(1.0 / (1.0 - p.b2_pow * pow((double)p.beta2, (double)g)));
       }
-      // the per-item state is replicated: every rank applies the same gradients to it (i first, then j, pyx:262-263)
-      if (lane == 0) { gi = adapt_item(p, gr, i, inv1, inv2); gj = adapt_item(p, gr, j, inv1, inv2); }
+      // the per-item state is replicated and frozen while a batch is applied: every rank derives the same scales
+      if (lane == 0) { gi = adapt_item_frozen(p, gr, i, inv1, inv2); gj = adapt_item_frozen(p, gr, j, inv1, inv2); }
       gi = __shfl_sync(0xffffffffu, gi, 0);
       gj = __shfl_sync(0xffffffffu, gj, 0);
     }
@@ -201,6 +222,24 @@ __global__ void __launch_bounds__(256) slim_shard_apply_kernel(const ShardParams
       if (sn != i) atomicAdd(Si + sn, p.lr * (gi - p.li_reg * Si[sn]));   // pyx:266-283
       if (sn != j) atomicAdd(Sj + sn, -p.lr * (gj - p.lj_reg * Sj[sn]));  // pyx:285-304
     }
+  }
+}
+
+// after the batch's cells are updated: the batch's gradients enter the per-item state (i then j per sample, pyx:262-263;
+// the order BETWEEN the samples of a batch is free: a sum for adagrad, an atomic read-modify-write per hit for the averages)
+__global__ void slim_shard_state_kernel(const ShardParams sp, const float* __restrict__ x_sum) {
+  const Params& p = sp.p;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= sp.n_batch) return;
+  const long long g = sp.first + n;
+  const float gr = 1.f / (1.f + expf(x_sum[n]));
+  const int items[2] = {p.si[g], p.sj[g]};
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int it = items[t];
+    if (p.sgd_mode == ADAGRAD) atomicAdd(p.c + it, gr * gr);
+    else if (p.sgd_mode == RMSPROP) ema_atomic(p.c + it, p.gamma, (1.f - p.gamma) * gr * gr);
+    else if (p.sgd_mode == ADAM) { ema_atomic(p.m1 + it, p.beta1, (1.f - p.beta1) * gr); ema_atomic(p.m2 + it, p.beta2, (1.f - p.beta2) * gr * gr); }
   }
 }
 
@@ -434,6 +473,11 @@ int b200_slim_shard_apply_device(b200_slim_t h, int64_t first, int n_batch, cons
     slim_shard_apply_kernel<<<std::min<int>(div_up(n_batch, 8), sm_count() * 8), 256, 0, (cudaStream_t)stream>>>(sp, d_x_sum);
     B200_CUDA(cudaGetLastError());
     count_launch();
+    if (h->p.sgd_mode != SGD) {
+      slim_shard_state_kernel<<<div_up(n_batch, 256), 256, 0, (cudaStream_t)stream>>>(sp, d_x_sum);
+      B200_CUDA(cudaGetLastError());
+      count_launch();
+    }
     if (first + n_batch == h->p.n_users) {  // the epoch is complete
       if (h->p.sgd_mode == ADAM) {
         h->p.b1_pow *= pow((double)h->p.beta1, (double)h->p.n_users);

@@ -75,6 +75,35 @@ def test_minibatch_mode_is_run_to_run_deterministic():
                 assert np.allclose(a, b, rtol=1e-6, atol=1e-8), float(np.abs(a - b).max())
 
 
+@pytest.mark.parametrize("shape", ["sparse", "dense_profiles", "cold_users"])
+@pytest.mark.parametrize("algo", ["MF_BPR", "FUNK_SVD"])
+def test_glibc_stream_resolved_on_the_device_equals_the_host_replay(algo, shape, monkeypatch):
+    """The reference's rand() stream with its rejection loops, resolved in parallel on the device (lengths at every stream
+    position + pointer doubling), against the sequential host replay: identical (u, i, j | rating) streams over several
+    epochs (the unread tail of one epoch's buffer opens the next), with many negative rejections (dense profiles: the buffer
+    has to be extended) and many user rejections (empty profiles)."""
+    if shape == "sparse":
+        X = synth_urm(3000, 900, 0.01, seed=21, values="ratings")
+    elif shape == "dense_profiles":
+        X = synth_urm(200, 40, 0.7, seed=22, values="ratings")   # most negative draws are rejected
+    else:
+        X = synth_urm(500, 200, 0.004, seed=23, values="ratings")  # most users have an empty profile
+    kw = dict(algorithm_name=algo, n_factors=8, batch_size=50, learning_rate=0.01, random_seed=77, sgd_mode="sgd",
+              negative_interactions_quota=0.35)
+    monkeypatch.setenv("B200REC_GLIBC_HOST", "1")
+    host = _cls()(X, **kw)
+    monkeypatch.setenv("B200REC_GLIBC_HOST", "0")
+    dev = _cls()(X, **kw)
+    for _ in range(3):
+        host.epochIteration_Cython()
+        dev.epochIteration_Cython()
+        a, b = host.get_samples(), dev.get_samples()
+        assert len(a[0]) == len(b[0]) > 0
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    _compare(dev, host)
+
+
 def test_dataflow_kernel_under_heavy_row_sharing():
     """Few rows, large batches: almost every (row, batch) pair is hit many times, so the accumulate-and-last-arriver path,
     the waits on the previous batch and the per-row arrival counters all run hot (the C5 shape exercises almost only the

@@ -182,7 +182,7 @@ def test_column_sharded_batches_and_row_topk():
     S3 = torch.cat([s.slab() for s in three], dim=1).cpu().numpy()
     S1 = one[0].slab().cpu().numpy()
     assert np.abs(S1).max() > 0 and (np.diag(S1) == 0).all()
-    assert np.allclose(S3, S1, rtol=1e-4, atol=1e-7), float(np.abs(S3 - S1).max())  # float atomics: order of a batch's updates
+    assert np.allclose(S3, S1, rtol=1e-4, atol=2e-5), float(np.abs(S3 - S1).max())  # fp32 atomics: the order of a batch's updates
     W = ShardedSLIM_BPR.merge_row_topk([s.local_row_topk() for s in three], 260, 12)
     assert sps.issparse(W) and W.shape == (260, 260)
     W = W.toarray()

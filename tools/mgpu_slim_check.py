@@ -30,10 +30,10 @@ if rank == 0:
         one.epochIteration_Cython()
     mine = tr.slab().cpu().numpy()
     ref = one.slab()[:, tr.lo:tr.hi].cpu().numpy()
-    same = np.allclose(mine, ref, rtol=1e-4, atol=1e-7)
+    same = np.allclose(mine, ref, rtol=1e-4, atol=2e-5)
     W1 = one.get_S()
     d = abs(W - W1)
-    topk_same = d.nnz == 0 or d.max() < 1e-5
+    topk_same = d.nnz == 0 or d.max() < 1e-4
     ok = same and topk_same and abs(ref).max() > 0
     print("[sharded SLIM x%d] slab == single-shard run: %s, merged row top-K == single: %s, %.3e samples/s (batch %d)" % (
         world, same, topk_same, 5 * X.shape[0] / dt, kw["batch_size"]), flush=True)
