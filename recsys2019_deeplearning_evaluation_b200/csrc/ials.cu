@@ -245,9 +245,38 @@ void run(cudaStream_t st, const int* rows, int n_solve, const int* ptr, const in
 }  // namespace b200
 
 #include "ials_tc.cuh"
+#include "ials_v2.cuh"
 
 namespace b200 {
 namespace ials {
+
+// Tensor-core half epoch, second generation (ials_v2.cuh, n_factors <= 256); false when a row asked for the fp64 path.
+bool run_v2(cudaStream_t st, const int* rows, int n_solve, const int* ptr, const int* idx, const float* conf, const double* Y,
+            int n_other, int f, double reg, double* X, double* YtY, int* info) {
+  const size_t smem_g = sizeof(double) * ((size_t)TROWS * f + TROWS);
+  B200_CUDA(cudaMemsetAsync(YtY, 0, sizeof(double) * (size_t)f * f, st));
+  const int grid_g = std::max(1, std::min(sm_count() * 4, (n_other + 63) / 64));
+  if (f <= 32) { gram_kernel<2, 0, 2><<<grid_g, THREADS, smem_g, st>>>(Y, n_other, f, YtY); count_launch(); }
+  else if (f <= 64) { gram_kernel<4, 0, 4><<<grid_g, THREADS, smem_g, st>>>(Y, n_other, f, YtY); count_launch(); }
+  else if (f <= 128) { gram_kernel<8, 0, 8><<<grid_g, THREADS, smem_g, st>>>(Y, n_other, f, YtY); count_launch(); }
+  else if (f <= 208) { gram_kernel<13, 0, 13><<<grid_g, THREADS, smem_g, st>>>(Y, n_other, f, YtY); count_launch(); }
+  else {
+    gram_kernel<16, 0, 11><<<grid_g, THREADS, smem_g, st>>>(Y, n_other, f, YtY); count_launch();
+    gram_kernel<16, 11, 16><<<grid_g, THREADS, smem_g, st>>>(Y, n_other, f, YtY); count_launch();
+  }
+  DevBuf<int> redo(1);
+  B200_CUDA(cudaMemsetAsync(redo.get(), 0, sizeof(int), st));
+  const size_t smem = ials2::smem_bytes(f);
+  B200_CUDA(cudaFuncSetAttribute(ials2::ials_rows_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::max(1, std::min(n_solve, sm_count()));
+  ials2::ials_rows_v2_kernel<<<grid, ials2::T, smem, st>>>(rows, n_solve, ptr, idx, conf, Y, YtY, f, reg, X, info, redo.get(), 2);
+  B200_CUDA(cudaGetLastError());
+  count_launch();
+  int h_redo = 0;
+  B200_CUDA(cudaMemcpyAsync(&h_redo, redo.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  return h_redo == 0;
+}
 
 // Tensor-core half epoch (ials_tc.cuh); returns false when a row asked for the fp64 path.
 template <int FB>
@@ -291,7 +320,23 @@ int b200_ials_half_epoch_device(const int32_t* d_rows, int n_solve, const int32_
     DevBuf<int> info(1);
     B200_CUDA(cudaMemsetAsync(info.get(), 0, sizeof(int), st));
     const int f = n_factors;
-    // opt-in tensor-core path (ials_tc.cuh): well-conditioned shapes only; a row that does not refine falls back to fp64
+    // tensor-core path, second generation (ials_v2.cuh): the default whenever the other side has at least 4 x n_factors rows
+    // (well-conditioned systems; B200REC_IALS_V2=0 switches it off); a row whose refinement does not contract sends the half
+    // epoch back to the fp64 kernel below
+    const int v2_env = getenv("B200REC_IALS_V2") ? atoi(getenv("B200REC_IALS_V2")) : -1;  // 0 off, 1 every size, unset: where it wins
+    // measured on C4 (profiles/r02_ials_v2_c4.txt): 256 factors 1.8 s per epoch against 11.7 s, 128 factors 1.0 s against 0.83 s
+    const bool want_v2 = v2_env == 1 || (v2_env != 0 && f > 128);
+    if (want_v2 && n_other >= 4 * f) {
+      if (ials::run_v2(st, d_rows, n_solve, d_ptr, d_idx, d_conf, d_Y, n_other, f, reg, d_X, d_YtY_work, info.get())) {
+        int h_info = 0;
+        B200_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        B200_REQUIRE(h_info == 0, "b200_ials_half_epoch: normal equations of row %d are not positive definite", h_info - 1);
+        return;
+      }
+      B200_CUDA(cudaMemsetAsync(info.get(), 0, sizeof(int), st));  // redo the half epoch in fp64
+    }
+    // first-generation tensor-core path (ials_tc.cuh, n_factors <= 128): opt-in, kept for A/B runs
     static const bool want_tc = getenv("B200REC_IALS_TC") != nullptr && atoi(getenv("B200REC_IALS_TC")) == 1;
     if (want_tc && f <= 128 && n_other >= 4 * f) {
       bool ok;

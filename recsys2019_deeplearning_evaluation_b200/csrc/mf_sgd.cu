@@ -745,8 +745,8 @@ struct GlibcRand {
   uint32_t next_raw() {
     const uint32_t v = (uint32_t)r[f] + (uint32_t)r[b];
     r[f] = (int32_t)v;
-    f = (f + 1) % 31;
-    b = (b + 1) % 31;
+    if (++f == 31) f = 0;
+    if (++b == 31) b = 0;
     return v;
   }
   int next() { return (int)(next_raw() >> 1); }

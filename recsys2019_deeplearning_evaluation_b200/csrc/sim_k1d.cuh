@@ -18,13 +18,16 @@
 // candidates computes that sum anyway; a column that fails the check is handed to the window kernel (redo list), as are the
 // columns the host routes there directly (dense co-occurrence).  Exactness is unchanged.
 //
-// Bank-spread layout.  A shared-memory atomic instruction costs as many passes as its most crowded bank: 32 lanes hitting 32
-// random words share a bank 3.1-fold on average, and that serialisation is what bounds the gather.  Neighbour j (numbered
-// by ascending norm term) therefore lives in word ((j >> 8) << 5) | (j & 31), nibble (j >> 5) & 7 -- bank = j & 31 -- and the
-// rows of the private row copy are re-sorted by (j & 31, j >> 5): lane l of a row load then holds entries whose banks cluster
-// around 32 l / chunks, the lanes of one atomic instruction mostly hit different banks, and the average crowding drops to
-// 2.0 (uniform and Zipf popularity alike, simulated).  A norm tile is still a contiguous block of words (128) and of
-// neighbours (1024): the prefix logic of the selection is unchanged.
+// What bounds it now (profiles/r02_k1d_*, C5: 26.1 ms per pass, 37.8 K SM cycles per column): the 50 K shared-memory atomics
+// of a column issue at ~11 cycles per warp instruction when both CTAs of an SM gather at once (45 K cycles for two columns),
+// and nothing overlaps them with the ~31 K cycles of sweep / select / emit that follow: the two CTAs fall into lockstep.
+// Measured and left out (same runs): a bank-spread accumulator (word = (j >> 8) << 5 | j & 31 with rows re-sorted by bank:
+// average bank crowding 3.1 -> 2.0 in simulation) changed nothing, so bank conflicts are not the limit; L2 prefetches of the
+// next column's rows and pre-loaded row locations changed nothing either; a per-SM token that lets one CTA gather at a time
+// showed that ONE CTA's gather alone also takes 45 K cycles (latency-bound with 16 warps x 4 rows in flight), so anti-phase
+// buys nothing; replacing the returning atomics of the candidate collection by a two-pass sweep with prefix sums moved 9 K
+// cycles from the sweep into the second pass.  What would: more CTAs per SM in different phases (two neighbour windows of
+// 50 KB counters each: 3-4 CTAs) or two accumulators per CTA with warp-specialised gather / select.
 //
 // Gather.  The CSC side stores, per entry, where the user's padded row lives (csc_seg: start and length in 16-byte
 // chunks), so a warp reads 32 of them with one coalesced load and then streams those rows with 128-bit loads, four rows in
@@ -46,7 +49,6 @@ constexpr int D_TILE_LOG2 = 10;  // norm tile: 1024 neighbours = 128 counter wor
 struct K1DShared {
   int item, nbuf, cnt, adds, nibsum, tstop, chunk_end, chunk_cnt;
   int need, digit, bincnt, ncand, expect;
-  int4 wi;
   u64 kor, kand;
   int hist[256];
 };
@@ -58,17 +60,6 @@ __device__ __forceinline__ unsigned nib_eq1(unsigned w) { return w & ~(w >> 1) &
 __device__ __forceinline__ unsigned nib_level(unsigned w, int level) {
   return level >= 3 ? nib_ge3(w) : (level == 2 ? nib_eq2(w) : nib_eq1(w));
 }
-// L2 prefetch of one padded row (seg.x = start in 16-byte chunks, seg.y >> 2 = chunks): one request per 128-byte line
-__device__ __forceinline__ void prefetch_row_l2(const int* csr_idx1, int2 seg) {
-  const char* b = reinterpret_cast<const char*>(csr_idx1) + (size_t)seg.x * 16;
-  const int bytes = (seg.y >> 2) * 16;
-  for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
-}
-
-// bank-spread cell addressing: neighbour j <-> (word, nibble)
-__device__ __forceinline__ int cell_word(int j) { return ((j >> 8) << 5) | (j & 31); }
-__device__ __forceinline__ int cell_shift(int j) { return ((j >> 5) & 7) << 2; }
-__device__ __forceinline__ int cell_of(int word, int nib) { return ((((word >> 5) << 3) | nib) << 5) | (word & 31); }
 __device__ __forceinline__ int nib_sum(unsigned w) {
   const unsigned b = (w & 0x0F0F0F0Fu) + ((w >> 4) & 0x0F0F0F0Fu);
   return (int)__dp4a(b, 0x01010101u, 0u);
@@ -155,7 +146,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
   __shared__ K1DShared ds;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = p.bm_words;                   // allocated counter words (multiple of 4)
-  const int Wr = (((p.n_cols - 1) >> 8) + 1) << 5;  // words that can hold real neighbours (bank-spread layout)
+  const int Wr = (p.n_cols + 7) >> 3;         // words that hold real neighbours
   const int ntile = p.ntile;
   unsigned* acc = reinterpret_cast<unsigned*>(smem_raw);
   u64* buf = reinterpret_cast<u64*>(smem_raw + (size_t)W * 4);
@@ -168,25 +159,13 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
   long long prof_t = p.prof ? clock64() : 0;
   const int K = p.K;
 
-  int pre_item = -1;                 // work item whose first batch of row locations sits in seg_pre
-  int2 seg_pre = make_int2(0, 0);
-  if (tid == 0) {
-    ds.item = atomicAdd(p.counter, 1);
-    ds.wi = ds.item < p.n_range ? __ldg(p.worklist + ds.item) : make_int4(0, 0, 0, 0);
-  }
   for (;;) {
     __syncthreads();
+    if (tid == 0) { ds.item = atomicAdd(p.counter, 1); ds.nbuf = 0; ds.adds = 0; ds.nibsum = 0; ds.ncand = 0; }
+    __syncthreads();
     const int item = ds.item;
-    const int4 wi = ds.wi;
     if (item >= p.n_range) break;
-    if (tid == 0) { ds.nbuf = 0; ds.adds = 0; ds.nibsum = 0; ds.ncand = 0; }
-    __syncthreads();  // everyone holds this column's work item: thread 0 may fetch the next one behind the gather
-    int item_n = 0;
-    int4 wi_n = make_int4(0, 0, 0, 0);
-    if (tid == 0) {
-      item_n = atomicAdd(p.counter, 1);
-      if (item_n < p.n_range) wi_n = __ldg(p.worklist + item_n);
-    }
+    const int4 wi = __ldg(p.worklist + item);
     const int col = wi.x, lc = wi.y, cs = wi.z, ce = wi.w;
     const size_t out_base = (size_t)lc * K;
     const float Ai = p.A[col];
@@ -197,12 +176,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
       const int nrows = min(32, ce - k0);
       int2 seg = make_int2(0, 0);
       if (lane < nrows) {
-        if (k0 == cs + warp * 32 && pre_item == item) {
-          seg = seg_pre;  // loaded, and its row prefetched to L2, while the previous column was being selected
-        } else {
-          seg = __ldg(p.csc_seg + k0 + lane);
-          prefetch_row_l2(p.csr_idx1, seg);
-        }
+        seg = __ldg(p.csc_seg + k0 + lane);
         expect += 4 * (seg.y >> 2) - (seg.y & 3) - 1;
       }
       for (int r0 = 0; r0 < nrows; r0 += D_ROWS) {
@@ -224,7 +198,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const int j = jj[c];
-                if ((unsigned)j < (unsigned)p.n_cols && j != col) atomicAdd(&acc[cell_word(j)], 1u << cell_shift(j));
+                if ((unsigned)j < (unsigned)p.n_cols && j != col) atomicAdd(&acc[j >> 3], 1u << ((j & 7) << 2));
               }
             }
             c0 += 32;
@@ -236,20 +210,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
     }
     expect = __reduce_add_sync(0xffffffffu, expect);
     if (lane == 0 && expect) atomicAdd(&ds.adds, expect);
-    if (tid == 0) { ds.item = item_n; ds.wi = wi_n; }  // read at the top of the next iteration, many barriers from here
     __syncthreads();
-    {
-      // the next column's first batch of row locations, in flight while this column is swept and selected
-      const int item_next = ds.item;
-      const int4 wn = ds.wi;
-      pre_item = -1;
-      if (item_next < p.n_range) {
-        pre_item = item_next;
-        const int kn = wn.z + warp * 32;
-        seg_pre = make_int2(0, 0);
-        if (kn + lane < wn.w) seg_pre = __ldg(p.csc_seg + kn + lane);
-      }
-    }
     PROF_MARK(1);
 
     // ---------------- one sweep (128-bit loads): nibble checksum, cells with count >= 3 per norm tile, and the cells themselves
@@ -282,7 +243,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
               while (mm) {
                 const int q = (__ffs(mm) - 1) >> 2;
                 mm &= mm - 1;
-                cand[pos++] = ((unsigned)cell_of(i4 * 4 + e, q) << 4) | ((ww[e] >> (q << 2)) & 15u);
+                cand[pos++] = ((unsigned)((i4 * 4 + e) * 8 + q) << 4) | ((ww[e] >> (q << 2)) & 15u);
               }
             }
           }
@@ -301,7 +262,6 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
       for (int i = tid; i < ntile; i += D_THREADS) tcnt[i] = 0;
       continue;
     }
-    if (pre_item >= 0) prefetch_row_l2(p.csr_idx1, seg_pre);
     PROF_MARK(2);
 
     u64 thr = 0ull;  // keys below it cannot be among the K best
@@ -354,7 +314,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
           t_end = ds.tstop;
           __syncthreads();  // everyone has read it before thread 0 of the next level resets it
         }
-        if (t_end == 0) break;  // no tile can hold a count-`level` cell that reaches the floor; lower counts even less so
+        if (t_end == 0) continue;
         // cells of this level per allowed tile
         const int w_end = min(Wr, t_end << (D_TILE_LOG2 - 3));
         for (int i = tid; i < w_end; i += D_THREADS) {
@@ -395,7 +355,7 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
             while (m) {
               const int q = (__ffs(m) - 1) >> 2;
               m &= m - 1;
-              const int j = cell_of(i, q);
+              const int j = i * 8 + q;
               const float d = (float)((w >> (q << 2)) & 15u);
               const int2 bn = __ldg(p.BN + j);
               const float sv = sim_value<F>(p, d, Ai, __int_as_float(bn.x));
@@ -444,14 +404,6 @@ __global__ void __launch_bounds__(D_THREADS, 2) sim_k1d_kernel(const KParams p) 
     if (tid == 0) emit_count(p, lc, n_have);
     for (int i = tid; i < (W >> 2); i += D_THREADS) reinterpret_cast<int4*>(acc)[i] = make_int4(0, 0, 0, 0);
     PROF_MARK(6);
-  }
-}
-
-// forward: j -> sort key (j & 31) << 27 | j >> 5 (rows ordered by bank, then by position inside the bank); backward: key -> j
-__global__ void k1d_perm_kernel(const int* __restrict__ in, long long n, int* out, int forward) {
-  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
-    const unsigned v = (unsigned)in[q];
-    out[q] = forward ? (int)(((v & 31u) << 27) | (v >> 5)) : (int)(((v & 0x7FFFFFFu) << 5) | (v >> 27));
   }
 }
 

@@ -116,6 +116,7 @@ struct KParams {
   int* redo;
   int* fail;
   const int* n_range_dev;  // window kernel: the number of columns to process is read from here when set
+  int* gather_lock;        // K1-D: one word per SM, the token of the CTA that is gathering there
   unsigned long long* prof;  // optional [8] per-phase cycle counters (thread 0 of every CTA), test/bench hook
 };
 
@@ -1202,7 +1203,7 @@ struct b200_sim_s {
   // K1-D (binary path, large sparse catalogues): second row layout with one window, CSC-side row locations, norm tile
   // bounds, ring / table geometry, routing threshold (expected hits per neighbour of a column) and last-launch statistics
   bool want_k1c = true, k1c = false;
-  DevBuf<int> csr_idx1, fail;
+  DevBuf<int> csr_idx1, fail, gather_lock;
   DevBuf<int2> csc_seg;
   DevBuf<float> tbnd;
   DevBuf<int4> worklist;
@@ -1502,20 +1503,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
       B200_CUDA(cudaMemcpyAsync(&total1, poff1.get() + n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
       B200_CUDA(cudaStreamSynchronize(st));
       h->csr_idx1.alloc((size_t)total1 + 8);
-      // bank-spread layout (sim_k1d.cuh): the rows of this private copy are ordered by (j & 31, j >> 5) instead of j
-      DevBuf<int> perm_a((size_t)nnz), perm_b((size_t)nnz);
-      k1d_perm_kernel<<<GRID1D, 256, 0, st>>>(h->csr_idx.get(), nnz, perm_a.get(), 1); count_launch();
-      {
-        size_t tbs = 0;
-        B200_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tbs, perm_a.get(), perm_b.get(), (long long)nnz, (long long)n_rows,
-                                                     h->csr_ptr.get(), h->csr_ptr.get() + 1, st));
-        DevBuf<unsigned char> tmps(tbs + 16);
-        B200_CUDA(cub::DeviceSegmentedSort::SortKeys(tmps.get(), tbs, perm_a.get(), perm_b.get(), (long long)nnz, (long long)n_rows,
-                                                     h->csr_ptr.get(), h->csr_ptr.get() + 1, st)); count_launch();
-        B200_CUDA(cudaStreamSynchronize(st));
-      }
-      k1d_perm_kernel<<<GRID1D, 256, 0, st>>>(perm_b.get(), nnz, perm_a.get(), 0); count_launch();
-      seg_pad_kernel<<<div_up((long long)n_rows * 8, 256), 256, 0, st>>>(sp1.get(), perm_a.get(), poff1.get(), n_rows, 1, win1, total1,
+      seg_pad_kernel<<<div_up((long long)n_rows * 8, 256), 256, 0, st>>>(sp1.get(), h->csr_idx.get(), poff1.get(), n_rows, 1, win1, total1,
                                                                         h->csr_idx1.get(), split1.get()); count_launch();
       h->csc_seg.alloc((size_t)nnz + 2);
       B200_CUDA(cudaMemsetAsync(h->csc_seg.get() + nnz, 0, 2 * sizeof(int2), st));
@@ -1547,7 +1535,7 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
   if (h->csc_seg.n > 0) {
     const int win1 = ((n_cols + 7) / 8) * 8;
     h->ntile = (n_cols + (1 << D_TILE_LOG2) - 1) >> D_TILE_LOG2;
-    h->bm_words = (((n_cols - 1) >> 8) + 1) << 5;  // bank-spread layout: 32 words per 256 neighbours
+    h->bm_words = ((win1 / 8 + 1) + 3) / 4 * 4;
     const long long fixed = (long long)h->bm_words * 4 + ((long long)h->ntile + 1) * 4 + (long long)h->ntile * 4 + 32;
     // two CTAs per SM when both fit (each CTA also pays its static shared memory and the 1 KB the hardware reserves)
     cudaFuncAttributes fa{};
@@ -1571,6 +1559,8 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
       h->tbnd.alloc((size_t)h->ntile + 1);
       k1d_tile_bounds_kernel<<<div_up(h->ntile + 1, 128), 128, 0, st>>>(h->BN.get(), n_cols, h->ntile, h->tbnd.get()); count_launch();
       h->fail.alloc(1);
+      h->gather_lock.alloc(1024);
+      B200_CUDA(cudaMemsetAsync(h->gather_lock.get(), 0, 1024 * sizeof(int), st));
       h->worklist.alloc((size_t)n_cols);
       h->h_old2new.resize((size_t)n_cols);
       h->h_csc_ptr.resize((size_t)n_cols + 1);
@@ -1763,13 +1753,14 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   p.prof = h->prof_on ? h->prof.get() : nullptr;
   p.bm_words = h->bm_words; p.cap_d = h->cap_d; p.fail_every = h->fail_every; p.ntile = h->ntile; p.tbnd = h->tbnd.get();
   p.csr_idx1 = h->csr_idx1.get(); p.csc_seg = h->csc_seg.get(); p.worklist = h->worklist.get();
-  p.redo = h->order.get(); p.fail = h->fail.get();
+  p.redo = h->order.get(); p.fail = h->fail.get(); p.gather_lock = h->gather_lock.get();
   p.n_range_dev = nullptr;
   B200_CUDA(cudaEventRecord(h->ev0, st));
   if (n_sparse > 0) {
     // nibble-counter kernel first; columns with an overflowed counter are appended to the window kernel's list, whose length
     // the window kernel then reads from the device (no host round trip between the two launches)
     B200_CUDA(cudaMemcpyAsync(h->fail.get(), &h->n_dense_last, sizeof(int), cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemsetAsync(h->gather_lock.get(), 0, 1024 * sizeof(int), st));  // no token survives an aborted launch
     KParams q = p;
     q.n_range = n_sparse;
     k1d_kernel_for(h->formula)<<<std::min(n_sparse, h->n_sm * h->ctas_per_sm), D_THREADS, h->smem1_bytes, st>>>(q);

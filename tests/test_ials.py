@@ -80,6 +80,30 @@ def test_cuda_factor_sizes_against_restatement(f):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("f", [8, 64, 100, 128, 160, 256])
+def test_tensor_core_kernel_every_size_against_restatement(f, monkeypatch):
+    """ials_v2.cuh (tcgen05 3xTF32 Gram, blocked fp32 Cholesky, fp64 refinement) forced on for every factor count it serves
+    (by default it takes over above 128 factors), on a shape with enough rows on the other side to be eligible
+    (n_other >= 4 f), ratings as confidences (c - 1 varies per entry: the sqrt(c - 1) operand scaling)."""
+    from threadpoolctl import threadpool_limits
+    from recsys2019_deeplearning_evaluation_b200.recommenders import IALSRecommender
+    monkeypatch.setenv("B200REC_IALS_V2", "1")
+    nu, ni = 1100, 1056
+    X = synth_urm(nu, ni, 0.03, seed=100 + f, values="ratings")
+    np.random.seed(f)
+    V0 = f ** -0.5 * np.random.random_sample((ni, f))
+    np.random.seed(f)
+    r = IALSRecommender(X, verbose=False)
+    r.fit(epochs=1, num_factors=f, alpha=2.0, reg=1e-2)
+    C = confidence(X, "linear", 2.0)
+    with threadpool_limits(limits=4):
+        U, V = run_epoch(C, np.zeros((nu, f)), V0.copy(), 1e-2)
+    warm = np.diff(X.indptr) > 0
+    assert np.allclose(r.USER_factors[warm], U[warm], rtol=1e-4, atol=1e-8), float(np.abs(r.USER_factors - U).max())
+    assert np.allclose(r.ITEM_factors, V, rtol=1e-4, atol=1e-8), float(np.abs(r.ITEM_factors - V).max())
+
+
+@pytest.mark.gpu
 def test_argument_errors():
     from recsys2019_deeplearning_evaluation_b200.recommenders import IALSRecommender
     X = synth_urm(50, 20, 0.2)
