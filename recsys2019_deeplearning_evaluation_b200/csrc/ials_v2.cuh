@@ -32,6 +32,7 @@ constexpr int KC = 32;                   // profile entries per step
 constexpr int STAGES = 2;
 constexpr int TILE = 256 * KC * 4;       // one 256 x 32 fp32 tile: 32 KB
 constexpr int NB = 32;                   // Cholesky panel width
+constexpr int NBP = NB + 1;              // row stride of the stored diagonal-block inverses (no shared bank across rows)
 constexpr uint32_t TMEM_COLS = 512;
 // kind::tf32, D = fp32, A and B K-major, M = 128, N = 128 / 256 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
 constexpr uint32_t IDESC_N128 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -69,7 +70,7 @@ struct Smem {
   unsigned char* tiles;
   uint64_t* bars;
   double *b0, *xs, *rs, *part;  // rhs, solution, residual / correction, [8][f] partial sums
-  float* dinv;     // [f / 32][32][32] inverses of the diagonal blocks of L (lower triangular, row-major)
+  float* dinv;     // [f / 32][32][33] inverses of the diagonal blocks of L (lower triangular, row-major, padded rows)
   float* sw;       // [KC] sqrt(c - 1) of the step's entries
   double* cw;      // [KC] c
   int* rk;         // [KC] factor-row indices (-1 past the profile)
@@ -81,10 +82,10 @@ __device__ __forceinline__ void solve_forward(const Smem& S, double* v, int f) {
   for (int k0 = 0; k0 < f; k0 += NB) {
     const int nb = min(NB, f - k0);
     if (warp == 0) {  // z_blk = inv(L11) v_blk
-      const float* inv = S.dinv + (k0 / NB) * NB * NB;
+      const float* inv = S.dinv + (k0 / NB) * NB * NBP;
       double z = 0.0;
       if (lane < nb)
-        for (int c = 0; c <= lane; ++c) z += (double)inv[lane * NB + c] * v[k0 + c];
+        for (int c = 0; c <= lane; ++c) z += (double)inv[lane * NBP + c] * v[k0 + c];
       __syncwarp();
       if (lane < nb) v[k0 + lane] = z;
     }
@@ -106,10 +107,10 @@ __device__ __forceinline__ void solve_backward(const Smem& S, double* v, int f) 
   for (int kb = nblk - 1; kb >= 0; --kb) {
     const int k0 = kb * NB, nb = min(NB, f - k0);
     if (warp == 0) {  // x_blk = inv(L11)^T v_blk
-      const float* inv = S.dinv + kb * NB * NB;
+      const float* inv = S.dinv + kb * NB * NBP;
       double z = 0.0;
       if (lane < nb)
-        for (int c = lane; c < nb; ++c) z += (double)inv[c * NB + lane] * v[k0 + c];
+        for (int c = lane; c < nb; ++c) z += (double)inv[c * NBP + lane] * v[k0 + c];
       __syncwarp();
       if (lane < nb) v[k0 + lane] = z;
     }
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
     S.rs = reinterpret_cast<double*>(smem + o); o += sizeof(double) * f;
     S.part = reinterpret_cast<double*>(smem + o); o += sizeof(double) * 8 * f;
     S.cw = reinterpret_cast<double*>(smem + o); o += sizeof(double) * KC;
-    S.dinv = reinterpret_cast<float*>(smem + o); o += sizeof(float) * ((f + NB - 1) / NB) * NB * NB;
+    S.dinv = reinterpret_cast<float*>(smem + o); o += sizeof(float) * ((f + NB - 1) / NB) * NB * NBP;
     S.sw = reinterpret_cast<float*>(smem + o); o += sizeof(float) * KC;
     S.rk = reinterpret_cast<int*>(smem + o);
   }
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
             if (c <= lane) S.L[roff(k0 + lane) + k0 + c] = a[c];
         }
         // inverse of the block: lane j solves L11 w = e_j (column j of the inverse), w[i] for i >= j
-        float* inv = S.dinv + (k0 / NB) * NB * NB;
+        float* inv = S.dinv + (k0 / NB) * NB * NBP;
         float w[NB];
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i)
-          if (lane < NB) inv[i * NB + lane] = w[i];  // inv[i][j] = w_j[i]
+          if (lane < NB) inv[i * NBP + lane] = w[i];  // inv[i][j] = w_j[i]
       }
       __syncthreads();
       const int R0 = k0 + nb;
@@ -420,7 +421,8 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
       if (tid < f) {
         double ax = reg * S.xs[tid];
         for (int w = 0; w < 8; ++w) ax += S.part[w * f + tid];
-        for (int n = 0; n < f; ++n) ax += YtY[(size_t)n * f + tid] * S.xs[n];  // symmetric: coalesced over tid
+#pragma unroll 8
+        for (int n = 0; n < f; ++n) ax += YtY[(size_t)n * f + tid] * S.xs[n];  // symmetric: coalesced over tid; eight loads in flight
         S.rs[tid] = S.b0[tid] - ax;
       }
       __syncthreads();
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
 inline size_t smem_bytes(int f) {
   size_t o = std::max<size_t>((size_t)roff(f) * 4, (size_t)STAGES * 2 * TILE);
   o = (o + 127) & ~(size_t)127;
-  o += 64 + sizeof(double) * (3 * (size_t)f + 8 * (size_t)f + KC) + sizeof(float) * ((size_t)((f + NB - 1) / NB) * NB * NB + KC) + sizeof(int) * KC;
+  o += 64 + sizeof(double) * (3 * (size_t)f + 8 * (size_t)f + KC) + sizeof(float) * ((size_t)((f + NB - 1) / NB) * NB * NBP + KC) + sizeof(int) * KC;
   return o + 64;
 }
 

@@ -1,5 +1,7 @@
-"""torchrun --nproc-per-node N tools/mgpu_ials_check.py : row-sharded IALS == single-GPU IALS (1e-9: Y^T Y is summed with
-fp64 atomics, so two runs agree to rounding, not bit for bit)."""
+"""torchrun --nproc-per-node N tools/mgpu_ials_check.py : row-sharded IALS == single-GPU IALS.  Y^T Y is summed with fp64
+atomics, so two runs agree to rounding, not bit for bit: 1e-9 on the fp64 kernel; 1e-6 on the tensor-core kernel (above 128
+factors), whose fp32 factorisation turns a last-bit change of Y^T Y into a ~1e-8 relative change of the refined solution --
+four orders below the 1e-4 parity bar."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -21,7 +23,8 @@ for f in (64, 256):
     np.random.seed(7)
     b = IALSRecommender(X, verbose=False)
     b.fit(epochs=2, num_factors=f, alpha=2.0, reg=1e-2)
-    same = np.allclose(a.USER_factors, b.USER_factors, rtol=1e-9, atol=1e-12) and np.allclose(a.ITEM_factors, b.ITEM_factors, rtol=1e-9, atol=1e-12)
+    tol = 1e-9 if f <= 128 else 1e-6
+    same = np.allclose(a.USER_factors, b.USER_factors, rtol=tol, atol=1e-3 * tol) and np.allclose(a.ITEM_factors, b.ITEM_factors, rtol=tol, atol=1e-3 * tol)
     print("[rank %d/%d] f=%d sharded==single: %s (max diff %.3e)" % (rank, world, f, same, float(np.abs(a.USER_factors - b.USER_factors).max())), flush=True)
     ok = ok and same
 t = torch.tensor([1 if ok else 0], device="cuda")
