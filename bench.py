@@ -489,9 +489,12 @@ def bpr_leg_sharded(args, X, rank, world):
     import torch.distributed as dist
     from recsys2019_deeplearning_evaluation_b200.dist import ShardedBPR
     f = 128
+    from recsys2019_deeplearning_evaluation_b200.synth import synth_config
     out = {}
-    for scaling in ("weak", "strong"):
-        tr = ShardedBPR(X, scaling=scaling, n_factors=f, batch_size=1000, learning_rate=1e-3, random_seed=42, sgd_mode="sgd")
+    for scaling, Xw in (("weak", X), ("strong", X), ("c3_weak", None), ("c3_strong", None)):
+        if Xw is None:
+            Xw = synth_config("C3", values="binary")  # BASELINE.json configs[2]: 138 K x 27 K
+        tr = ShardedBPR(Xw, scaling=scaling.replace("c3_", ""), n_factors=f, batch_size=1000, learning_rate=1e-3, random_seed=42, sgd_mode="sgd")
         for _ in range(3):
             tr.epoch()
         tr.flush()
@@ -514,6 +517,7 @@ def bpr_leg_sharded(args, X, rank, world):
     return {"metric": "BPR-MF samples/sec", "unit": "samples/s", "value": out["weak"]["value"], "scaling": "weak",
             "ms_per_epoch": out["weak"]["ms_per_step"], "samples_per_epoch": out["weak"]["samples_per_step"],
             "strong_scaling": out["strong"],
+            "c3": {"workload": "C3 (configs[2]) MF_BPR n_factors=%d, same sharding" % f, "weak": out["c3_weak"], "strong": out["c3_strong"]},
             "config": {"workload": "%s MF_BPR n_factors=%d sgd lr=1e-3" % (args.workload, f),
                        "parallelism": "user-sharded hogwild x%d, item factors replicated, one NCCL all-reduce of the ranks' item-factor movement (%.0f MB) per epoch, overlapped with the next epoch" % (
                            world, X.shape[1] * f * 4 / 1e6)}}
@@ -580,6 +584,28 @@ def bpr_leg(args, X):
             res["parity"] = {"ok": False, "error": repr(ex)}
     res["value"] = res["modes"]["hogwild_philox"]["value"]
     res["reference_semantics_value"] = res["modes"]["minibatch_bs1000_philox"]["value"]
+    # BASELINE.json configs[2] as written: BPRMF, 128 factors, MovieLens-20M-shape URM (C3: 138 K x 27 K)
+    try:
+        from recsys2019_deeplearning_evaluation_b200.synth import synth_config
+        X3 = synth_config("C3", values="binary")
+        c3 = {"workload": "C3 (configs[2]) MF_BPR n_factors=%d sgd lr=1e-3, epoch = %d samples" % (f, (X3.shape[0] // 1000 + 1) * 1000)}
+        for label, kw in (("minibatch_bs1000_philox", dict(batch_size=1000, sampler="philox")),
+                          ("hogwild_philox", dict(batch_size=1000, sampler="philox", hogwild=True))):
+            m = MatrixFactorization_Cython_Epoch(X3, n_factors=f, algorithm_name="MF_BPR", learning_rate=1e-3, random_seed=42,
+                                                 sgd_mode="sgd", **kw)
+            for _ in range(3):
+                m.epochIteration_Cython()
+            torch.cuda.synchronize()
+            devs = []
+            for _ in range(10):
+                m.epochIteration_Cython()
+                torch.cuda.synchronize()
+                devs.append(m.last_epoch_ms() * 1e-3)
+            c3[label] = {"value": m.samples_last_epoch() / float(np.mean(devs)), "device_ms_per_epoch": 1e3 * float(np.mean(devs))}
+            m._dealloc()
+        res["c3"] = c3
+    except Exception as ex:
+        res["c3"] = {"error": repr(ex)}
     if not args.no_cpu_baseline:
         from oracle import ref_loader
         mod = ref_loader.load("MatrixFactorization_Cython_Epoch")

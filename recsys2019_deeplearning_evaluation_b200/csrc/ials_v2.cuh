@@ -74,6 +74,7 @@ struct Smem {
   float* sw;       // [KC] sqrt(c - 1) of the step's entries
   double* cw;      // [KC] c
   int* rk;         // [KC] factor-row indices (-1 past the profile)
+  float* rdiag;    // [NB] reciprocals of the current diagonal block's diagonal
 };
 
 // ---- L z = v (forward) or L^T z = v (backward) in place on v (fp64), blocked by NB with the stored diagonal-block inverses
@@ -147,7 +148,8 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
     S.cw = reinterpret_cast<double*>(smem + o); o += sizeof(double) * KC;
     S.dinv = reinterpret_cast<float*>(smem + o); o += sizeof(float) * ((f + NB - 1) / NB) * NB * NBP;
     S.sw = reinterpret_cast<float*>(smem + o); o += sizeof(float) * KC;
-    S.rk = reinterpret_cast<int*>(smem + o);
+    S.rk = reinterpret_cast<int*>(smem + o); o += sizeof(int) * KC;
+    S.rdiag = reinterpret_cast<float*>(smem + o);
   }
   const uint32_t bar0 = tc::smem_u32(S.bars);
   const bool two = f > 128;  // rows 128.. exist: the second accumulator is in use
@@ -275,61 +277,60 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
       // ---- diagonal block in the registers of warp 0: lane i holds row i; its inverse for the solves
       if (warp == 0) {
         float a[NB];
+        {
+          // row k0 + lane, columns k0 .. k0 + 31 (16-byte aligned); entries past the diagonal belong to the next row or to
+          // padding and are never used (see below), lanes >= nb read a valid address of the last row
+          const float* src = S.L + roff(k0 + min(lane, nb - 1)) + k0;
 #pragma unroll
-        for (int c = 0; c < NB; ++c) a[c] = (lane < nb && c <= lane) ? S.L[roff(k0 + lane) + k0 + c] : 0.f;
+          for (int c4 = 0; c4 < NB / 4; ++c4) {
+            const float4 t4 = (c4 * 4 <= lane) ? *reinterpret_cast<const float4*>(src + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a[c4 * 4 + 0] = t4.x; a[c4 * 4 + 1] = t4.y; a[c4 * 4 + 2] = t4.z; a[c4 * 4 + 3] = t4.w;
+          }
+        }
+        // Lane i holds row i; only the lower triangle (c <= i) of a[] is ever read -- by this lane, or through the shuffles that
+        // fetch lane c's a[j] with c > j -- so nothing below is predicated on the lane: the entries above the diagonal hold
+        // garbage that feeds only garbage.  One reciprocal square root per step instead of a square root and a division (the
+        // factor only has to be fp32-good: the refinement is against the exact operator).
+        bool bad = false;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           if (j < nb) {
             const float ajj = __shfl_sync(0xffffffffu, a[j], j);
-            if (!(ajj > 0.f) && lane == 0) atomicExch(info, row + 1);
-            const float ljj = sqrtf(fmaxf(ajj, 1e-30f));
-            if (lane == j) a[j] = ljj; else if (lane > j) a[j] = a[j] / ljj;
+            bad = bad || !(ajj > 0.f);
+            const float rinv = rsqrtf(fmaxf(ajj, 1e-30f));
+            if (lane == 0) S.rdiag[j] = rinv;  // 1 / L11[j][j] for the forward substitutions below
+            a[j] = (lane == j) ? ajj * rinv : a[j] * rinv;
 #pragma unroll
-            for (int c = j + 1; c < NB; ++c) {
-              const float lcj = __shfl_sync(0xffffffffu, a[j], c);
-              if (lane >= c) a[c] -= a[j] * lcj;
-            }
+            for (int c = j + 1; c < NB; ++c) a[c] = fmaf(-a[j], __shfl_sync(0xffffffffu, a[j], c), a[c]);
           }
         }
+        if (bad && lane == 0) atomicExch(info, row + 1);
         if (lane < nb) {
 #pragma unroll
           for (int c = 0; c < NB; ++c)
             if (c <= lane) S.L[roff(k0 + lane) + k0 + c] = a[c];
         }
-        // inverse of the block: lane j solves L11 w = e_j (column j of the inverse), w[i] for i >= j
-        float* inv = S.dinv + (k0 / NB) * NB * NBP;
-        float w[NB];
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {
-          // row i of L11 is in lane i's registers: broadcast its entries as needed
-          float s = (i == lane) ? 1.f : 0.f;
-#pragma unroll
-          for (int c = 0; c < NB; ++c) {
-            if (c < i) {
-              const float lic = __shfl_sync(0xffffffffu, a[c], i);
-              s -= lic * w[c];
-            }
-          }
-          const float lii = __shfl_sync(0xffffffffu, a[i], i);
-          w[i] = (i >= lane && i < nb) ? s / lii : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-          if (lane < NB) inv[i * NBP + lane] = w[i];  // inv[i][j] = w_j[i]
       }
       __syncthreads();
       const int R0 = k0 + nb;
-      if (R0 >= f) break;
-      // ---- panel: row r of L21 = A21 L11^-T, one thread per row
+      // ---- one forward substitution against L11 for 32 + n_below right-hand sides: the rows of the panel below the block
+      // (row r of L21 = A21 L11^-T, threads 32..) and, in warp 0, the unit vectors -- column `lane` of inv(L11), kept for the
+      // solves.  The inverse costs the critical path nothing: it runs beside the panel.
       {
-        const int r = R0 + tid;
-        if (r < f) {
-          float* Lr = S.L + roff(r) + k0;
+        const bool is_inv = tid < 32;
+        const int r = R0 + tid - 32;
+        if (is_inv || r < f) {
+          float* Lr = is_inv ? nullptr : S.L + roff(r) + k0;
           float x[NB];
+          if (is_inv) {
 #pragma unroll
-          for (int c4 = 0; c4 < NB / 4; ++c4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(Lr + c4 * 4);
-            x[c4 * 4 + 0] = t4.x; x[c4 * 4 + 1] = t4.y; x[c4 * 4 + 2] = t4.z; x[c4 * 4 + 3] = t4.w;
+            for (int c = 0; c < NB; ++c) x[c] = (c == lane) ? 1.f : 0.f;
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < NB / 4; ++c4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(Lr + c4 * 4);
+              x[c4 * 4 + 0] = t4.x; x[c4 * 4 + 1] = t4.y; x[c4 * 4 + 2] = t4.z; x[c4 * 4 + 3] = t4.w;
+            }
           }
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
@@ -339,25 +340,37 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
 #pragma unroll
               for (int c = 0; c < NB; ++c)
                 if (c < j) s -= x[c] * Lj[c];
-              x[j] = s / Lj[j];
+              x[j] = s * S.rdiag[j];
             }
           }
+          if (is_inv) {
+            float* inv = S.dinv + (k0 / NB) * NB * NBP;
 #pragma unroll
-          for (int c4 = 0; c4 < NB / 4; ++c4)
-            *reinterpret_cast<float4*>(Lr + c4 * 4) = make_float4(x[c4 * 4 + 0], x[c4 * 4 + 1], x[c4 * 4 + 2], x[c4 * 4 + 3]);
+            for (int i = 0; i < NB; ++i) inv[i * NBP + lane] = (i >= lane && i < nb && lane < nb) ? x[i] : 0.f;  // inv[i][j] = (L11^-1 e_j)[i]
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < NB / 4; ++c4)
+              *reinterpret_cast<float4*>(Lr + c4 * 4) = make_float4(x[c4 * 4 + 0], x[c4 * 4 + 1], x[c4 * 4 + 2], x[c4 * 4 + 3]);
+          }
         }
       }
       __syncthreads();
+      if (R0 >= f) break;
       // ---- trailing update A22 -= L21 L21^T (lower part).  A warp owns a 16-row x 32-column block: lane -> 4 x 4 tile
       // (rows 4 (lane >> 3).., columns 4 (lane & 7)..): the 128-bit loads of a row / column panel are shared by 8 / 4 lanes
       {
         const int nt = f - R0;                    // trailing order
-        const int nsr = (nt + 15) / 16;           // 16-row strips
-        int st = 0;
-        for (int si = 0; si < nsr; ++si) {
-          const int ncs = (si * 16 + 15) / 32 + 1;  // 32-column strips that reach the lower triangle of this row strip
-          for (int sj = 0; sj < ncs; ++sj, ++st) {
-            if ((st & 7) != warp) continue;       // super-tiles dealt round-robin to the 8 warps
+        const int nsr = (nt + 15) / 16;           // 16-row strips; strip si meets (si >> 1) + 1 column strips of 32
+        // super-tiles in row-major order of the lower triangle, dealt round-robin to the warps: strips 2a and 2a + 1 start at
+        // a (a + 1) and (a + 1)^2
+        const int n_super = (nsr & 1) ? ((nsr + 1) / 2) * ((nsr + 1) / 2) : (nsr / 2) * (nsr / 2 + 1);
+        for (int n = warp; n < n_super; n += 8) {
+          {
+            int a = (int)sqrtf((float)n);
+            while (a * a > n) --a;
+            while ((a + 1) * (a + 1) <= n) ++a;
+            int si, sj;
+            if (n >= a * (a + 1)) { si = 2 * a; sj = n - a * (a + 1); } else { si = 2 * a - 1; sj = n - a * a; }
             const int r0 = R0 + si * 16 + (lane >> 3) * 4, c0 = R0 + sj * 32 + (lane & 7) * 4;
             if (c0 > r0 + 3 || r0 >= f) continue;
             float acc[4][4];
@@ -399,7 +412,8 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
     for (int it = 0; it < n_refine; ++it) {
       // part[w][m] = sum over this warp's profile entries of (c_k - 1) (y_k . x) y_k[m]; lane owns m = lane + 32 t
       double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int q = p0 + warp; q < p1; q += 8) {
+#pragma unroll 2
+      for (int q = p0 + warp; q < p1; q += 8) {  // two entries' loads in flight
         const double* y = Y + (size_t)idx[q] * f;
         double yv[8], dot = 0.0;
 #pragma unroll
@@ -455,7 +469,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
 inline size_t smem_bytes(int f) {
   size_t o = std::max<size_t>((size_t)roff(f) * 4, (size_t)STAGES * 2 * TILE);
   o = (o + 127) & ~(size_t)127;
-  o += 64 + sizeof(double) * (3 * (size_t)f + 8 * (size_t)f + KC) + sizeof(float) * ((size_t)((f + NB - 1) / NB) * NB * NBP + KC) + sizeof(int) * KC;
+  o += 64 + sizeof(double) * (3 * (size_t)f + 8 * (size_t)f + KC) + sizeof(float) * ((size_t)((f + NB - 1) / NB) * NB * NBP + KC) + sizeof(int) * KC + sizeof(float) * NB;
   return o + 64;
 }
 

@@ -26,7 +26,8 @@
 // next column's rows and pre-loaded row locations changed nothing either; a per-SM token that lets one CTA gather at a time
 // showed that ONE CTA's gather alone also takes 45 K cycles (latency-bound with 16 warps x 4 rows in flight), so anti-phase
 // buys nothing; replacing the returning atomics of the candidate collection by a two-pass sweep with prefix sums moved 9 K
-// cycles from the sweep into the second pass.  What would: more CTAs per SM in different phases (two neighbour windows of
+// cycles from the sweep into the second pass, and an atomic-free one-pass sweep (per-warp candidate regions, shuffle prefix
+// sums, two vectors in flight) left the sweep at 16 K cycles: its shared loads queue behind the OTHER CTA's atomics.  What would: more CTAs per SM in different phases (two neighbour windows of
 // 50 KB counters each: 3-4 CTAs) or two accumulators per CTA with warp-specialised gather / select.
 //
 // Gather.  The CSC side stores, per entry, where the user's padded row lives (csc_seg: start and length in 16-byte

@@ -318,6 +318,30 @@ def make_sharded_ials(group=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# K5: EASE_R with the Gram sharded over the users: G = X^T X = sum over user shards of X_r^T X_r.  Every
+# rank runs the dense mode of the similarity kernel on its own rows (equal interaction mass), one all-reduce of the n_items^2
+# fp32 matrix (1.25 GB at C4) gives every rank the full Gram, and every rank inverts it (the dense inverse does not shard at
+# this size: replicas).
+
+def make_sharded_ease(group=None):
+    """Returns a subclass of recommenders.EASE_R_Recommender whose Gram is accumulated over the ranks of `group`."""
+    import torch.distributed as dist
+    from .recommenders import EASE_R_Recommender
+
+    class ShardedEASE_R_Recommender(EASE_R_Recommender):
+        RECOMMENDER_NAME = "EASE_R_Recommender"
+
+        def _gram_device(self, rows=None):
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            b = balanced_ranges(np.diff(self.URM_train.indptr), world)
+            G = EASE_R_Recommender._gram_device(self, rows=(int(b[rank]), int(b[rank + 1])))
+            dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+            return G
+
+    return ShardedEASE_R_Recommender
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # K3 model parallelism: SLIM-BPR with S sharded by columns (SURVEY.md 8(e)).  At 200 K items the dense S is 160 GB: no
 # single GPU holds it (the reference trains such catalogues in its tree-sparse mode, SLIM_BPR_Cython_Epoch.pyx:509-1031).
 # Rank g owns S[:, cols_g]; every rank walks the SAME sample stream (counter-based Philox, common seed); per batch each rank

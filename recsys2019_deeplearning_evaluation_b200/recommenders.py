@@ -523,7 +523,6 @@ class EASE_R_Recommender(BaseItemSimilarityMatrixRecommender):
 
     def fit(self, topK=None, l2_norm=1e3, normalize_matrix=False, verbose=True):
         import torch
-        from .similarity import Compute_Similarity_Cython
         self.verbose = verbose
         if normalize_matrix:  # :47-51, sklearn.normalize l2 on rows then columns
             X = self.URM_train.astype(np.float64)
@@ -533,9 +532,7 @@ class EASE_R_Recommender(BaseItemSimilarityMatrixRecommender):
             self.URM_train = sps.csr_matrix(X.dot(sps.diags(1.0 / cn)), dtype=np.float32)
             self._d_urm = None
         n = self.n_items
-        sim = Compute_Similarity_Cython(self.URM_train, shrink=0, topK=n if n > 2048 else 0, normalize=False, similarity="cosine")
-        G = sim.compute_dense_device(0, n)  # symmetric: orientation is irrelevant
-        sim._dealloc()
+        G = self._gram_device()
         _, d_idx, _ = self._urm_device()
         B = torch.empty((n, n), dtype=torch.float32, device=G.device)
         _lib.check(self._lib.b200_ease_from_gram_device(G.data_ptr(), n, d_idx.data_ptr(), self.URM_train.nnz, float(l2_norm), None,
@@ -548,6 +545,17 @@ class EASE_R_Recommender(BaseItemSimilarityMatrixRecommender):
             from .slim_bpr_epoch import dense_topk_to_sparse
             self._d_B = None
             self.W_sparse = sps.csr_matrix(dense_topk_to_sparse(B, n, topK, along_columns=True, mode=0), dtype=np.float32)
+
+    def _gram_device(self, rows=None):
+        """X^T X (EASE_R_Recommender.py:55-56) as a dense [n_items, n_items] fp32 CUDA tensor, from all users or from the
+        user rows [rows[0], rows[1]) only (the partial Gram of one rank, dist.make_sharded_ease)."""
+        from .similarity import Compute_Similarity_Cython
+        n = self.n_items
+        X = self.URM_train if rows is None else self.URM_train[rows[0]:rows[1]]
+        sim = Compute_Similarity_Cython(X, shrink=0, topK=n if n > 2048 else 0, normalize=False, similarity="cosine")
+        G = sim.compute_dense_device(0, n)  # symmetric: orientation is irrelevant
+        sim._dealloc()
+        return G
 
     def _model_loaded(self):
         import torch

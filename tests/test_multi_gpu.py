@@ -46,3 +46,8 @@ def test_row_sharded_ials_matches_single_gpu():
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
 def test_column_sharded_slim_matches_single_shard():
     _torchrun("mgpu_slim_check.py")
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_user_sharded_ease_gram_matches_single_gpu():
+    _torchrun("mgpu_ease_check.py")
