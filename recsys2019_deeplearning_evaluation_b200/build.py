@@ -1,4 +1,6 @@
-"""In-tree build of libb200rec.so (sm_100a only) and of the C oracle.  `python -m recsys2019_deeplearning_evaluation_b200.build`.
+"""In-tree build of libb200rec.so (sm_100a only).  `python -m recsys2019_deeplearning_evaluation_b200.build`.
+(The checkers -- the C oracle and the compiled reference -- are built by oracle/build_oracle.py and oracle/build_ref.py,
+called from __graft_entry__.build().)
 
 nvcc cross-compiles without a GPU.  The resulting .so is git-ignored but travels to the GPU box with the
 gpurun snapshot.  Incremental: a source is recompiled only when it (or a header) is newer than its object.

@@ -324,7 +324,7 @@ int b200_ials_half_epoch_device(const int32_t* d_rows, int n_solve, const int32_
     // (well-conditioned systems; B200REC_IALS_V2=0 switches it off); a row whose refinement does not contract sends the half
     // epoch back to the fp64 kernel below
     const int v2_env = getenv("B200REC_IALS_V2") ? atoi(getenv("B200REC_IALS_V2")) : -1;  // 0 off, 1 every size, unset: where it wins
-    // measured on C4 (profiles/r02_ials_v2_c4.txt): 256 factors 1.25 s per epoch against 11.7 s, 128 factors 0.73 s against 0.83 s
+    // measured on C4 (profiles/r02_ials_v2_c4.txt): 256 factors 1.06 s per epoch against 11.7 s, 128 factors 0.56 s against 0.83 s
     const bool want_v2 = v2_env == 1 || (v2_env != 0 && f >= 128);
     if (want_v2 && n_other >= 4 * f) {
       if (ials::run_v2(st, d_rows, n_solve, d_ptr, d_idx, d_conf, d_Y, n_other, f, reg, d_X, d_YtY_work, info.get())) {

@@ -20,14 +20,15 @@
 //   * The solution is refined against the EXACT operator in fp64,  r = b - (Y^T Y x + Y_p^T((c-1) .* (Y_p x)) + reg x),
 //     matrix-free, twice: only the fp32 factor is approximate, so each step contracts the error by ~cond * 1e-7.  A row whose
 //     residual does not contract (ill-conditioned system) raises `redo`; the host then repeats the half epoch with ials.cu.
-// Y^T Y comes from gram_kernel (ials.cu, fp64).  One CTA (256 threads) per SM, rows strided over the grid.
+// Y^T Y comes from gram_kernel (ials.cu, fp64).  One CTA (512 threads) per SM, rows strided over the grid.
 #pragma once
 #include "gemm_tc.cuh"
 
 namespace b200 {
 namespace ials2 {
 
-constexpr int T = 256;
+constexpr int T = 512;                   // 16 warps: the phases between the barriers are latency-bound, more warps hide more of it
+constexpr int NW = T / 32;
 constexpr int KC = 32;                   // profile entries per step
 constexpr int STAGES = 2;
 constexpr int TILE = 256 * KC * 4;       // one 256 x 32 fp32 tile: 32 KB
@@ -69,7 +70,7 @@ struct Smem {
   float* L;        // padded lower triangle (aliases the staging tiles)
   unsigned char* tiles;
   uint64_t* bars;
-  double *b0, *xs, *rs, *part;  // rhs, solution, residual / correction, [8][f] partial sums
+  double *b0, *xs, *rs, *part;  // rhs, solution, residual / correction, [NW][f] partial sums
   float* dinv;     // [f / 32][32][33] inverses of the diagonal blocks of L (lower triangular, row-major, padded rows)
   float* sw;       // [KC] sqrt(c - 1) of the step's entries
   double* cw;      // [KC] c
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
     S.b0 = reinterpret_cast<double*>(smem + o); o += sizeof(double) * f;
     S.xs = reinterpret_cast<double*>(smem + o); o += sizeof(double) * f;
     S.rs = reinterpret_cast<double*>(smem + o); o += sizeof(double) * f;
-    S.part = reinterpret_cast<double*>(smem + o); o += sizeof(double) * 8 * f;
+    S.part = reinterpret_cast<double*>(smem + o); o += sizeof(double) * NW * f;
     S.cw = reinterpret_cast<double*>(smem + o); o += sizeof(double) * KC;
     S.dinv = reinterpret_cast<float*>(smem + o); o += sizeof(float) * ((f + NB - 1) / NB) * NB * NBP;
     S.sw = reinterpret_cast<float*>(smem + o); o += sizeof(float) * KC;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
     const int nk = (p1 - p0 + KC - 1) / KC;
 
     // ================= Gram on the tensor core
-    double my_rhs = 0.0;  // thread tid < f owns b0[tid] = (Y_p^T c)[tid]  (IALSRecommender.py:201)
+    double my_rhs = 0.0;  // threads m and m + 256 each hold half of b0[m] = (Y_p^T c)[m]  (IALSRecommender.py:201)
     for (int kb = 0; kb < nk; ++kb, ++gk) {
       const int s = (int)(gk & 1u);
       unsigned char* t_hi = S.tiles + (size_t)(s * 2 + 0) * TILE;
@@ -189,11 +190,12 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
       }
       if (gk >= (unsigned)STAGES) tc::mbar_wait(bar0 + 8u * s, (uint32_t)(((gk >> 1) - 1u) & 1u));  // the MMAs that read this stage are done
       __syncthreads();
-      // tile(m, k) = sqrt(c_k - 1) * Y[rk[k]][m]; thread = factor m, four entries per 128-bit store; zero past f / the profile
+      // tile(m, k) = sqrt(c_k - 1) * Y[rk[k]][m]; thread = (factor m, half of the step's entries), four entries per 128-bit
+      // store; zero past f / the profile
       {
-        const int m = tid;
+        const int m = tid & 255, kh = tid >> 8;
 #pragma unroll
-        for (int kq = 0; kq < KC / 4; ++kq) {
+        for (int kq = kh * (KC / 8); kq < (kh + 1) * (KC / 8); ++kq) {
           float h[4], l[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -242,11 +244,11 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
     // ================= accumulators -> B = A + Y^T Y + reg I, fp32, lower triangle.  Warp w owns TMEM lanes 32 (w % 4) .. + 31
     // (a row of each accumulator per thread) and half of the columns.
     {
-      const int g = warp & 3, hcol = warp >> 2;
+      const int g = warp & 3, hcol = warp >> 2;  // hcol in [0, NW / 4)
       for (int acc_i = 0; acc_i < (two ? 2 : 1); ++acc_i) {
         const int r = acc_i * 128 + g * 32 + lane;             // row of B
         const int ncol = acc_i == 0 ? 128 : 256;               // columns this accumulator holds
-        const int cbeg = hcol * (ncol / 2), cend = cbeg + ncol / 2;
+        const int cbeg = hcol * (ncol / (NW / 4)), cend = cbeg + ncol / (NW / 4);
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
           if (c0 > acc_i * 128 + g * 32 + 31) continue;         // above the diagonal for every row of this warp (uniform)
           uint32_t v[32];
@@ -267,9 +269,11 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
         }
       }
     }
-    if (tid < f) { S.b0[tid] = my_rhs; S.xs[tid] = my_rhs; }
+    if (tid >= 256 && tid - 256 < f) S.rs[tid - 256] = my_rhs;  // the upper half's share of the right-hand side
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // every warp has read the accumulators: the next row may overwrite them
+    if (tid < f) { const double b = my_rhs + S.rs[tid]; S.b0[tid] = b; S.xs[tid] = b; }
+    __syncthreads();
 
     // ================= blocked Cholesky, fp32, in place
     for (int k0 = 0; k0 < f; k0 += NB) {
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
         // super-tiles in row-major order of the lower triangle, dealt round-robin to the warps: strips 2a and 2a + 1 start at
         // a (a + 1) and (a + 1)^2
         const int n_super = (nsr & 1) ? ((nsr + 1) / 2) * ((nsr + 1) / 2) : (nsr / 2) * (nsr / 2 + 1);
-        for (int n = warp; n < n_super; n += 8) {
+        for (int n = warp; n < n_super; n += NW) {
           {
             int a = (int)sqrtf((float)n);
             while (a * a > n) --a;
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
       // part[w][m] = sum over this warp's profile entries of (c_k - 1) (y_k . x) y_k[m]; lane owns m = lane + 32 t
       double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 2
-      for (int q = p0 + warp; q < p1; q += 8) {  // two entries' loads in flight
+      for (int q = p0 + warp; q < p1; q += NW) {  // two entries' loads in flight
         const double* y = Y + (size_t)idx[q] * f;
         double yv[8], dot = 0.0;
 #pragma unroll
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
       __syncthreads();
       if (tid < f) {
         double ax = reg * S.xs[tid];
-        for (int w = 0; w < 8; ++w) ax += S.part[w * f + tid];
+        for (int w = 0; w < NW; ++w) ax += S.part[w * f + tid];
 #pragma unroll 8
         for (int n = 0; n < f; ++n) ax += YtY[(size_t)n * f + tid] * S.xs[n];  // symmetric: coalesced over tid; eight loads in flight
         S.rs[tid] = S.b0[tid] - ax;
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(T, 1) ials_rows_v2_kernel(const int* __restric
 inline size_t smem_bytes(int f) {
   size_t o = std::max<size_t>((size_t)roff(f) * 4, (size_t)STAGES * 2 * TILE);
   o = (o + 127) & ~(size_t)127;
-  o += 64 + sizeof(double) * (3 * (size_t)f + 8 * (size_t)f + KC) + sizeof(float) * ((size_t)((f + NB - 1) / NB) * NB * NBP + KC) + sizeof(int) * KC + sizeof(float) * NB;
+  o += 64 + sizeof(double) * (3 * (size_t)f + NW * (size_t)f + KC) + sizeof(float) * ((size_t)((f + NB - 1) / NB) * NB * NBP + KC) + sizeof(int) * KC + sizeof(float) * NB;
   return o + 64;
 }
 

@@ -585,6 +585,9 @@ int b200_slim_get_S_dense(b200_slim_t h, float* h_out, float* d_out) {
     DevBuf<float> tmp;
     float* dst = d_out;
     if (!dst) { tmp.alloc(cells); dst = tmp.get(); }
+    // the epoch kernels run on the caller's stream (possibly a non-blocking one) and need not have finished: this entry
+    // point has no stream argument, so it waits for the whole device before it reads S on the default stream
+    B200_CUDA(cudaDeviceSynchronize());
     slim_full_kernel<<<div_up((long long)cells, 256), 256>>>(h->p.S, n, h->p.symmetric, dst);
     B200_CUDA(cudaGetLastError());
     count_launch();
