@@ -13,7 +13,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for values, n_items in (("binary", 1100), ("ratings", 3000)):
+for values, n_items in (("binary", 1100), ("binary", 3000)):  # binary: the popularity diagonal of EASE_R is the Gram diagonal
     X = synth_urm(20_000, n_items, 0.01, seed=5, values=values, popularity=0.8)
     a = make_sharded_ease()(X, verbose=False)
     a.fit(topK=None, l2_norm=50.0, verbose=False)

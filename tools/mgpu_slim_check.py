@@ -36,8 +36,12 @@ if rank == 0:
     same = rel < 1e-3
     W1 = one.get_S()
     a, b = (W != 0).astype(np.int8), (W1 != 0).astype(np.int8)
-    overlap = float(a.multiply(b).sum() / max(1, b.sum()))
-    topk_same = overlap > 0.99 and abs(W - W1).max() < 1e-2 * abs(W1).max()
+    both = a.multiply(b)
+    overlap = float(both.sum() / max(1, b.sum()))
+    # cells near the K-th value may swap between the two runs (they differ by rounding): membership must agree on > 99 % of
+    # the entries and the common entries must carry the same value
+    common_diff = float(abs((W - W1).multiply(both)).max())
+    topk_same = overlap > 0.99 and common_diff < 1e-3 * float(abs(W1).max())
     ok = same and topk_same and abs(ref).max() > 0
     print("[sharded SLIM x%d] slab vs single-shard run: rel. Frobenius %.2e (max abs %.2e, max |S| %.2e): %s; merged row top-K overlap %.4f: %s; %.3e samples/s (batch %d)" % (
         world, rel, float(abs(mine - ref).max()), float(abs(ref).max()), same, overlap, topk_same, 5 * X.shape[0] / dt, kw["batch_size"]), flush=True)
