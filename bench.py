@@ -313,10 +313,12 @@ def run_b200(args, rank, world, local_rank):
         if int(flag.item()) == 0:
             table = None
 
+    out_tab = sim.compute_topk_device(lo, hi) if table is None else None  # the output table is allocated once, every step refills it
+
     def step():
         if table is not None:
             return table.fill(sim, lo, hi)
-        tab = sim.compute_topk_device(lo, hi)
+        tab = sim.compute_topk_device(lo, hi, out=out_tab)
         if world > 1:
             return allgather_topk_tables(tab.idx, tab.val, tab.cnt, bounds)
         return tab.idx, tab.val, tab.cnt
@@ -346,9 +348,11 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- kernel-only roofline leg (CUDA events around the kernel on its launching stream, inside the library)
     kms = []
+    scratch = sim.compute_topk_device(lo, hi)
     for _ in range(args.steps):
-        sim.compute_topk_device(lo, hi)
+        sim.compute_topk_device(lo, hi, out=scratch)
         kms.append(sim.last_kernel_ms())
+    del scratch
     kernel_avg_ms = float(np.mean(kms))
     ent = sim.gathered_entries(lo, hi)
     bpe = 4 if sim.binary_path else 8
@@ -370,7 +374,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- e2e arm: host scipy CSR in -> scipy CSR out through the reference-facing class; inputs in page-locked memory (the
     # contract's case) and in ordinary pageable numpy arrays (what a caller's scipy matrix is)
-    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    e2e_steps = max(3, args.e2e_steps)
     h2d = X.data.nbytes + X.indices.nbytes + X.indptr.nbytes
     d2h = 0
 
@@ -692,7 +696,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C5", help="C1..C5 (synth.CONFIGS); the metric is quoted on C5")
     ap.add_argument("--values", default="binary", choices=["binary", "ratings", "continuous"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-cols", type=int, default=2000, help="columns in the CPU-baseline slice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bpr", action="store_true", help="skip the BPR-MF samples/sec leg")

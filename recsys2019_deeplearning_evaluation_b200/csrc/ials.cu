@@ -244,7 +244,6 @@ void run(cudaStream_t st, const int* rows, int n_solve, const int* ptr, const in
 }  // namespace ials
 }  // namespace b200
 
-#include "ials_tc.cuh"
 #include "ials_v2.cuh"
 
 namespace b200 {
@@ -270,29 +269,6 @@ bool run_v2(cudaStream_t st, const int* rows, int n_solve, const int* ptr, const
   B200_CUDA(cudaFuncSetAttribute(ials2::ials_rows_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::max(1, std::min(n_solve, sm_count()));
   ials2::ials_rows_v2_kernel<<<grid, ials2::T, smem, st>>>(rows, n_solve, ptr, idx, conf, Y, YtY, f, reg, X, info, redo.get(), 2);
-  B200_CUDA(cudaGetLastError());
-  count_launch();
-  int h_redo = 0;
-  B200_CUDA(cudaMemcpyAsync(&h_redo, redo.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
-  B200_CUDA(cudaStreamSynchronize(st));
-  return h_redo == 0;
-}
-
-// Tensor-core half epoch (ials_tc.cuh); returns false when a row asked for the fp64 path.
-template <int FB>
-bool run_tc(cudaStream_t st, const int* rows, int n_solve, const int* ptr, const int* idx, const float* conf, const double* Y,
-            int n_other, int f, double reg, double* X, double* YtY, int* info) {
-  const size_t smem_g = sizeof(double) * ((size_t)TROWS * f + TROWS);
-  B200_CUDA(cudaMemsetAsync(YtY, 0, sizeof(double) * (size_t)f * f, st));
-  const int grid_g = std::max(1, std::min(sm_count() * 4, (n_other + 63) / 64));
-  gram_kernel<FB, 0, FB><<<grid_g, THREADS, smem_g, st>>>(Y, n_other, f, YtY);
-  count_launch();
-  DevBuf<int> redo(1);
-  B200_CUDA(cudaMemsetAsync(redo.get(), 0, sizeof(int), st));
-  const size_t smem = tc_smem_bytes(f);
-  B200_CUDA(cudaFuncSetAttribute(ials_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::max(1, std::min(n_solve, sm_count()));
-  ials_rows_tc_kernel<<<grid, TC_THREADS, smem, st>>>(rows, n_solve, ptr, idx, conf, Y, YtY, f, reg, X, info, redo.get(), 2);
   B200_CUDA(cudaGetLastError());
   count_launch();
   int h_redo = 0;
@@ -328,22 +304,6 @@ int b200_ials_half_epoch_device(const int32_t* d_rows, int n_solve, const int32_
     const bool want_v2 = v2_env == 1 || (v2_env != 0 && f >= 128);
     if (want_v2 && n_other >= 4 * f) {
       if (ials::run_v2(st, d_rows, n_solve, d_ptr, d_idx, d_conf, d_Y, n_other, f, reg, d_X, d_YtY_work, info.get())) {
-        int h_info = 0;
-        B200_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaStreamSynchronize(st));
-        B200_REQUIRE(h_info == 0, "b200_ials_half_epoch: normal equations of row %d are not positive definite", h_info - 1);
-        return;
-      }
-      B200_CUDA(cudaMemsetAsync(info.get(), 0, sizeof(int), st));  // redo the half epoch in fp64
-    }
-    // first-generation tensor-core path (ials_tc.cuh, n_factors <= 128): opt-in, kept for A/B runs
-    static const bool want_tc = getenv("B200REC_IALS_TC") != nullptr && atoi(getenv("B200REC_IALS_TC")) == 1;
-    if (want_tc && f <= 128 && n_other >= 4 * f) {
-      bool ok;
-      if (f <= 32) ok = ials::run_tc<2>(st, d_rows, n_solve, d_ptr, d_idx, d_conf, d_Y, n_other, f, reg, d_X, d_YtY_work, info.get());
-      else if (f <= 64) ok = ials::run_tc<4>(st, d_rows, n_solve, d_ptr, d_idx, d_conf, d_Y, n_other, f, reg, d_X, d_YtY_work, info.get());
-      else ok = ials::run_tc<8>(st, d_rows, n_solve, d_ptr, d_idx, d_conf, d_Y, n_other, f, reg, d_X, d_YtY_work, info.get());
-      if (ok) {
         int h_info = 0;
         B200_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, st));
         B200_CUDA(cudaStreamSynchronize(st));

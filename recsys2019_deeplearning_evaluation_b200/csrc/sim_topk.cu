@@ -116,7 +116,6 @@ struct KParams {
   int* redo;
   int* fail;
   const int* n_range_dev;  // window kernel: the number of columns to process is read from here when set
-  int* gather_lock;        // K1-D: one word per SM, the token of the CTA that is gathering there
   unsigned long long* prof;  // optional [8] per-phase cycle counters (thread 0 of every CTA), test/bench hook
 };
 
@@ -1203,7 +1202,7 @@ struct b200_sim_s {
   // K1-D (binary path, large sparse catalogues): second row layout with one window, CSC-side row locations, norm tile
   // bounds, ring / table geometry, routing threshold (expected hits per neighbour of a column) and last-launch statistics
   bool want_k1c = true, k1c = false;
-  DevBuf<int> csr_idx1, fail, gather_lock;
+  DevBuf<int> csr_idx1, fail;
   DevBuf<int2> csc_seg;
   DevBuf<float> tbnd;
   DevBuf<int4> worklist;
@@ -1559,8 +1558,6 @@ void build(b200_sim_s* h, const int32_t* h_indptr, const int32_t* h_indices, con
       h->tbnd.alloc((size_t)h->ntile + 1);
       k1d_tile_bounds_kernel<<<div_up(h->ntile + 1, 128), 128, 0, st>>>(h->BN.get(), n_cols, h->ntile, h->tbnd.get()); count_launch();
       h->fail.alloc(1);
-      h->gather_lock.alloc(1024);
-      B200_CUDA(cudaMemsetAsync(h->gather_lock.get(), 0, 1024 * sizeof(int), st));
       h->worklist.alloc((size_t)n_cols);
       h->h_old2new.resize((size_t)n_cols);
       h->h_csc_ptr.resize((size_t)n_cols + 1);
@@ -1753,14 +1750,13 @@ static void launch_topk(b200_sim_t h, int start_col, int end_col, int32_t* d_idx
   p.prof = h->prof_on ? h->prof.get() : nullptr;
   p.bm_words = h->bm_words; p.cap_d = h->cap_d; p.fail_every = h->fail_every; p.ntile = h->ntile; p.tbnd = h->tbnd.get();
   p.csr_idx1 = h->csr_idx1.get(); p.csc_seg = h->csc_seg.get(); p.worklist = h->worklist.get();
-  p.redo = h->order.get(); p.fail = h->fail.get(); p.gather_lock = h->gather_lock.get();
+  p.redo = h->order.get(); p.fail = h->fail.get();
   p.n_range_dev = nullptr;
   B200_CUDA(cudaEventRecord(h->ev0, st));
   if (n_sparse > 0) {
     // nibble-counter kernel first; columns with an overflowed counter are appended to the window kernel's list, whose length
     // the window kernel then reads from the device (no host round trip between the two launches)
     B200_CUDA(cudaMemcpyAsync(h->fail.get(), &h->n_dense_last, sizeof(int), cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaMemsetAsync(h->gather_lock.get(), 0, 1024 * sizeof(int), st));  // no token survives an aborted launch
     KParams q = p;
     q.n_range = n_sparse;
     k1d_kernel_for(h->formula)<<<std::min(n_sparse, h->n_sm * h->ctas_per_sm), D_THREADS, h->smem1_bytes, st>>>(q);

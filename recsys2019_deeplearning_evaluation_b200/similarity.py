@@ -137,13 +137,19 @@ class Compute_Similarity_Cython:
         return sps.csr_matrix(dense_topk_to_sparse(D, n, self.TopK, along_columns=False, mode=1).T)
 
     # ------------------------------------------------------------------ device-level API (multi-GPU, bench)
-    def compute_topk_device(self, lo, hi, stream=None):
+    def compute_topk_device(self, lo, hi, stream=None, out=None):
+        """Top-K rows of the columns [lo, hi) as a device-resident TopKTable; `out` (a table of the same range from an earlier
+        call) is overwritten in place instead of allocating a new one."""
         import torch
         n = hi - lo
-        dev = torch.device("cuda", torch.cuda.current_device())
-        idx = torch.empty((max(n, 1), self.K), dtype=torch.int32, device=dev)
-        val = torch.empty((max(n, 1), self.K), dtype=torch.float32, device=dev)
-        cnt = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+        if out is not None:
+            assert out.start_col == lo and out.end_col == hi and out.K == self.K, "out= must come from the same column range"
+            idx, val, cnt = out.idx, out.val, out.cnt
+        else:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            idx = torch.empty((max(n, 1), self.K), dtype=torch.int32, device=dev)
+            val = torch.empty((max(n, 1), self.K), dtype=torch.float32, device=dev)
+            cnt = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         _lib.check(self._lib.b200_sim_compute_device(self._h, lo, hi, idx.data_ptr(), val.data_ptr(), cnt.data_ptr(),
                                                      ctypes.c_void_p(st)))

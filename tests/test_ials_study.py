@@ -42,7 +42,7 @@ def test_one_refinement_step_reaches_fp64_level():
 
 
 def test_contraction_check_of_the_device_kernel_on_the_model():
-    """The check of ials_tc.cuh (|r|^2 must shrink >= 1000-fold between the first and the second correction): only the
+    """The check of ials_v2.cuh (|r|^2 must shrink >= 1000-fold between the first and the second correction): only the
     PROFILE Gram is approximate (Y^T Y stays fp64), so both a well-conditioned system and the ill-conditioned shape with
     barely more rows than factors contract by many orders of magnitude; a factor that is really off (1 % error) is caught."""
     rng = np.random.default_rng(5)
