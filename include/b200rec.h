@@ -151,7 +151,7 @@ int b200_sim_col_work(b200_sim_t h, int64_t* out_n_cols);
  * replaces  MatrixFactorization/Cython/MatrixFactorization_Cython_Epoch.pyx:51-987
  *           (ctor :96-151, epochIteration_Cython :276-286, BPR :583-678, FunkSVD :289-390,
  *            apply :773-832, adaptive_gradient :838-876, samplers :881-987, getters :688-705)
- * AsySVD (:396-578) is out of scope.
+ * AsySVD (:396-578) has its own handle below (K2b).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct b200_mf_s* b200_mf_t;
 
@@ -197,10 +197,35 @@ int b200_mf_delta_snapshot_device(const float* d_V, float* d_B, float* d_own, fl
 int b200_mf_delta_apply_device(float* d_V, float* d_B, const float* d_sum, const float* d_own, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K2b: AsymmetricSVD epochs  
+ * replaces  MatrixFactorization_Cython_Epoch.pyx:396-578 epochIteration_Cython_ASY_SVD_SGD (algorithm_name="ASY_SVD",
+ *           batch size 1 :399) with sampleMSE_Cython :881-938 and adaptive_gradient :838-876
+ * Both factor tables have one row per ITEM (pyx:163-166): h_profile_factors is the reference's USER_factors (the Y of the
+ * paper, summed over a user's profile), h_item_factors its ITEM_factors; row-major [n_items x n_factors] doubles drawn by the
+ * caller exactly as pyx:177-178 does.  The sample stream is the reference's own: srand(random_seed) / rand() replayed on the
+ * host (has_seed == 0: glibc's default stream, seed 1).  One epoch = nnz + 1 samples (pyx:402), strictly in order.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200_asysvd_s* b200_asysvd_t;
+int b200_asysvd_create(b200_asysvd_t* out, int64_t n_users, int64_t n_items, int64_t nnz, const int32_t* h_indptr,
+                       const int32_t* h_indices, const float* h_data, int n_factors, double negative_interactions_quota,
+                       float learning_rate, int use_bias, float user_reg, float item_reg, float bias_reg, int sgd_mode,
+                       float gamma, float beta_1, float beta_2, const double* h_profile_factors,
+                       const double* h_item_factors, int has_seed, uint32_t random_seed);
+int b200_asysvd_destroy(b200_asysvd_t h);
+int b200_asysvd_epoch(b200_asysvd_t h, void* stream);
+/* the (user, item, rating) stream of the last epoch, nnz + 1 entries each */
+int b200_asysvd_get_samples(b200_asysvd_t h, int32_t* u, int32_t* i, float* r);
+/* get_USER_factors (= Y, n_items rows) / get_ITEM_factors / get_USER_bias / get_ITEM_bias / get_GLOBAL_bias; any may be NULL */
+int b200_asysvd_get_factors(b200_asysvd_t h, double* profile_factors, double* item_factors, double* user_bias,
+                            double* item_bias, double* global_bias);
+int b200_asysvd_last_epoch_ms(b200_asysvd_t h, float* ms);
+
+/* ------------------------------------------------------------------------------------------------
  * K3: SLIM-BPR epochs on a dense / symmetric item-item matrix  (hot path ii)
  * replaces  SLIM_BPR/Cython/SLIM_BPR_Cython_Epoch.pyx:60-480  (ctor :88-134, epochIteration_Cython :211-335,
  *           sampleBPR_Cython :436-480, adaptive_gradient :395-433, get_S :340-388, Triangular_Matrix :1223-1415)
- * The tree-sparse training mode (Sparse_Matrix_Tree_CSR, :509-1031) is out of scope.
+ * The tree-sparse training mode (train_with_sparse_weights, Sparse_Matrix_Tree_CSR :579-1031) keeps its semantics on the
+ * dense array: b200_slim_enable_tree / b200_slim_tree_prune below.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct b200_slim_s* b200_slim_t;
 
@@ -218,6 +243,15 @@ int b200_slim_get_samples(b200_slim_t h, int32_t* u, int32_t* i, int32_t* j);
  * pyx:1363-1372), row-major fp32, to a host buffer and/or a device buffer (either may be NULL) */
 int b200_slim_get_S_dense(b200_slim_t h, float* h_out, float* d_out);
 int b200_slim_last_epoch_ms(b200_slim_t h, float* ms);
+/* train_with_sparse_weights=True (pyx:111-134): call once after b200_slim_create (symmetric = 0, hogwild = 0) and before the
+ * first epoch.  A byte map records the cells the reference's row trees would hold (add_value, pyx:617-680); every epoch cuts
+ * the rows that hold >= topK cells back to their topK largest after the samples n with n % (n_users / 5) == 0
+ * (rebalance_tree, pyx:318-319, :782-802; ties keep the higher column like the reference's stable qsort, :991).
+ * topK = 0 is the reference's topK=False: nothing is ever removed. */
+int b200_slim_enable_tree(b200_slim_t h, int topK);
+/* the selection get_S() applies IN PLACE before it emits the rows (get_scipy_csr(TopK), pyx:762-763); touch_diagonal != 0
+ * first creates the diagonal cells with value 0 like get_S does (pyx:349-350) -- they count towards a row's length */
+int b200_slim_tree_prune(b200_slim_t h, int touch_diagonal, void* stream);
 /* Column-sharded S for catalogues whose dense S does not fit one GPU (the reference's answer to that is
  * the tree-sparse mode, pyx:509-1031): this handle owns S[:, col_lo:col_hi) as an [n_items, col_hi - col_lo] slab (full
  * matrix, not the triangular storage).  Every rank creates one with the SAME random_seed and draws the same Philox sample
@@ -241,7 +275,9 @@ int b200_slim_shard_device(b200_slim_t h, float** d_S, int* col_lo, int* col_hi)
  * mode 0: the K largest of the non-zero values; mode 1: the K largest over all cells, zeros then dropped.
  * Output table [n, K] like b200_sim_compute_device (line = row or column, idx = position along it).
  * ------------------------------------------------------------------------------------------------ */
-enum b200_topk_mode { B200_TOPK_NONZERO = 0, B200_TOPK_ZEROS_OUTRANK = 1 };
+enum b200_topk_mode { B200_TOPK_NONZERO = 0, B200_TOPK_ZEROS_OUTRANK = 1,
+                      /* SLIMElasticNetRecommender.py:99-107: the min(nnz - 1, K) largest non-zero values of a line */
+                      B200_TOPK_NONZERO_DROP_LAST = 2 };
 int b200_dense_topk_device(const float* d_matrix, int n, int K, int along_columns, int mode, int32_t* d_idx,
                            float* d_val, int32_t* d_cnt, void* stream);
 /* mode 0 over the lines of a rectangular dense matrix (line l starts at l * stride_line, its cells are stride_inner apart);
@@ -277,6 +313,19 @@ int b200_score_mask_device(const int32_t* d_users, int n_users_block, const int3
 /* per row the `cutoff` (<= 1024) best items, best first, ties by ascending item index: [n_rows, cutoff] tables */
 int b200_score_topn_device(const float* d_scores, int n_rows, int n_items, int cutoff, int32_t* d_items,
                            float* d_item_scores, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7: SLIM ElasticNet  
+ * replaces  SLIM_ElasticNet/SLIMElasticNetRecommender.py:77-131 -- one sklearn ElasticNet(precompute=True, fit_intercept=False,
+ *           selection='random', max_iter=100, tol=1e-4).fit(URM with column j zeroed, URM[:, j]) per item
+ * d_G: the Gram matrix X^T X, [n_items x n_items] fp32 (its diagonal is not read), d_diag: the sum of squares of every column.
+ * For item j the coordinate descent runs on Q = G without row / column j, q = G[:, j], with sklearn's stopping rule
+ * (max|dw| / max|w| < tol -> duality gap < tol * ||y||^2) in CYCLIC coordinate order (the reference's order is drawn from an
+ * unseeded generator).  d_coef_T[j, :] receives the coefficients of item j (dense; top-K selection: b200_dense_topk_device,
+ * mode B200_TOPK_NONZERO_DROP_LAST), d_n_iter (nullable) the passes used.
+ * ------------------------------------------------------------------------------------------------ */
+int b200_slim_enet_device(const float* d_G, const float* d_diag, int n_items, int64_t n_users, double l1_ratio, double alpha,
+                          int positive_only, int max_iter, float tol, float* d_coef_T, int32_t* d_n_iter, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5: EASE^R closed form  (hot path iii)

@@ -6,11 +6,14 @@
  *   MatrixFactorization/Cython/MatrixFactorization_Cython_Epoch.pyx
  *       epochIteration_Cython_BPR_SGD       :583-678      sampleBPR_Cython   :943-987
  *       epochIteration_Cython_FUNK_SVD_SGD  :289-390      sampleMSE_Cython   :881-938
+ *       epochIteration_Cython_ASY_SVD_SGD   :396-578      (batch size 1; USER_factors is the n_items x f matrix Y)
  *       _apply_minibatch_updates_...        :773-832      adaptive_gradient  :838-876
  *       first-touch lists                   :709-769      adam powers        :220-221, :361-364, :649-652
  *   SLIM_BPR/Cython/SLIM_BPR_Cython_Epoch.pyx
  *       epochIteration_Cython :211-335, sampleBPR_Cython :436-480, adaptive_gradient :395-433,
  *       Triangular_Matrix add_value/get_value :1272-1330 (symmetric storage)
+ *       Sparse_Matrix_Tree_CSR (train_with_sparse_weights): add_value/get_value :617-733, rebalance_tree :782-802,
+ *       topK_selection_from_list :954-1031 -- restated on a dense array plus a cell-exists map (slim_prune below)
  *   libc rand()/srand(): glibc TYPE_3 additive-feedback generator (not under the reference tree; its published
  *   algorithm is restated in glibc_rand_* below and pinned against libc's rand() in tests/test_oracle_sgd.py).
  *
@@ -138,7 +141,7 @@ static double adapt(const adapt_t* a, double g, double* cache, double* m1, doubl
 
 /* ---------------------------------------------------------------- MF trainer state (caller-owned arrays) */
 typedef struct {
-  int n_users, n_items, f, batch_size, algorithm; /* algorithm: 0 MF_BPR, 1 FUNK_SVD */
+  int n_users, n_items, f, batch_size, algorithm; /* algorithm: 0 MF_BPR, 1 FUNK_SVD, 2 ASY_SVD (U holds n_items rows) */
   int use_bias;
   double lr, user_reg, item_reg, bias_reg, positive_reg, negative_reg, quota;
   adapt_t ad;
@@ -213,11 +216,67 @@ static void clear_minibatch(mf_t* s) { /* pyx:723-735 */
   s->n_users_touched = 0;
 }
 
+/* pyx:396-578: one sample per step; the user is represented by the sum of the Y rows (s->U, n_items x f) of the items
+ * in the profile divided by sqrt(profile length); Y rows of the whole profile and the X row (s->V) of the sampled item are
+ * updated at once, every parameter with its own adaptive state. */
+static long asy_svd_epoch(mf_t* s) {
+  const int f = s->f;
+  const long n_total = s->nnz / 1 + 1; /* pyx:402 with batch_size == 1 */
+  long b, k, count = 0;
+  int q;
+  double* acc = (double*)malloc(sizeof(double) * (size_t)f);
+  for (b = 0; b < n_total; ++b, ++count) {
+    long u, i, start, end;
+    double r = 0.0, pred, err, den, g;
+    if (s->ext_u) { u = s->ext_u[s->ext_pos]; i = s->ext_i[s->ext_pos]; r = s->ext_r[s->ext_pos]; s->ext_pos++; }
+    else sample_mse(&s->rng, s->indptr, s->indices, s->data, s->n_users, s->n_items, s->quota, &u, &i, &r);
+    if (s->rec_u) { s->rec_u[s->rec_pos] = (int32_t)u; s->rec_i[s->rec_pos] = (int32_t)i; s->rec_j[s->rec_pos] = -1; s->rec_pos++; }
+    start = s->indptr[u]; end = s->indptr[u + 1];
+    for (q = 0; q < f; ++q) acc[q] = 0.0;
+    for (k = start; k < end; ++k) { const long it = s->indices[k]; for (q = 0; q < f; ++q) acc[q] += s->U[it * f + q]; }
+    den = sqrt((double)(end - start));
+    for (q = 0; q < f; ++q) acc[q] /= den;
+    pred = s->use_bias ? s->mu[0] + s->bu[u] + s->bi[i] : 0.0;
+    for (q = 0; q < f; ++q) pred += acc[q] * s->V[i * f + q];
+    err = r - pred;
+    if (s->use_bias) {
+      g = err - s->bias_reg * s->mu[0];
+      g = adapt(&s->ad, g, s->cmu, s->m1mu, s->m2mu);
+      s->mu[0] += s->lr * g;
+      g = adapt(&s->ad, err - s->bias_reg * s->bi[i], s->cbi ? s->cbi + i : 0, s->m1bi ? s->m1bi + i : 0, s->m2bi ? s->m2bi + i : 0);
+      {
+        const double gu = adapt(&s->ad, err - s->bias_reg * s->bu[u], s->cbu ? s->cbu + u : 0, s->m1bu ? s->m1bu + u : 0, s->m2bu ? s->m2bu + u : 0);
+        s->bi[i] += s->lr * g;
+        s->bu[u] += s->lr * gu;
+      }
+    }
+    for (k = start; k < end; ++k) { /* pyx:505-521: every Y row of the profile, H_i read from the not yet updated X row */
+      const long it = s->indices[k];
+      for (q = 0; q < f; ++q) {
+        const double Hi = s->V[i * f + q], Wu = s->U[it * f + q];
+        g = err * Hi - s->user_reg * Wu;
+        g = adapt(&s->ad, g, s->cU ? s->cU + it * f + q : 0, s->m1U ? s->m1U + it * f + q : 0, s->m2U ? s->m2U + it * f + q : 0);
+        s->U[it * f + q] += s->lr * g;
+      }
+    }
+    for (q = 0; q < f; ++q) { /* pyx:524-539: the accumulated profile from BEFORE the Y update */
+      const double Hi = s->V[i * f + q];
+      g = err * acc[q] - s->item_reg * Hi;
+      g = adapt(&s->ad, g, s->cV ? s->cV + i * f + q : 0, s->m1V ? s->m1V + i * f + q : 0, s->m2V ? s->m2V + i * f + q : 0);
+      s->V[i * f + q] += s->lr * g;
+    }
+    if (s->ad.mode == 3) { s->ad.b1_pow *= s->ad.beta1; s->ad.b2_pow *= s->ad.beta2; } /* per sample, pyx:544-547 */
+  }
+  free(acc);
+  return count;
+}
+
 /* one epochIteration_Cython; returns the number of samples processed */
 long mf_epoch(mf_t* s) {
   const int f = s->f;
   long n_batches, b, smp, count = 0;
   int q;
+  if (s->algorithm == 2) return asy_svd_epoch(s);
   if (s->algorithm == 0) n_batches = (long)(s->n_users / s->batch_size) + 1;  /* pyx:586 */
   else n_batches = (long)(s->nnz / s->batch_size) + 1;                        /* pyx:292 */
   for (b = 0; b < n_batches; ++b) {
@@ -286,6 +345,8 @@ typedef struct {
   glibc_rand_t rng;
   const int32_t* ext_u; const int32_t* ext_i; const int32_t* ext_j; long ext_pos;
   int32_t *rec_u, *rec_i, *rec_j; long rec_pos;
+  unsigned char* exists;       /* tree mode (train_with_sparse_weights): 1 where the reference's row tree holds a cell */
+  int tree_topk;               /* the TopK of rebalance_tree (0 = False: nothing is removed) */
 } slim_t;
 
 static double slim_get(const slim_t* s, long a, long b) {
@@ -295,6 +356,42 @@ static double slim_get(const slim_t* s, long a, long b) {
 static void slim_add(slim_t* s, long a, long b, double v) {
   if (s->symmetric && b > a) { long t = a; a = b; b = t; }
   s->S[a * (long)s->n_items + b] += v;
+  if (s->exists) s->exists[a * (long)s->n_items + b] = 1; /* add_value creates the cell, pyx:627-680 */
+}
+
+/* rebalance_tree(TopK) pyx:782-802 / the selection inside get_scipy_csr(TopK) pyx:762-763, through
+ * topK_selection_from_list pyx:954-1031: a row that holds at least TopK cells keeps the TopK largest by value.  The list is
+ * in ascending column order and glibc's qsort is a stable merge sort at these sizes, so among equal values the higher
+ * columns sit last and are the ones kept.  Cells that are dropped cease to exist (they read as 0 again). */
+typedef struct { double v; long col; } slim_cell_t;
+static int slim_cell_cmp(const void* a, const void* b) {
+  const slim_cell_t *x = (const slim_cell_t*)a, *y = (const slim_cell_t*)b;
+  if (x->v < y->v) return -1;
+  if (x->v > y->v) return 1;
+  return x->col < y->col ? -1 : (x->col > y->col ? 1 : 0);
+}
+void slim_prune(slim_t* s, long topk) {
+  const long n = s->n_items;
+  long r, c, m, q;
+  slim_cell_t* cells;
+  if (!s->exists || topk <= 0) return;
+  cells = (slim_cell_t*)malloc(sizeof(slim_cell_t) * (size_t)n);
+  for (r = 0; r < n; ++r) {
+    m = 0;
+    for (c = 0; c < n; ++c)
+      if (s->exists[r * n + c]) { cells[m].v = s->S[r * n + c]; cells[m].col = c; ++m; }
+    if (m < topk) continue;
+    qsort(cells, (size_t)m, sizeof(slim_cell_t), slim_cell_cmp);
+    for (q = 0; q < m - topk; ++q) { s->S[r * n + cells[q].col] = 0.0; s->exists[r * n + cells[q].col] = 0; }
+  }
+  free(cells);
+}
+/* get_S in tree mode touches every diagonal cell (add_value(index, index, -get_value(index, index)), pyx:349-350): the
+ * cell exists afterwards, with value 0 */
+void slim_touch_diagonal(slim_t* s) {
+  long r;
+  if (!s->exists) return;
+  for (r = 0; r < s->n_items; ++r) { s->S[r * (long)s->n_items + r] = 0.0; s->exists[r * (long)s->n_items + r] = 1; }
 }
 
 long slim_epoch(slim_t* s) { /* pyx:211-335 */
@@ -316,6 +413,8 @@ long slim_epoch(slim_t* s) { /* pyx:211-335 */
       if (sn != j) slim_add(s, j, sn, -s->lr * (gj - s->lj_reg * slim_get(s, j, sn)));
     }
     if (s->ad.mode == 3) { s->ad.b1_pow *= s->ad.beta1; s->ad.b2_pow *= s->ad.beta2; } /* per sample, pyx:309-312 */
+    /* pyx:318-319: `n_current_sample % (self.n_users/5) == 0` is a float modulo under language_level=3 */
+    if (s->exists && n != 0 && fmod((double)n, (double)s->n_users / 5.0) == 0.0) slim_prune(s, s->tree_topk);
   }
   return count;
 }

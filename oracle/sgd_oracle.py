@@ -70,7 +70,8 @@ class SLIMState(C.Structure):
                 ("S", P), ("c", P), ("m1", P), ("m2", P),
                 ("rng", GlibcRandState),
                 ("ext_u", P), ("ext_i", P), ("ext_j", P), ("ext_pos", C.c_long),
-                ("rec_u", P), ("rec_i", P), ("rec_j", P), ("rec_pos", C.c_long)]
+                ("rec_u", P), ("rec_i", P), ("rec_j", P), ("rec_pos", C.c_long),
+                ("exists", P), ("tree_topk", C.c_int)]
 
 
 def _p(a):
@@ -99,8 +100,10 @@ class MFOracle:
                  init_factors=None, samples=None, record=0):
         if sgd_mode not in _MODES:
             raise ValueError("sgd_mode")
-        if algorithm_name not in ("FUNK_SVD", "MF_BPR"):
-            raise ValueError("algorithm_name (ASY_SVD is out of scope)")
+        if algorithm_name not in ("FUNK_SVD", "MF_BPR", "ASY_SVD"):
+            raise ValueError("algorithm_name")
+        if algorithm_name == "ASY_SVD":
+            assert batch_size == 1, "Batch size other than 1 not supported for ASY_SVD"  # pyx:399
         X = sps.csr_matrix(URM_train, dtype=np.float32).sorted_indices()
         self.nu, self.ni = X.shape
         f = self.f = int(n_factors)
@@ -110,7 +113,8 @@ class MFOracle:
         k["data"] = np.ascontiguousarray(X.data, np.float64)
         s = self.s = MFState()
         s.n_users, s.n_items, s.f, s.batch_size = self.nu, self.ni, f, int(batch_size)
-        s.algorithm = 0 if algorithm_name == "MF_BPR" else 1
+        s.algorithm = {"MF_BPR": 0, "FUNK_SVD": 1, "ASY_SVD": 2}[algorithm_name]
+        nuf = self.ni if algorithm_name == "ASY_SVD" else self.nu  # pyx:163-166: USER_factors has one row per ITEM
         s.use_bias = int(bool(use_bias))
         s.lr, s.user_reg, s.item_reg, s.bias_reg = learning_rate, user_reg, item_reg, bias_reg
         s.positive_reg, s.negative_reg, s.quota = positive_reg, negative_reg, negative_interactions_quota
@@ -124,7 +128,7 @@ class MFOracle:
         else:
             _lib.glibc_rand_seed(C.byref(s.rng), C.c_uint(1))
         if init_factors is None:
-            k["U"] = np.random.normal(init_mean, init_std_dev, (self.nu, f)).astype(np.float64)  # pyx:177-178
+            k["U"] = np.random.normal(init_mean, init_std_dev, (nuf, f)).astype(np.float64)  # pyx:177-178
             k["V"] = np.random.normal(init_mean, init_std_dev, (self.ni, f)).astype(np.float64)
         else:
             k["U"] = np.array(init_factors[0], np.float64, copy=True)
@@ -135,12 +139,12 @@ class MFOracle:
             return _p(k[name])
 
         s.U, s.V = _p(k["U"]), _p(k["V"])
-        s.accU, s.accV = z("accU", (self.nu, f)), z("accV", (self.ni, f))
+        s.accU, s.accV = z("accU", (nuf, f)), z("accV", (self.ni, f))
         s.bu, s.bi, s.mu = z("bu", self.nu), z("bi", self.ni), z("mu", 1)
         s.accbu, s.accbi, s.accmu = z("accbu", self.nu), z("accbi", self.ni), z("accmu", 1)
         if sgd_mode != "sgd":
-            s.cU, s.cV, s.cbu, s.cbi, s.cmu = z("cU", (self.nu, f)), z("cV", (self.ni, f)), z("cbu", self.nu), z("cbi", self.ni), z("cmu", 1)
-            s.m1U, s.m2U, s.m1V, s.m2V = z("m1U", (self.nu, f)), z("m2U", (self.nu, f)), z("m1V", (self.ni, f)), z("m2V", (self.ni, f))
+            s.cU, s.cV, s.cbu, s.cbi, s.cmu = z("cU", (nuf, f)), z("cV", (self.ni, f)), z("cbu", self.nu), z("cbi", self.ni), z("cmu", 1)
+            s.m1U, s.m2U, s.m1V, s.m2V = z("m1U", (nuf, f)), z("m2U", (nuf, f)), z("m1V", (self.ni, f)), z("m2V", (self.ni, f))
             s.m1bu, s.m2bu, s.m1bi, s.m2bi = z("m1bu", self.nu), z("m2bu", self.nu), z("m1bi", self.ni), z("m2bi", self.ni)
             s.m1mu, s.m2mu = z("m1mu", 1), z("m2mu", 1)
         s.items_list, s.users_list = z("il", 2 * int(batch_size), np.int64), z("ul", int(batch_size), np.int64)
@@ -185,11 +189,12 @@ class SLIMOracle:
     def __init__(self, URM_mask, train_with_sparse_weights=False, final_model_sparse_weights=True, learning_rate=0.01,
                  li_reg=0.0, lj_reg=0.0, topK=150, symmetric=True, verbose=False, random_seed=None, sgd_mode="adam",
                  gamma=0.995, beta_1=0.9, beta_2=0.999, samples=None, record=0):
-        if train_with_sparse_weights:
-            raise ValueError("the tree-sparse S mode is out of scope (SURVEY.md 2.1)")
         X = sps.csr_matrix(URM_mask, dtype=np.float32).sorted_indices()
         self.nu, self.ni = X.shape
         self.topK = min(topK, self.ni)
+        self.tree = bool(train_with_sparse_weights)
+        if self.tree:
+            symmetric = False  # pyx:111-112
         self._keep = k = {}
         k["indptr"] = np.ascontiguousarray(X.indptr, np.int32)
         k["indices"] = np.ascontiguousarray(X.indices, np.int32)
@@ -203,6 +208,10 @@ class SLIMOracle:
         _lib.glibc_rand_seed(C.byref(s.rng), C.c_uint(int(random_seed) if random_seed is not None else 1))
         k["S"] = np.zeros((self.ni, self.ni), np.float64)
         s.S = _p(k["S"])
+        if self.tree:  # Sparse_Matrix_Tree_CSR restated as dense values + a cell-exists map (sgd_oracle.c slim_prune)
+            k["exists"] = np.zeros((self.ni, self.ni), np.uint8)
+            s.exists = _p(k["exists"])
+            s.tree_topk = int(self.topK) if self.topK else 0
         if sgd_mode != "sgd":
             for n in ("c", "m1", "m2"):
                 k[n] = np.zeros(self.ni, np.float64)
@@ -221,6 +230,18 @@ class SLIMOracle:
     def recorded(self):
         n = self.s.rec_pos
         return self._keep["ru"][:n].copy(), self._keep["ri"][:n].copy(), self._keep["rj"][:n].copy()
+
+    def get_S_tree(self):
+        """get_S of the tree mode (pyx:340-388 with train_with_sparse_weights): the diagonal cells are touched, the rows are
+        cut to their TopK IN PLACE (get_scipy_csr(TopK) replaces each row's list, pyx:762-763; zero-valued cells, the diagonal
+        among them, count towards the row length and can take a place among the TopK) and the non-zero cells that are
+        left are emitted (from_linked_list_to_python_list skips zeros, pyx:849-862)."""
+        assert self.tree
+        lib().slim_touch_diagonal(C.byref(self.s))
+        if self.topK:
+            lib().slim_prune(C.byref(self.s), C.c_long(int(self.topK)))
+        S, E = self._keep["S"], self._keep["exists"]
+        return sps.csr_matrix(np.where(E != 0, S, 0.0))
 
     def S_full(self):
         """The full item-item matrix (symmetric mode: mirrored lower triangle), diagonal as stored."""

@@ -65,6 +65,19 @@ SIGNATURES = {
     "b200_slim_get_samples": (ctypes.c_int, [c_void, c_void, c_void, c_void]),
     "b200_slim_get_S_dense": (ctypes.c_int, [c_void, c_void, c_void]),
     "b200_slim_last_epoch_ms": (ctypes.c_int, [c_void, c_float_p]),
+    "b200_slim_enable_tree": (ctypes.c_int, [c_void, ctypes.c_int]),
+    "b200_slim_tree_prune": (ctypes.c_int, [c_void, ctypes.c_int, c_void]),
+    "b200_slim_enet_device": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_float, c_void, c_void, c_void]),
+    "b200_asysvd_create": (ctypes.c_int, [ctypes.POINTER(c_void), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void, c_void, c_void,
+                                          ctypes.c_int, ctypes.c_double, ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                          ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void, c_void,
+                                          ctypes.c_int, ctypes.c_uint32]),
+    "b200_asysvd_destroy": (ctypes.c_int, [c_void]),
+    "b200_asysvd_epoch": (ctypes.c_int, [c_void, c_void]),
+    "b200_asysvd_get_samples": (ctypes.c_int, [c_void, c_void, c_void, c_void]),
+    "b200_asysvd_get_factors": (ctypes.c_int, [c_void, c_void, c_void, c_void, c_void, c_void]),
+    "b200_asysvd_last_epoch_ms": (ctypes.c_int, [c_void, c_float_p]),
     "b200_slim_create_sharded": (ctypes.c_int, [ctypes.POINTER(c_void), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void, c_void,
                                                 ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                                 ctypes.c_float, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]),

@@ -1,0 +1,325 @@
+// K2b: AsymmetricSVD epochs (Koren 2008), sm_100a.
+//
+// Replaces MatrixFactorization/Cython/MatrixFactorization_Cython_Epoch.pyx:396-578 epochIteration_Cython_ASY_SVD_SGD
+// (batch size 1, :399), with sampleMSE_Cython :881-938 and adaptive_gradient :838-876.  The model is two n_items x f
+// tables: Y (the reference's USER_factors, :163-166) and X (ITEM_factors).  A sample (u, i, r) reads the Y rows of the whole
+// profile of u (their sum / sqrt(len_u) stands in for the user), predicts r with the X row of i, and then updates EVERY Y row
+// of the profile and the X row of i, each parameter with its own adaptive state.
+//
+// The recursion is strictly sequential (sample t+1 reads rows sample t wrote: two profiles of ~150 items out of 27 K share
+// an item more often than not), so ONE CTA walks the replayed sample stream in order and spreads the len_u x f reads and
+// read-modify-writes of a sample over its 16 warps (one warp per profile row, lanes over the factors).  Roofline: L2 / HBM
+// latency per sample, 2 * len_u * f * 4 bytes read + len_u * f * 4 written (+ the adaptive state), not bandwidth.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+namespace asy {
+
+enum SgdMode { SGD = 0, ADAGRAD = 1, RMSPROP = 2, ADAM = 3 };
+constexpr int THREADS = 512;
+constexpr int WARPS = THREADS / 32;
+
+struct Params {
+  int n_users, n_items, f, use_bias, sgd_mode;
+  float lr, user_reg, item_reg, bias_reg, gamma, beta1, beta2;
+  double b1_pow, b2_pow;
+  const int* __restrict__ indptr;
+  const int* __restrict__ indices;
+  float *Y, *X, *bu, *bi, *mu;
+  float *cY, *cX, *cbu, *cbi, *cmu;            // adagrad / rmsprop cache, or adam first moment
+  float *m2Y, *m2X, *m2bu, *m2bi, *m2mu;       // adam second moment
+  const int* su; const int* si; const float* sr;
+  long long n_samples;
+  double* pow_out;
+};
+
+// pyx:838-876; c is the adagrad / rmsprop cache or adam's first moment, m2 adam's second moment
+__device__ __forceinline__ float adapt(const Params& p, float g, float* c, float* m2, float inv1, float inv2) {
+  if (p.sgd_mode == ADAGRAD) {
+    const float cc = *c + g * g;
+    *c = cc;
+    return g / (sqrtf(cc) + 1e-8f);
+  } else if (p.sgd_mode == RMSPROP) {
+    const float cc = *c * p.gamma + (1.f - p.gamma) * g * g;
+    *c = cc;
+    return g / (sqrtf(cc) + 1e-8f);
+  } else if (p.sgd_mode == ADAM) {
+    const float a = *c * p.beta1 + (1.f - p.beta1) * g;
+    const float b = *m2 * p.beta2 + (1.f - p.beta2) * g * g;
+    *c = a;
+    *m2 = b;
+    return (a * inv1) / (sqrtf(b * inv2) + 1e-8f);
+  }
+  return g;
+}
+
+// dynamic shared memory: part[WARPS][f] partial profile sums, acc[f] the profile vector, hx[f] the X row before its update
+__global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params p) {
+  extern __shared__ float sm[];
+  __shared__ float red[WARPS];
+  __shared__ float s_err;
+  const int f = p.f;
+  float* part = sm;
+  float* acc = sm + (size_t)WARPS * f;
+  float* hx = acc + f;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double b1p = p.b1_pow, b2p = p.b2_pow;
+  for (long long n = 0; n < p.n_samples; ++n) {
+    const int u = p.su[n], i = p.si[n];
+    const float r = p.sr[n];
+    const int s = p.indptr[u], e = p.indptr[u + 1];
+    // pyx:436-448: sum of the Y rows of the profile
+    for (int q = lane; q < f; q += 32) part[warp * f + q] = 0.f;
+    for (int k = s + warp; k < e; k += WARPS) {
+      const float* row = p.Y + (size_t)p.indices[k] * f;
+      for (int q = lane; q < f; q += 32) part[warp * f + q] += row[q];
+    }
+    __syncthreads();
+    const float inv_den = 1.f / sqrtf((float)(e - s));  // pyx:451-455
+    float dot = 0.f;
+    for (int q = tid; q < f; q += THREADS) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) a += part[w * f + q];
+      a *= inv_den;
+      const float h = p.X[(size_t)i * f + q];
+      acc[q] = a;
+      hx[q] = h;
+      dot += a * h;  // pyx:463-464
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if (lane == 0) red[warp] = dot;
+    __syncthreads();
+    const float inv1 = (float)(1.0 / (1.0 - b1p)), inv2 = (float)(1.0 / (1.0 - b2p));
+    if (tid == 0) {
+      float pred = p.use_bias ? p.mu[0] + p.bu[u] + p.bi[i] : 0.f;  // pyx:458-461
+      for (int w = 0; w < WARPS; ++w) pred += red[w];
+      const float err = r - pred;  // pyx:468-471 with batch_size == 1
+      s_err = err;
+      if (p.use_bias) {  // pyx:476-502: global, then item and user bias, all from the same error
+        float g = adapt(p, err - p.bias_reg * p.mu[0], p.cmu, p.m2mu, inv1, inv2);
+        p.mu[0] += p.lr * g;
+        g = adapt(p, err - p.bias_reg * p.bi[i], p.cbi ? p.cbi + i : nullptr, p.m2bi ? p.m2bi + i : nullptr, inv1, inv2);
+        const float gu = adapt(p, err - p.bias_reg * p.bu[u], p.cbu ? p.cbu + u : nullptr, p.m2bu ? p.m2bu + u : nullptr, inv1, inv2);
+        p.bi[i] += p.lr * g;
+        p.bu[u] += p.lr * gu;
+      }
+    }
+    __syncthreads();
+    const float err = s_err;
+    // pyx:505-521: every Y row of the profile (the rows are distinct items), H_i from before the X update
+    for (int k = s + warp; k < e; k += WARPS) {
+      const size_t base = (size_t)p.indices[k] * f;
+      for (int q = lane; q < f; q += 32) {
+        const float w = p.Y[base + q];
+        float g = err * hx[q] - p.user_reg * w;
+        g = adapt(p, g, p.cY ? p.cY + base + q : nullptr, p.m2Y ? p.m2Y + base + q : nullptr, inv1, inv2);
+        p.Y[base + q] = w + p.lr * g;
+      }
+    }
+    // pyx:524-539: the X row of the sampled item, with the profile vector from before the Y update
+    for (int q = tid; q < f; q += THREADS) {
+      const size_t c = (size_t)i * f + q;
+      float g = err * acc[q] - p.item_reg * hx[q];
+      g = adapt(p, g, p.cX ? p.cX + c : nullptr, p.m2X ? p.m2X + c : nullptr, inv1, inv2);
+      p.X[c] = hx[q] + p.lr * g;
+    }
+    if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:544-547
+    __syncthreads();
+  }
+  if (tid == 0) { p.pow_out[0] = b1p; p.pow_out[1] = b2p; }
+}
+
+}  // namespace asy
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::asy;
+
+struct b200_asysvd_s {
+  Params p{};
+  double quota = 0.0;
+  GlibcRandHost rng;
+  std::vector<int> h_indptr, h_indices, hs_u, hs_i;
+  std::vector<float> h_data, hs_r;
+  DevBuf<int> d_indptr, d_indices, su, si;
+  DevBuf<float> sr, Y, X, bu, bi, mu, cY, cX, cbu, cbi, cmu, m2Y, m2X, m2bu, m2bi, m2mu;
+  DevBuf<double> pow_out;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  long long n_last = 0;
+};
+
+namespace {
+void upload_doubles(DevBuf<float>& dst, const double* src, size_t n) {
+  std::vector<float> tmp(n);
+  for (size_t k = 0; k < n; ++k) tmp[k] = (float)src[k];
+  dst.alloc(n);
+  B200_CUDA(cudaMemcpy(dst.get(), tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+}
+void zeros(DevBuf<float>& dst, size_t n) {
+  dst.alloc(n);
+  B200_CUDA(cudaMemset(dst.get(), 0, n * sizeof(float)));
+}
+void download_doubles(double* dst, const float* src, size_t n) {
+  if (!dst) return;
+  std::vector<float> tmp(n);
+  B200_CUDA(cudaMemcpy(tmp.data(), src, n * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < n; ++k) dst[k] = (double)tmp[k];
+}
+}  // namespace
+
+extern "C" {
+
+int b200_asysvd_create(b200_asysvd_t* out, int64_t n_users, int64_t n_items, int64_t nnz, const int32_t* h_indptr,
+                       const int32_t* h_indices, const float* h_data, int n_factors, double negative_interactions_quota,
+                       float learning_rate, int use_bias, float user_reg, float item_reg, float bias_reg, int sgd_mode,
+                       float gamma, float beta_1, float beta_2, const double* h_profile_factors, const double* h_item_factors,
+                       int has_seed, uint32_t random_seed) {
+  if (out) *out = nullptr;
+  b200_asysvd_s* h = nullptr;
+  int rc = guarded([&] {
+    B200_REQUIRE(out && h_indptr && h_indices && h_data && h_profile_factors && h_item_factors, "b200_asysvd_create: NULL argument");
+    B200_REQUIRE(n_users > 0 && n_items > 0 && nnz > 0 && nnz < (1ll << 31) - 1, "b200_asysvd_create: bad shape");
+    B200_REQUIRE(n_factors > 0 && n_factors <= 1024, "b200_asysvd_create: n_factors must be in [1, 1024] (got %d)", n_factors);
+    B200_REQUIRE(sgd_mode >= SGD && sgd_mode <= ADAM, "b200_asysvd_create: unknown sgd_mode %d", sgd_mode);
+    h = new b200_asysvd_s();
+    Params& p = h->p;
+    const size_t f = (size_t)n_factors, nf = (size_t)n_items * f;
+    p.n_users = (int)n_users; p.n_items = (int)n_items; p.f = n_factors; p.use_bias = use_bias != 0; p.sgd_mode = sgd_mode;
+    p.lr = learning_rate; p.user_reg = user_reg; p.item_reg = item_reg; p.bias_reg = bias_reg;
+    p.gamma = gamma; p.beta1 = beta_1; p.beta2 = beta_2;
+    p.b1_pow = beta_1; p.b2_pow = beta_2;  // pyx:220-221
+    h->quota = negative_interactions_quota;
+    h->rng.seed(has_seed ? random_seed : 1u);
+    h->h_indptr.assign(h_indptr, h_indptr + n_users + 1);
+    h->h_indices.assign(h_indices, h_indices + nnz);
+    h->h_data.assign(h_data, h_data + nnz);
+    h->d_indptr.alloc((size_t)n_users + 1);
+    h->d_indices.alloc((size_t)nnz);
+    B200_CUDA(cudaMemcpy(h->d_indptr.get(), h_indptr, sizeof(int) * ((size_t)n_users + 1), cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(h->d_indices.get(), h_indices, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
+    p.indptr = h->d_indptr.get(); p.indices = h->d_indices.get();
+    upload_doubles(h->Y, h_profile_factors, nf); p.Y = h->Y.get();
+    upload_doubles(h->X, h_item_factors, nf); p.X = h->X.get();
+    zeros(h->bu, (size_t)n_users); zeros(h->bi, (size_t)n_items); zeros(h->mu, 1);  // pyx:184-186
+    p.bu = h->bu.get(); p.bi = h->bi.get(); p.mu = h->mu.get();
+    if (sgd_mode != SGD) {  // pyx:248-270
+      zeros(h->cY, nf); zeros(h->cX, nf); zeros(h->cbu, (size_t)n_users); zeros(h->cbi, (size_t)n_items); zeros(h->cmu, 1);
+      p.cY = h->cY.get(); p.cX = h->cX.get(); p.cbu = h->cbu.get(); p.cbi = h->cbi.get(); p.cmu = h->cmu.get();
+    }
+    if (sgd_mode == ADAM) {
+      zeros(h->m2Y, nf); zeros(h->m2X, nf); zeros(h->m2bu, (size_t)n_users); zeros(h->m2bi, (size_t)n_items); zeros(h->m2mu, 1);
+      p.m2Y = h->m2Y.get(); p.m2X = h->m2X.get(); p.m2bu = h->m2bu.get(); p.m2bi = h->m2bi.get(); p.m2mu = h->m2mu.get();
+    }
+    const size_t n_epoch = (size_t)nnz + 1;  // pyx:402: int(len(data) / batch_size) + 1 with batch_size == 1
+    h->su.alloc(n_epoch); h->si.alloc(n_epoch); h->sr.alloc(n_epoch);
+    p.su = h->su.get(); p.si = h->si.get(); p.sr = h->sr.get();
+    h->pow_out.alloc(2);
+    p.pow_out = h->pow_out.get();
+    B200_CUDA(cudaEventCreate(&h->ev0));
+    B200_CUDA(cudaEventCreate(&h->ev1));
+    const int smem = (int)((WARPS + 2) * f * sizeof(float));
+    B200_CUDA(cudaFuncSetAttribute(asysvd_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    *out = h;
+  });
+  if (rc != B200_OK && h) delete h;
+  return rc;
+}
+
+int b200_asysvd_destroy(b200_asysvd_t h) {
+  if (!h) return B200_OK;
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return B200_OK;
+}
+
+int b200_asysvd_epoch(b200_asysvd_t h, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr, "b200_asysvd_epoch: NULL handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    Params& p = h->p;
+    const long long n = (long long)h->h_indices.size() + 1;
+    p.n_samples = n;
+    h->hs_u.resize((size_t)n); h->hs_i.resize((size_t)n); h->hs_r.resize((size_t)n);
+    const int* indptr = h->h_indptr.data();
+    const int* indices = h->h_indices.data();
+    for (long long g = 0; g < n; ++g) {  // sampleMSE_Cython pyx:881-938, draw for draw
+      long u = 0, start = 0, len = 0;
+      while (len == 0 || len == p.n_items) {
+        u = h->rng.next() % p.n_users;
+        start = indptr[u];
+        len = indptr[u + 1] - start;
+      }
+      bool positive = true;
+      if (h->quota != 0.0) positive = (double)h->rng.next() <= h->quota * 2147483647.0;  // pyx:901
+      long item;
+      float rating = 0.f;
+      if (positive) {
+        const long idx = h->rng.next() % len;
+        item = indices[start + idx];
+        rating = h->h_data[(size_t)(start + idx)];
+      } else {
+        for (;;) {
+          item = h->rng.next() % p.n_items;
+          const int* lo = std::lower_bound(indices + start, indices + start + len, (int)item);
+          if (lo == indices + start + len || *lo != item) break;
+        }
+      }
+      h->hs_u[(size_t)g] = (int)u; h->hs_i[(size_t)g] = (int)item; h->hs_r[(size_t)g] = rating;
+    }
+    B200_CUDA(cudaMemcpyAsync(h->su.get(), h->hs_u.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(h->si.get(), h->hs_i.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(h->sr.get(), h->hs_r.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaEventRecord(h->ev0, st));
+    const size_t smem = (size_t)(WARPS + 2) * (size_t)p.f * sizeof(float);
+    asysvd_sequential_kernel<<<1, THREADS, smem, st>>>(p);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+    B200_CUDA(cudaEventRecord(h->ev1, st));
+    h->timed = true;
+    double pw[2];
+    B200_CUDA(cudaMemcpyAsync(pw, h->pow_out.get(), sizeof(pw), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));  // the host sample buffers are reused by the next epoch
+    if (p.sgd_mode == ADAM) { p.b1_pow = pw[0]; p.b2_pow = pw[1]; }
+    h->n_last = n;
+  });
+}
+
+int b200_asysvd_get_samples(b200_asysvd_t h, int32_t* u, int32_t* i, float* r) {
+  return guarded([&] {
+    B200_REQUIRE(h && u && i && r && h->n_last > 0, "b200_asysvd_get_samples: NULL argument or no epoch run yet");
+    std::copy(h->hs_u.begin(), h->hs_u.end(), u);
+    std::copy(h->hs_i.begin(), h->hs_i.end(), i);
+    std::copy(h->hs_r.begin(), h->hs_r.end(), r);
+  });
+}
+
+int b200_asysvd_get_factors(b200_asysvd_t h, double* profile_factors, double* item_factors, double* user_bias, double* item_bias,
+                            double* global_bias) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr, "b200_asysvd_get_factors: NULL handle");
+    B200_CUDA(cudaDeviceSynchronize());
+    const size_t nf = (size_t)h->p.n_items * (size_t)h->p.f;
+    download_doubles(profile_factors, h->Y.get(), nf);
+    download_doubles(item_factors, h->X.get(), nf);
+    download_doubles(user_bias, h->bu.get(), (size_t)h->p.n_users);
+    download_doubles(item_bias, h->bi.get(), (size_t)h->p.n_items);
+    download_doubles(global_bias, h->mu.get(), 1);
+  });
+}
+
+int b200_asysvd_last_epoch_ms(b200_asysvd_t h, float* ms) {
+  return guarded([&] {
+    B200_REQUIRE(h && ms && h->timed, "b200_asysvd_last_epoch_ms: no epoch run yet");
+    B200_CUDA(cudaEventSynchronize(h->ev1));
+    B200_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  });
+}
+
+}  // extern "C"

@@ -5,6 +5,8 @@
 //     (negatives survive when there are fewer than k positives)                       -> mode B200_TOPK_NONZERO
 //   * SLIM_BPR_Cython_Epoch.pyx:340-388 get_S / Triangular_Matrix.get_scipy_csr :1335-1415 -- per ROW, the k
 //     largest over ALL cells, zeros then dropped (zeros outrank negatives)            -> mode B200_TOPK_ZEROS_OUTRANK
+//   * SLIM_ElasticNet/SLIMElasticNetRecommender.py:99-107 -- per item, the min(nnz - 1, k) largest of the non-zero
+//     coefficients: a line with <= k non-zeros loses its smallest one                  -> mode 2
 // One CTA per line; the line is streamed from HBM/L2 once per radix pass (11-bit digits over the 64-bit key
 // value-bits << 32 | ~index, so ties resolve to the ascending index); survivors are written as a [lines, K] table.
 #include <algorithm>
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(THREADS) topk_lines_kernel(const float* __rest
     const int nzero = n_inner_dense - npos - nneg;
     int keep;  // how many non-zero cells survive
     if (mode == 0) keep = min(K, npos + nneg);                                   // similarityMatrixTopK
+    else if (mode == 2) keep = max(0, min(K, npos + nneg - 1));                  // SLIMElasticNetRecommender.py:103
     else keep = min(K, npos) + min(nneg, max(0, K - npos - nzero));               // zeros outrank negatives
     u64 thr = 0;
     if (keep > 0 && keep < npos + nneg) {
@@ -136,7 +139,7 @@ int b200_dense_topk_device(const float* d_matrix, int n, int K, int along_column
   return guarded([&] {
     B200_REQUIRE(d_matrix && d_idx && d_val && d_cnt, "b200_dense_topk: NULL argument");
     B200_REQUIRE(n > 0 && K > 0 && K <= n, "b200_dense_topk: need 0 < K <= n (got K=%d n=%d)", K, n);
-    B200_REQUIRE(mode == 0 || mode == 1, "b200_dense_topk: unknown mode %d", mode);
+    B200_REQUIRE(mode >= 0 && mode <= 2, "b200_dense_topk: unknown mode %d", mode);
     cudaStream_t st = (cudaStream_t)stream;
     const long long sl = along_columns ? 1 : n, si = along_columns ? n : 1;
     dtk::topk_lines_kernel<false><<<std::min(n, sm_count() * 8), dtk::THREADS, 0, st>>>(d_matrix, nullptr, nullptr, n, n, sl, si, K, mode, d_idx, d_val, d_cnt);

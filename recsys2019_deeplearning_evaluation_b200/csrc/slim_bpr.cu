@@ -2,8 +2,10 @@
 //
 // Replaces SLIM_BPR/Cython/SLIM_BPR_Cython_Epoch.pyx: epochIteration_Cython :211-335, sampleBPR_Cython :436-480,
 // adaptive_gradient :395-433 (per-ITEM scalar state shared by the positive and negative roles), symmetric storage
-// Triangular_Matrix :1272-1330, get_S :340-388 (diagonal zeroed).  The tree-sparse training mode (:509-1031) is
-// not reproduced: S is dense fp32 in HBM (C2: 55 MB, L2-resident).
+// Triangular_Matrix :1272-1330, get_S :340-388 (diagonal zeroed).  S is dense fp32 in HBM (C2: 55 MB, L2-resident).
+// The tree-sparse training mode (train_with_sparse_weights, Sparse_Matrix_Tree_CSR :579-1031) keeps its SEMANTICS on the
+// same dense array: a byte map records which cells the reference's row trees would hold, and the periodic
+// rebalance_tree(TopK) :782-802 / the in-place selection of get_scipy_csr(TopK) :762-763 is slim_tree_prune_kernel.
 //
 // Two execution modes (DESIGN.md "K3"):
 //   * sequential (the reference's semantics exactly): the recursion is batch-1 and every sample reads cells the
@@ -32,6 +34,9 @@ struct Params {
   const int* su; const int* si; const int* sj;
   long long n_samples;
   double* pow_out;
+  unsigned char* exists;   // tree mode: 1 where the reference's row tree holds a cell (add_value creates it, pyx:617-680)
+  long long first;         // first sample of this launch (tree mode runs an epoch as segments between two prunings)
+  int chain_pow;           // continue the Adam powers from pow_out (segment > 0) instead of b1_pow / b2_pow
 };
 
 __device__ __forceinline__ size_t cell(const Params& p, int a, int b) {
@@ -65,8 +70,9 @@ __global__ void __launch_bounds__(SEQ_THREADS) slim_sequential_kernel(const Para
   __shared__ float red[SEQ_THREADS / 32];
   __shared__ float s_gi, s_gj;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double b1p = p.b1_pow, b2p = p.b2_pow;
-  for (long long n = 0; n < p.n_samples; ++n) {
+  double b1p = p.chain_pow ? p.pow_out[0] : p.b1_pow, b2p = p.chain_pow ? p.pow_out[1] : p.b2_pow;
+  __syncthreads();  // pow_out is rewritten at the end
+  for (long long n = p.first; n < p.first + p.n_samples; ++n) {
     const int u = p.su[n], i = p.si[n], j = p.sj[n];
     const int s = p.indptr[u], e = p.indptr[u + 1];
     float x = 0.f;
@@ -93,8 +99,14 @@ __global__ void __launch_bounds__(SEQ_THREADS) slim_sequential_kernel(const Para
     // (it is a sampled negative), so the cell sets are disjoint and the order inside the sample is free.
     for (int k = s + tid; k < e; k += SEQ_THREADS) {
       const int sn = p.indices[k];
-      if (sn != i) { const size_t c = cell(p, i, sn); const float v = p.S[c]; p.S[c] = v + p.lr * (gi - p.li_reg * v); }
-      if (sn != j) { const size_t c = cell(p, j, sn); const float v = p.S[c]; p.S[c] = v - p.lr * (gj - p.lj_reg * v); }
+      if (sn != i) {
+        const size_t c = cell(p, i, sn); const float v = p.S[c]; p.S[c] = v + p.lr * (gi - p.li_reg * v);
+        if (p.exists) p.exists[c] = 1;
+      }
+      if (sn != j) {
+        const size_t c = cell(p, j, sn); const float v = p.S[c]; p.S[c] = v - p.lr * (gj - p.lj_reg * v);
+        if (p.exists) p.exists[c] = 1;
+      }
     }
     if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:309-312
     __syncthreads();
@@ -243,6 +255,76 @@ __global__ void slim_shard_state_kernel(const ShardParams sp, const float* __res
   }
 }
 
+// ---- tree mode: rebalance_tree(TopK) pyx:782-802 and the in-place selection inside get_scipy_csr(TopK) pyx:762-763, both
+// through topK_selection_from_list pyx:954-1031.  A row whose tree holds at least K cells keeps the K largest by value; the
+// reference sorts the column-ordered list with a stable qsort on the value, so among equal values the HIGHER columns
+// survive: key = (value bits << 32) | column, keep the K largest keys.  Cells that are dropped cease to exist and read as 0.
+// One CTA per row, 11-bit radix select over the 64-bit keys (the row is L2-resident across the six passes).
+__device__ __forceinline__ unsigned tree_orderable(float v) {
+  const unsigned b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__global__ void __launch_bounds__(256) slim_tree_prune_kernel(float* S, unsigned char* exists, int n, int K, int touch_diagonal) {
+  typedef unsigned long long u64;
+  constexpr int BINS = 2048;
+  __shared__ int hist[BINS];
+  __shared__ int s_digit, s_need, s_m;
+  const int tid = threadIdx.x;
+  for (int row = blockIdx.x; row < n; row += gridDim.x) {
+    float* Sr = S + (size_t)row * n;
+    unsigned char* Er = exists + (size_t)row * n;
+    if (tid == 0) {
+      s_m = 0;
+      if (touch_diagonal) { Sr[row] = 0.f; Er[row] = 1; }  // get_S: add_value(index, index, -get_value(index, index)), pyx:349-350
+    }
+    __syncthreads();
+    int m = 0;
+    for (int c = tid; c < n; c += 256) m += Er[c] != 0;
+    m = __reduce_add_sync(0xffffffffu, m);
+    if ((tid & 31) == 0 && m) atomicAdd(&s_m, m);
+    __syncthreads();
+    m = s_m;
+    __syncthreads();
+    if (K <= 0 || m <= K) continue;  // fewer than K cells: the list is returned as it is (pyx:977-978); exactly K: all stay
+    u64 prefix = 0, mask = 0;
+    int need = K;
+    for (int shift = 53; ; shift -= 11) {
+      const int sh = max(shift, 0);
+      const int nb = shift >= 0 ? 11 : 11 + shift;
+      for (int i = tid; i < BINS; i += 256) hist[i] = 0;
+      __syncthreads();
+      for (int c = tid; c < n; c += 256) {
+        if (Er[c]) {
+          const u64 key = (((u64)tree_orderable(Sr[c])) << 32) | (u64)(unsigned)c;
+          if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> sh) & ((1u << nb) - 1))], 1);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {  // the need-th largest digit
+        int cum = 0;
+        for (int b = (1 << nb) - 1; b >= 0; --b) {
+          const int cnt = hist[b];
+          if (cum + cnt >= need) { s_digit = b; s_need = need - cum; break; }
+          cum += cnt;
+        }
+      }
+      __syncthreads();
+      prefix |= ((u64)s_digit) << sh;
+      mask |= ((u64)((1u << nb) - 1)) << sh;
+      need = s_need;
+      __syncthreads();
+      if (shift <= 0) break;
+    }
+    for (int c = tid; c < n; c += 256) {
+      if (Er[c]) {
+        const u64 key = (((u64)tree_orderable(Sr[c])) << 32) | (u64)(unsigned)c;
+        if (key < prefix) { Sr[c] = 0.f; Er[c] = 0; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // expands the stored matrix into the full n x n view get_S returns before its top-K (diagonal zeroed, pyx:345-355;
 // symmetric mode mirrors the lower triangle, pyx:1363-1372)
 __global__ void slim_full_kernel(const float* __restrict__ S, int n, int symmetric, float* out) {
@@ -300,31 +382,7 @@ __global__ void slim_sample_kernel(const int* __restrict__ indptr, const int* __
   su[g] = u; si[g] = item; sj[g] = neg;
 }
 
-struct GlibcRand {
-  int32_t r[31];
-  int f = 3, b = 0;
-  void seed(unsigned s) {
-    int32_t word = s == 0 ? 1 : (int32_t)s;
-    r[0] = word;
-    for (int i = 1; i < 31; ++i) {
-      const long hi = word / 127773, lo = word % 127773;
-      long w = 16807 * lo - 2836 * hi;
-      if (w < 0) w += 2147483647;
-      word = (int32_t)w;
-      r[i] = word;
-    }
-    f = 3; b = 0;
-    for (int i = 0; i < 310; ++i) raw();
-  }
-  uint32_t raw() {
-    const uint32_t v = (uint32_t)r[f] + (uint32_t)r[b];
-    r[f] = (int32_t)v;
-    f = (f + 1) % 31;
-    b = (b + 1) % 31;
-    return v;
-  }
-  int next() { return (int)(raw() >> 1); }
-};
+using GlibcRand = GlibcRandHost;  // common.cuh
 
 }  // namespace slim
 }  // namespace b200
@@ -345,6 +403,9 @@ struct b200_slim_s {
   bool timed = false;
   int shard_lo = 0, shard_hi = 0;  // column-sharded handle (b200_slim_create_sharded): S is [n_items, shard_hi - shard_lo]
   long long drawn_epoch = -1;      // the epoch whose sample stream is in su / si / sj
+  DevBuf<unsigned char> exists;    // tree mode (b200_slim_enable_tree)
+  bool tree = false;
+  int tree_topk = 0;
 };
 
 extern "C" {
@@ -546,6 +607,27 @@ int b200_slim_epoch(b200_slim_t h, void* stream) {
     if (h->hogwild) {
       slim_hogwild_kernel<<<sm_count() * 8, 256, 0, st>>>(p);
       if (p.sgd_mode == ADAM) { p.b1_pow *= pow((double)p.beta1, (double)n); p.b2_pow *= pow((double)p.beta2, (double)n); }
+    } else if (h->tree) {
+      // pyx:318-319: after sample n (n != 0) with `n % (n_users / 5) == 0` -- a float modulo under language_level=3 -- the rows
+      // are cut back to their TopK; the epoch runs as the segments between those points
+      long long first = 0;
+      int launches = 0;
+      const double period = (double)p.n_users / 5.0;
+      for (long long g = 1; g <= n; ++g) {
+        const bool prune_here = g < n && fmod((double)g, period) == 0.0;
+        if (!prune_here && g != n) continue;
+        const long long last = g < n ? g : n - 1;  // the segment ends with sample `last`
+        Params q = p;
+        q.first = first; q.n_samples = last - first + 1; q.chain_pow = first > 0;
+        if (q.n_samples > 0) { slim_sequential_kernel<<<1, SEQ_THREADS, 0, st>>>(q); ++launches; }
+        if (prune_here && h->tree_topk > 0) {
+          slim_tree_prune_kernel<<<std::min(p.n_items, sm_count() * 8), 256, 0, st>>>(p.S, p.exists, p.n_items, h->tree_topk, 0);
+          ++launches;
+        }
+        first = last + 1;
+        if (g == n) break;
+      }
+      if (launches > 1) count_launch(launches - 1);  // the last one is counted below
     } else {
       slim_sequential_kernel<<<1, SEQ_THREADS, 0, st>>>(p);
     }
@@ -562,6 +644,33 @@ int b200_slim_epoch(b200_slim_t h, void* stream) {
       B200_CUDA(cudaStreamSynchronize(st));
     }
     h->epoch += 1;
+  });
+}
+
+int b200_slim_enable_tree(b200_slim_t h, int topK) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr, "b200_slim_enable_tree: NULL handle");
+    B200_REQUIRE(h->shard_hi == 0 && !h->hogwild && !h->p.symmetric,
+                 "b200_slim_enable_tree: the tree mode is sequential, non-symmetric (pyx:111-112) and single-GPU");
+    B200_REQUIRE(h->epoch == 0 && !h->tree, "b200_slim_enable_tree: call once, before the first epoch");
+    B200_REQUIRE(topK >= 0, "b200_slim_enable_tree: topK must be >= 0 (0 = False: rows are never cut)");
+    const size_t cells = (size_t)h->p.n_items * (size_t)h->p.n_items;
+    h->exists.alloc(cells);
+    B200_CUDA(cudaMemset(h->exists.get(), 0, cells));
+    h->p.exists = h->exists.get();
+    h->tree = true;
+    h->tree_topk = std::min(topK, h->p.n_items);
+  });
+}
+
+int b200_slim_tree_prune(b200_slim_t h, int touch_diagonal, void* stream) {
+  return guarded([&] {
+    B200_REQUIRE(h != nullptr && h->tree, "b200_slim_tree_prune: not a tree-mode handle");
+    const int n = h->p.n_items;
+    slim_tree_prune_kernel<<<std::min(n, sm_count() * 8), 256, 0, (cudaStream_t)stream>>>(h->p.S, h->p.exists, n, h->tree_topk,
+                                                                                           touch_diagonal != 0);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
   });
 }
 

@@ -408,8 +408,6 @@ class _MatrixFactorization_Cython(BaseMatrixFactorizationRecommender, Incrementa
         assert 0.0 <= negative_interactions_quota < 1.0, "{}: negative_interactions_quota must be a float value >=0 and < 1.0, provided was '{}'".format(
             self.RECOMMENDER_NAME, negative_interactions_quota)  # MatrixFactorization_Cython.py:49-50
         self.negative_interactions_quota = negative_interactions_quota
-        if self.algorithm_name not in ("FUNK_SVD", "MF_BPR"):
-            raise NotImplementedError("ASY_SVD is not on the CUDA path")
         URM_train_positive = self.URM_train
         if self.algorithm_name == "MF_BPR":  # :63-72
             URM_train_positive = self.URM_train.copy()
@@ -469,17 +467,81 @@ class MatrixFactorization_FunkSVD_Cython(_MatrixFactorization_Cython):
         super(MatrixFactorization_FunkSVD_Cython, self).__init__(*pos_args, algorithm_name="FUNK_SVD", **key_args)
 
 
+class MatrixFactorization_AsySVD_Cython(_MatrixFactorization_Cython):
+    """MatrixFactorization_Cython.py:194-275: AsymmetricSVD.  The trainer holds two item-side tables (Y = its USER_factors, X =
+    its ITEM_factors); the user factors used for scoring are estimated from the profiles, URM . Y / sqrt(profile length)."""
+    RECOMMENDER_NAME = "MatrixFactorization_AsySVD_Cython_Recommender"
+
+    def __init__(self, *pos_args, **key_args):
+        super(MatrixFactorization_AsySVD_Cython, self).__init__(*pos_args, algorithm_name="ASY_SVD", **key_args)
+
+    def fit(self, **key_args):
+        if "batch_size" in key_args and key_args["batch_size"] > 1:  # :217-220
+            print("{}: batch_size not supported for this recommender, setting to default value 1.".format(self.RECOMMENDER_NAME))
+        key_args["batch_size"] = 1
+        super(MatrixFactorization_AsySVD_Cython, self).fit(**key_args)
+
+    def _prepare_model_for_validation(self):  # :226-242
+        self.ITEM_factors_Y = self.cythonEpoch.get_USER_factors()
+        self.USER_factors = self._estimate_user_factors(self.ITEM_factors_Y)
+        self.ITEM_factors = self.cythonEpoch.get_ITEM_factors()
+        if self.use_bias:
+            self.USER_bias = self.cythonEpoch.get_USER_bias()
+            self.ITEM_bias = self.cythonEpoch.get_ITEM_bias()
+            self.GLOBAL_bias = self.cythonEpoch.get_GLOBAL_bias()
+
+    def _update_best_model(self):  # :245-253
+        super(MatrixFactorization_AsySVD_Cython, self)._update_best_model()
+        self.ITEM_factors_Y_best = self.ITEM_factors_Y.copy()
+
+    def _estimate_user_factors(self, ITEM_factors_Y):  # :256-277: the RATINGS weigh the sum here (training sums unweighted rows)
+        profile_length_sqrt = np.sqrt(np.ediff1d(self.URM_train.indptr))
+        USER_factors = self.URM_train.dot(ITEM_factors_Y)
+        nz = profile_length_sqrt > 0
+        USER_factors[nz] /= profile_length_sqrt[nz][:, None]
+        return USER_factors
+
+
+class SLIMElasticNetRecommender(BaseItemSimilarityMatrixRecommender):
+    """SLIM_ElasticNet/SLIMElasticNetRecommender.py:20-148.  The reference fits one scikit-learn ElasticNet per item on the URM
+    with that item's column zeroed (recomputing X^T X each time); here the Gram matrix is formed once on the device (the dense
+    mode of the similarity kernel, as for EASE_R) and csrc/slim_enet.cu runs the Gram-matrix coordinate descent of all items,
+    one CTA per item, with sklearn's stopping rule in cyclic coordinate order (the reference's order is random and unseeded:
+    its own runs differ from each other by as much as this differs from them, tests/test_oracle_elasticnet.py)."""
+    RECOMMENDER_NAME = "SLIMElasticNetRecommender"
+
+    def fit(self, l1_ratio=0.1, alpha=1.0, positive_only=True, topK=100, max_iter=100, tol=1e-4):
+        import torch
+        assert l1_ratio >= 0 and l1_ratio <= 1, "{}: l1_ratio must be between 0 and 1, provided value was {}".format(
+            self.RECOMMENDER_NAME, l1_ratio)  # :43
+        self.l1_ratio, self.positive_only, self.topK = l1_ratio, positive_only, topK
+        n = self.n_items
+        G = EASE_R_Recommender._gram_device(self)
+        X = self.URM_train
+        diag = torch.from_numpy(np.asarray(X.multiply(X).sum(axis=0), dtype=np.float32).ravel()).to(G.device)
+        coefT = torch.empty((n, n), dtype=torch.float32, device=G.device)
+        self._n_iter = torch.empty((n,), dtype=torch.int32, device=G.device)
+        _lib.check(self._lib.b200_slim_enet_device(G.data_ptr(), diag.data_ptr(), n, self.n_users, float(l1_ratio), float(alpha),
+                                                   int(bool(positive_only)), int(max_iter), float(tol), coefT.data_ptr(),
+                                                   self._n_iter.data_ptr(), _stream()))
+        del G
+        from .slim_bpr_epoch import dense_topk_to_sparse
+        # :99-107: per item the min(nnz - 1, topK) largest non-zero coefficients; line j of coefT is the model of item j, i.e.
+        # column j of W_sparse (:119-121)
+        T = dense_topk_to_sparse(coefT, n, min(int(topK), n), along_columns=False, mode=2)
+        self.W_sparse = sps.csr_matrix(T.T, dtype=np.float32)
+
+
 class SLIM_BPR_Cython(BaseItemSimilarityMatrixRecommender, Incremental_Training_Early_Stopping):
-    """SLIM_BPR/Cython/SLIM_BPR_Cython.py:48-183 with S dense on the device (no RAM-based mode selection)."""
+    """SLIM_BPR/Cython/SLIM_BPR_Cython.py:48-183 with S dense on the device.  `train_with_sparse_weights=None` (the reference's
+    RAM-based auto selection, :85-103) resolves to the dense mode; True runs the tree mode's semantics (slim_bpr_epoch.py)."""
     RECOMMENDER_NAME = "SLIM_BPR_Recommender"
 
     def fit(self, epochs=300, positive_threshold_BPR=None, train_with_sparse_weights=None, symmetric=True, random_seed=None,
             lambda_i=0.0, lambda_j=0.0, learning_rate=1e-4, topK=200, sgd_mode="adagrad", gamma=0.995, beta_1=0.9,
             beta_2=0.999, sampler="glibc", hogwild=False, **earlystopping_kwargs):
         from .slim_bpr_epoch import SLIM_BPR_Cython_Epoch, similarityMatrixTopK
-        if train_with_sparse_weights:
-            raise NotImplementedError("train_with_sparse_weights=True is not on the CUDA path")
-        self.symmetric, self.train_with_sparse_weights = symmetric, False
+        self.symmetric, self.train_with_sparse_weights = symmetric, bool(train_with_sparse_weights)
         URM_train_positive = self.URM_train.copy()
         if positive_threshold_BPR is not None:  # SLIM_BPR_Cython.py:112-116
             URM_train_positive.data = URM_train_positive.data >= positive_threshold_BPR
@@ -488,7 +550,8 @@ class SLIM_BPR_Cython(BaseItemSimilarityMatrixRecommender, Incremental_Training_
         if topK is not False and topK < 1:  # :138-140
             raise ValueError("TopK not valid. Acceptable values are either False or a positive integer value. Provided value was '{}'".format(topK))
         self.topK, self._topk_fn = topK, similarityMatrixTopK
-        self.cythonEpoch = SLIM_BPR_Cython_Epoch(URM_train_positive, train_with_sparse_weights=False, final_model_sparse_weights=True,
+        self.cythonEpoch = SLIM_BPR_Cython_Epoch(URM_train_positive, train_with_sparse_weights=self.train_with_sparse_weights,
+                                                 final_model_sparse_weights=True,
                                                  topK=topK, learning_rate=learning_rate, li_reg=lambda_i, lj_reg=lambda_j,
                                                  symmetric=symmetric, sgd_mode=sgd_mode, verbose=self.verbose, random_seed=random_seed,
                                                  gamma=gamma, beta_1=beta_1, beta_2=beta_2, sampler=sampler, hogwild=hogwild)
@@ -510,7 +573,7 @@ class SLIM_BPR_Cython(BaseItemSimilarityMatrixRecommender, Incremental_Training_
     def get_S_incremental_and_set_W(self):  # :174-183: dense training applies a COLUMN top-K on top of get_S
         self.S_incremental = self.cythonEpoch.get_S()
         W = self.S_incremental
-        if self.topK is not False:
+        if self.topK is not False and not self.train_with_sparse_weights:  # :178-179: the tree mode keeps get_S's row top-K
             from .graph import sparse_column_topk
             W = sparse_column_topk(sps.csr_matrix(W, dtype=np.float32), self.topK)
         self.W_sparse = sps.csr_matrix(W, dtype=np.float32)

@@ -2,8 +2,10 @@
 equivalent of Base/Recommender_utils.py:55-122 `similarityMatrixTopK` for dense device matrices.
 
 Same constructor signature as pyx:88-94, `epochIteration_Cython()`, `get_S()`, `_dealloc()`.  Extra keywords:
-sampler="glibc"|"philox", hogwild=False (see mf_epoch.py).  `train_with_sparse_weights=True` (the PyMem tree,
-pyx:509-1031) is not provided: S is dense fp32 in HBM, optionally symmetric (lower-triangular addressing)."""
+sampler="glibc"|"philox", hogwild=False (see mf_epoch.py).  S is dense fp32 in HBM, optionally symmetric (lower-triangular
+addressing).  `train_with_sparse_weights=True` (Sparse_Matrix_Tree_CSR, pyx:579-1031) keeps the SEMANTICS of the tree mode on
+the dense array -- which cells exist, the periodic rebalance_tree(TopK) during the epoch (pyx:318-319), the in-place top-K
+of get_S (pyx:762-763) -- not its memory footprint (for catalogues whose dense S does not fit: dist.ShardedSLIM_BPR)."""
 import ctypes
 
 import numpy as np
@@ -54,8 +56,6 @@ class SLIM_BPR_Cython_Epoch:
                  gamma=0.995, beta_1=0.9, beta_2=0.999, sampler="glibc", hogwild=False):
         self._h = ctypes.c_void_p()
         self._lib = _lib.load()
-        if train_with_sparse_weights:
-            raise NotImplementedError("train_with_sparse_weights=True (Sparse_Matrix_Tree_CSR) is not on the CUDA path")
         if sgd_mode not in _MODE:
             raise ValueError("SLIM_BPR_Cython_Epoch: sgd_mode '{}' not recognized".format(sgd_mode))
         X = sps.csr_matrix(URM_mask, dtype=np.float32)
@@ -63,6 +63,11 @@ class SLIM_BPR_Cython_Epoch:
             X = X.sorted_indices()
         self.n_users, self.n_items = X.shape
         self.topK = min(topK, self.n_items) if topK is not False else False  # pyx:105
+        self.train_with_sparse_weights = bool(train_with_sparse_weights)
+        if self.train_with_sparse_weights:
+            symmetric = False  # pyx:111-112
+            if hogwild:
+                raise ValueError("SLIM_BPR_Cython_Epoch: train_with_sparse_weights is a sequential mode (hogwild=False)")
         self.symmetric = bool(symmetric)
         self.final_model_sparse_weights = final_model_sparse_weights
         indptr = np.ascontiguousarray(X.indptr, np.int32)
@@ -72,6 +77,8 @@ class SLIM_BPR_Cython_Epoch:
             float(li_reg), float(lj_reg), int(self.symmetric), _MODE[sgd_mode], float(gamma), float(beta_1), float(beta_2),
             int(random_seed is not None), int(random_seed) & 0xFFFFFFFF if random_seed is not None else 0,
             _SAMPLER[sampler], int(bool(hogwild))))
+        if self.train_with_sparse_weights:
+            _lib.check(self._lib.b200_slim_enable_tree(self._h, int(self.topK) if self.topK else 0))
 
     def epochIteration_Cython(self):
         import torch
@@ -99,6 +106,12 @@ class SLIM_BPR_Cython_Epoch:
         import torch
         n = self.n_items
         d = torch.empty((n, n), dtype=torch.float32, device="cuda")
+        if self.train_with_sparse_weights:
+            # pyx:349-350 touches the diagonal cells, get_scipy_csr(TopK) (pyx:737-778) cuts every row that holds >= TopK cells
+            # IN PLACE and emits the non-zero cells that are left; topK=False emits them all
+            _lib.check(self._lib.b200_slim_tree_prune(self._h, 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            _lib.check(self._lib.b200_slim_get_S_dense(self._h, None, d.data_ptr()))
+            return sps.csr_matrix(d.cpu().numpy().astype(np.float64))
         _lib.check(self._lib.b200_slim_get_S_dense(self._h, None, d.data_ptr()))
         if self.topK is False:
             if self.symmetric or self.final_model_sparse_weights:
