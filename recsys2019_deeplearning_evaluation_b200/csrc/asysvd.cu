@@ -19,8 +19,9 @@ namespace b200 {
 namespace asy {
 
 enum SgdMode { SGD = 0, ADAGRAD = 1, RMSPROP = 2, ADAM = 3 };
-constexpr int THREADS = 512;
+constexpr int THREADS = 1024;
 constexpr int WARPS = THREADS / 32;
+constexpr int ROWS = 4;  // profile rows a warp keeps in flight
 
 struct Params {
   int n_users, n_items, f, use_bias, sgd_mode;
@@ -36,26 +37,34 @@ struct Params {
   double* pow_out;
 };
 
-// pyx:838-876; c is the adagrad / rmsprop cache or adam's first moment, m2 adam's second moment
-__device__ __forceinline__ float adapt(const Params& p, float g, float* c, float* m2, float inv1, float inv2) {
+// pyx:838-876 on register copies of the state; c is the adagrad / rmsprop cache or adam's first moment, m2 adam's second moment
+__device__ __forceinline__ float adapt(const Params& p, float g, float& c, float& m2, float inv1, float inv2) {
   if (p.sgd_mode == ADAGRAD) {
-    const float cc = *c + g * g;
-    *c = cc;
-    return g / (sqrtf(cc) + 1e-8f);
+    c += g * g;
+    return g / (sqrtf(c) + 1e-8f);
   } else if (p.sgd_mode == RMSPROP) {
-    const float cc = *c * p.gamma + (1.f - p.gamma) * g * g;
-    *c = cc;
-    return g / (sqrtf(cc) + 1e-8f);
+    c = c * p.gamma + (1.f - p.gamma) * g * g;
+    return g / (sqrtf(c) + 1e-8f);
   } else if (p.sgd_mode == ADAM) {
-    const float a = *c * p.beta1 + (1.f - p.beta1) * g;
-    const float b = *m2 * p.beta2 + (1.f - p.beta2) * g * g;
-    *c = a;
-    *m2 = b;
-    return (a * inv1) / (sqrtf(b * inv2) + 1e-8f);
+    c = c * p.beta1 + (1.f - p.beta1) * g;
+    m2 = m2 * p.beta2 + (1.f - p.beta2) * g * g;
+    return (c * inv1) / (sqrtf(m2 * inv2) + 1e-8f);
   }
   return g;
 }
+// the same on state that lives in memory (nullptr in the modes that have none)
+__device__ __forceinline__ float adapt_at(const Params& p, float g, float* c, float* m2, float inv1, float inv2) {
+  float cv = c ? *c : 0.f, mv = m2 ? *m2 : 0.f;
+  const float r = adapt(p, g, cv, mv, inv1, inv2);
+  if (c) *c = cv;
+  if (m2) *m2 = mv;
+  return r;
+}
 
+// One CTA, samples strictly in order.  Per sample: (1) every warp sums the Y rows of its share of the profile, ROWS rows in
+// flight; (2) the partial sums are added across the warps, the X row of the item is read, the prediction is reduced;
+// (3) thread 0 forms the error and steps the biases; (4) every warp updates its Y rows (ROWS rows and their adaptive state in
+// flight), (5) the X row.  The next sample's (user, item, rating, profile bounds) are fetched while the current one runs.
 // dynamic shared memory: part[WARPS][f] partial profile sums, acc[f] the profile vector, hx[f] the X row before its update
 __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params p) {
   extern __shared__ float sm[];
@@ -67,22 +76,36 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
   float* hx = acc + f;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double b1p = p.b1_pow, b2p = p.b2_pow;
+  int u = 0, i = 0, s = 0, e = 0;
+  float r = 0.f;
+  if (p.n_samples > 0) { u = p.su[0]; i = p.si[0]; r = p.sr[0]; s = p.indptr[u]; e = p.indptr[u + 1]; }
   for (long long n = 0; n < p.n_samples; ++n) {
-    const int u = p.su[n], i = p.si[n];
-    const float r = p.sr[n];
-    const int s = p.indptr[u], e = p.indptr[u + 1];
-    // pyx:436-448: sum of the Y rows of the profile
+    int nu = 0, ni = 0;
+    float nr = 0.f;
+    if (n + 1 < p.n_samples) { nu = p.su[n + 1]; ni = p.si[n + 1]; nr = p.sr[n + 1]; }
+    float b_mu = 0.f, b_u = 0.f, b_i = 0.f;
+    if (tid == 0 && p.use_bias) { b_mu = p.mu[0]; b_u = p.bu[u]; b_i = p.bi[i]; }  // in flight during the gather
+    // (1) pyx:436-448: sum of the Y rows of the profile
     for (int q = lane; q < f; q += 32) part[warp * f + q] = 0.f;
-    for (int k = s + warp; k < e; k += WARPS) {
-      const float* row = p.Y + (size_t)p.indices[k] * f;
-      for (int q = lane; q < f; q += 32) part[warp * f + q] += row[q];
+    for (int k = s + warp; k < e; k += ROWS * WARPS) {
+      int it[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) it[j] = k + j * WARPS < e ? p.indices[k + j * WARPS] : -1;
+      for (int q = lane; q < f; q += 32) {
+        float v[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) v[j] = it[j] >= 0 ? p.Y[(size_t)it[j] * f + q] : 0.f;
+        part[warp * f + q] += (v[0] + v[1]) + (v[2] + v[3]);
+      }
     }
+    const int ns = p.indptr[nu], ne = p.indptr[nu + 1];  // next sample's profile bounds (row 0 past the end: harmless)
     __syncthreads();
+    // (2)
     const float inv_den = 1.f / sqrtf((float)(e - s));  // pyx:451-455
     float dot = 0.f;
     for (int q = tid; q < f; q += THREADS) {
       float a = 0.f;
-#pragma unroll
+#pragma unroll 8
       for (int w = 0; w < WARPS; ++w) a += part[w * f + q];
       a *= inv_den;
       const float h = p.X[(size_t)i * f + q];
@@ -95,40 +118,61 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
     if (lane == 0) red[warp] = dot;
     __syncthreads();
     const float inv1 = (float)(1.0 / (1.0 - b1p)), inv2 = (float)(1.0 / (1.0 - b2p));
+    // (3)
     if (tid == 0) {
-      float pred = p.use_bias ? p.mu[0] + p.bu[u] + p.bi[i] : 0.f;  // pyx:458-461
+      float pred = p.use_bias ? b_mu + b_u + b_i : 0.f;  // pyx:458-461
       for (int w = 0; w < WARPS; ++w) pred += red[w];
       const float err = r - pred;  // pyx:468-471 with batch_size == 1
       s_err = err;
       if (p.use_bias) {  // pyx:476-502: global, then item and user bias, all from the same error
-        float g = adapt(p, err - p.bias_reg * p.mu[0], p.cmu, p.m2mu, inv1, inv2);
-        p.mu[0] += p.lr * g;
-        g = adapt(p, err - p.bias_reg * p.bi[i], p.cbi ? p.cbi + i : nullptr, p.m2bi ? p.m2bi + i : nullptr, inv1, inv2);
-        const float gu = adapt(p, err - p.bias_reg * p.bu[u], p.cbu ? p.cbu + u : nullptr, p.m2bu ? p.m2bu + u : nullptr, inv1, inv2);
-        p.bi[i] += p.lr * g;
-        p.bu[u] += p.lr * gu;
+        const float gm = adapt_at(p, err - p.bias_reg * b_mu, p.cmu, p.m2mu, inv1, inv2);
+        const float gi = adapt_at(p, err - p.bias_reg * b_i, p.cbi ? p.cbi + i : nullptr, p.m2bi ? p.m2bi + i : nullptr, inv1, inv2);
+        const float gu = adapt_at(p, err - p.bias_reg * b_u, p.cbu ? p.cbu + u : nullptr, p.m2bu ? p.m2bu + u : nullptr, inv1, inv2);
+        p.mu[0] = b_mu + p.lr * gm;
+        p.bi[i] = b_i + p.lr * gi;
+        p.bu[u] = b_u + p.lr * gu;
       }
     }
     __syncthreads();
     const float err = s_err;
-    // pyx:505-521: every Y row of the profile (the rows are distinct items), H_i from before the X update
-    for (int k = s + warp; k < e; k += WARPS) {
-      const size_t base = (size_t)p.indices[k] * f;
+    // (4) pyx:505-521: every Y row of the profile (the rows are distinct items), H_i from before the X update
+    for (int k = s + warp; k < e; k += ROWS * WARPS) {
+      size_t base[ROWS];
+      bool on[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) {
+        on[j] = k + j * WARPS < e;
+        base[j] = on[j] ? (size_t)p.indices[k + j * WARPS] * f : 0;
+      }
       for (int q = lane; q < f; q += 32) {
-        const float w = p.Y[base + q];
-        float g = err * hx[q] - p.user_reg * w;
-        g = adapt(p, g, p.cY ? p.cY + base + q : nullptr, p.m2Y ? p.m2Y + base + q : nullptr, inv1, inv2);
-        p.Y[base + q] = w + p.lr * g;
+        float w[ROWS], c[ROWS], m2[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+          w[j] = on[j] ? p.Y[base[j] + q] : 0.f;
+          c[j] = on[j] && p.cY ? p.cY[base[j] + q] : 0.f;
+          m2[j] = on[j] && p.m2Y ? p.m2Y[base[j] + q] : 0.f;
+        }
+        const float h = hx[q];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+          if (!on[j]) continue;
+          float g = err * h - p.user_reg * w[j];
+          g = adapt(p, g, c[j], m2[j], inv1, inv2);
+          p.Y[base[j] + q] = w[j] + p.lr * g;
+          if (p.cY) p.cY[base[j] + q] = c[j];
+          if (p.m2Y) p.m2Y[base[j] + q] = m2[j];
+        }
       }
     }
-    // pyx:524-539: the X row of the sampled item, with the profile vector from before the Y update
+    // (5) pyx:524-539: the X row of the sampled item, with the profile vector from before the Y update
     for (int q = tid; q < f; q += THREADS) {
       const size_t c = (size_t)i * f + q;
       float g = err * acc[q] - p.item_reg * hx[q];
-      g = adapt(p, g, p.cX ? p.cX + c : nullptr, p.m2X ? p.m2X + c : nullptr, inv1, inv2);
+      g = adapt_at(p, g, p.cX ? p.cX + c : nullptr, p.m2X ? p.m2X + c : nullptr, inv1, inv2);
       p.X[c] = hx[q] + p.lr * g;
     }
     if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:544-547
+    u = nu; i = ni; r = nr; s = ns; e = ne;
     __syncthreads();
   }
   if (tid == 0) { p.pow_out[0] = b1p; p.pow_out[1] = b2p; }
@@ -223,8 +267,6 @@ int b200_asysvd_create(b200_asysvd_t* out, int64_t n_users, int64_t n_items, int
     p.pow_out = h->pow_out.get();
     B200_CUDA(cudaEventCreate(&h->ev0));
     B200_CUDA(cudaEventCreate(&h->ev1));
-    const int smem = (int)((WARPS + 2) * f * sizeof(float));
-    B200_CUDA(cudaFuncSetAttribute(asysvd_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     *out = h;
   });
   if (rc != B200_OK && h) delete h;
@@ -278,6 +320,8 @@ int b200_asysvd_epoch(b200_asysvd_t h, void* stream) {
     B200_CUDA(cudaMemcpyAsync(h->sr.get(), h->hs_r.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaEventRecord(h->ev0, st));
     const size_t smem = (size_t)(WARPS + 2) * (size_t)p.f * sizeof(float);
+    // per launch: the attribute belongs to the function, and handles with other factor counts share it
+    B200_CUDA(cudaFuncSetAttribute(asysvd_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     asysvd_sequential_kernel<<<1, THREADS, smem, st>>>(p);
     B200_CUDA(cudaGetLastError());
     count_launch();

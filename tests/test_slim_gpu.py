@@ -112,10 +112,14 @@ def test_philox_stream_and_hogwild():
     assert cos > 0.98 and abs(np.linalg.norm(H) / np.linalg.norm(R) - 1) < 0.1, cos
 
 
-def test_sparse_tree_mode_is_refused():
+def test_sparse_tree_mode_forces_the_full_matrix():
+    """train_with_sparse_weights=True (tests/test_next_rows_gpu.py has its parity tests): symmetric is switched off like
+    pyx:111-112 does, and the throughput mode is refused."""
     X = synth_urm(50, 20, 0.2)
-    with pytest.raises(NotImplementedError):
-        _cls()(X, train_with_sparse_weights=True)
+    g = _cls()(X, train_with_sparse_weights=True, symmetric=True, random_seed=1)
+    assert g.symmetric is False and g.train_with_sparse_weights is True
+    with pytest.raises(ValueError):
+        _cls()(X, train_with_sparse_weights=True, hogwild=True, sampler="philox", random_seed=1)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -27,6 +27,19 @@ X2 = synth_config("C2", values="ratings")
 nu, ni = X2.shape
 emit(bench="URM C2", shape=list(X2.shape), nnz=int(X2.nnz))
 
+only_asy = "--only-asy" in sys.argv
+if only_asy:
+    for mode in ("sgd", "adagrad", "adam"):
+        for f in (32, 128):
+            g = MatrixFactorization_Cython_Epoch(X2, n_factors=f, algorithm_name="ASY_SVD", batch_size=1, learning_rate=1e-3, random_seed=42,
+                                                 sgd_mode=mode, use_bias=True, negative_interactions_quota=0.2, user_reg=1e-3, item_reg=1e-3)
+            g.epochIteration_Cython(); sync()
+            ms = g.last_epoch_ms()
+            emit(bench="AsySVD epoch C2 f=%d %s" % (f, mode), samples=int(X2.nnz + 1), kernel_s=ms * 1e-3, samples_per_s=(X2.nnz + 1) / (ms * 1e-3),
+                 us_per_sample=ms * 1e3 / (X2.nnz + 1), mean_profile=float(X2.nnz / nu))
+            g._dealloc()
+    sys.exit(0)
+
 # ---- SLIM ElasticNet, C2 (the MovieLens-1M shape the reference's own sweep runs it on)
 kw = dict(l1_ratio=0.1, alpha=1e-3, positive_only=True, topK=100)
 rec = R.SLIMElasticNetRecommender(X2, verbose=False)
