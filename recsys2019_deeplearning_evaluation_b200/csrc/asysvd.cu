@@ -61,12 +61,23 @@ __device__ __forceinline__ float adapt_at(const Params& p, float g, float* c, fl
   return r;
 }
 
-// One CTA, samples strictly in order.  Per sample: (1) every warp sums the Y rows of its share of the profile, ROWS rows in
-// flight; (2) the partial sums are added across the warps, the X row of the item is read, the prediction is reduced;
-// (3) thread 0 forms the error and steps the biases; (4) every warp updates its Y rows (ROWS rows and their adaptive state in
-// flight), (5) the X row.  The next sample's (user, item, rating, profile bounds) are fetched while the current one runs.
-// dynamic shared memory: part[WARPS][f] partial profile sums, acc[f] the profile vector, hx[f] the X row before its update
-__global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params p) {
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One CTA, samples strictly in order.  Per sample:
+//  (1) every warp sums the Y rows of its share of the profile (row r of the profile belongs to warp r % WARPS), ROWS rows in
+//      flight; the rows are kept in a shared-memory stash and their adaptive state is pulled next to them with cp.async, so
+//      that step (4) reads nothing from L2 (rows beyond the stash capacity are read again);
+//  (2) the partial sums are added across the warps, the X row of the item is read, the prediction is reduced;
+//  (3) thread 0 forms the error and steps the biases;
+//  (4) every warp updates its Y rows and their state, (5) the X row.
+// The item ids of a warp's rows sit in its lanes (lane t holds row warp + WARPS * t); the next sample's (user, item, rating),
+// profile bounds and ids are fetched while the current one runs.
+// dynamic shared memory: part[WARPS][f] partial sums, acc[f] the profile vector, hx[f] the X row before its update, then the
+// stash: cap rows of Y [, of the first state array [, of the second]].
+__global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params p, const int cap) {
   extern __shared__ float sm[];
   __shared__ float red[WARPS];
   __shared__ float s_err;
@@ -74,31 +85,58 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
   float* part = sm;
   float* acc = sm + (size_t)WARPS * f;
   float* hx = acc + f;
+  float* stY = hx + f;
+  float* stC = stY + (size_t)cap * f;
+  float* stM = stC + (p.cY ? (size_t)cap * f : 0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double b1p = p.b1_pow, b2p = p.b2_pow;
-  int u = 0, i = 0, s = 0, e = 0;
-  float r = 0.f;
-  if (p.n_samples > 0) { u = p.su[0]; i = p.si[0]; r = p.sr[0]; s = p.indptr[u]; e = p.indptr[u + 1]; }
+  // sample n in (u, i, r, s, e, ids); sample n + 1 in (nu, ni, nr)
+  int u = 0, i = 0, s = 0, e = 0, ids = -1, nu = 0, ni = 0;
+  float r = 0.f, nr = 0.f;
+  if (p.n_samples > 0) {
+    u = p.su[0]; i = p.si[0]; r = p.sr[0]; s = p.indptr[u]; e = p.indptr[u + 1];
+    if (s + warp + WARPS * lane < e) ids = p.indices[s + warp + WARPS * lane];
+  }
+  if (p.n_samples > 1) { nu = p.su[1]; ni = p.si[1]; nr = p.sr[1]; }
   for (long long n = 0; n < p.n_samples; ++n) {
-    int nu = 0, ni = 0;
-    float nr = 0.f;
-    if (n + 1 < p.n_samples) { nu = p.su[n + 1]; ni = p.si[n + 1]; nr = p.sr[n + 1]; }
+    int nnu = 0, nni = 0;
+    float nnr = 0.f;
+    if (n + 2 < p.n_samples) { nnu = p.su[n + 2]; nni = p.si[n + 2]; nnr = p.sr[n + 2]; }
+    const int ns = p.indptr[nu], ne = p.indptr[nu + 1];  // nu arrived an iteration ago (user 0 past the end: harmless)
     float b_mu = 0.f, b_u = 0.f, b_i = 0.f;
     if (tid == 0 && p.use_bias) { b_mu = p.mu[0]; b_u = p.bu[u]; b_i = p.bi[i]; }  // in flight during the gather
+    const int my_rows = e - s > warp ? (e - s - warp + WARPS - 1) / WARPS : 0;   // rows of this warp: t = 0 .. my_rows - 1
     // (1) pyx:436-448: sum of the Y rows of the profile
     for (int q = lane; q < f; q += 32) part[warp * f + q] = 0.f;
-    for (int k = s + warp; k < e; k += ROWS * WARPS) {
+    for (int t0 = 0; t0 < my_rows; t0 += ROWS) {
       int it[ROWS];
 #pragma unroll
-      for (int j = 0; j < ROWS; ++j) it[j] = k + j * WARPS < e ? p.indices[k + j * WARPS] : -1;
+      for (int j = 0; j < ROWS; ++j) {
+        const int t = t0 + j;
+        it[j] = -1;
+        if (t < my_rows) it[j] = t < 32 ? __shfl_sync(0xffffffffu, ids, t & 31) : p.indices[s + warp + WARPS * t];
+        else if (t < 32) (void)__shfl_sync(0xffffffffu, ids, t & 31);
+      }
       for (int q = lane; q < f; q += 32) {
         float v[ROWS];
 #pragma unroll
         for (int j = 0; j < ROWS; ++j) v[j] = it[j] >= 0 ? p.Y[(size_t)it[j] * f + q] : 0.f;
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+          const int slot = warp + WARPS * (t0 + j);  // position of the row in the profile
+          if (it[j] >= 0 && slot < cap) {
+            if (p.cY) cp_async4(stC + (size_t)slot * f + q, p.cY + (size_t)it[j] * f + q);
+            if (p.m2Y) cp_async4(stM + (size_t)slot * f + q, p.m2Y + (size_t)it[j] * f + q);
+          }
+        }
         part[warp * f + q] += (v[0] + v[1]) + (v[2] + v[3]);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+          const int slot = warp + WARPS * (t0 + j);
+          if (it[j] >= 0 && slot < cap) stY[(size_t)slot * f + q] = v[j];
+        }
       }
     }
-    const int ns = p.indptr[nu], ne = p.indptr[nu + 1];  // next sample's profile bounds (row 0 past the end: harmless)
     __syncthreads();
     // (2)
     const float inv_den = 1.f / sqrtf((float)(e - s));  // pyx:451-455
@@ -116,6 +154,9 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
     if (lane == 0) red[warp] = dot;
+    // the next sample's item ids, one per lane (its bounds arrived during the gather)
+    int nids = -1;
+    if (ns + warp + WARPS * lane < ne) nids = p.indices[ns + warp + WARPS * lane];
     __syncthreads();
     const float inv1 = (float)(1.0 / (1.0 - b1p)), inv2 = (float)(1.0 / (1.0 - b2p));
     // (3)
@@ -133,35 +174,31 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
         p.bu[u] = b_u + p.lr * gu;
       }
     }
+    cp_async_wait_all();  // this thread's state copies (it reads back only what it copied itself)
     __syncthreads();
     const float err = s_err;
     // (4) pyx:505-521: every Y row of the profile (the rows are distinct items), H_i from before the X update
-    for (int k = s + warp; k < e; k += ROWS * WARPS) {
-      size_t base[ROWS];
-      bool on[ROWS];
-#pragma unroll
-      for (int j = 0; j < ROWS; ++j) {
-        on[j] = k + j * WARPS < e;
-        base[j] = on[j] ? (size_t)p.indices[k + j * WARPS] * f : 0;
-      }
+    for (int t = 0; t < my_rows; ++t) {
+      const int slot = warp + WARPS * t;
+      const int item = t < 32 ? __shfl_sync(0xffffffffu, ids, t & 31) : p.indices[s + slot];
+      const size_t base = (size_t)item * f;
+      const bool stashed = slot < cap;
       for (int q = lane; q < f; q += 32) {
-        float w[ROWS], c[ROWS], m2[ROWS];
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-          w[j] = on[j] ? p.Y[base[j] + q] : 0.f;
-          c[j] = on[j] && p.cY ? p.cY[base[j] + q] : 0.f;
-          m2[j] = on[j] && p.m2Y ? p.m2Y[base[j] + q] : 0.f;
+        float w, c = 0.f, m2 = 0.f;
+        if (stashed) {
+          w = stY[(size_t)slot * f + q];
+          if (p.cY) c = stC[(size_t)slot * f + q];
+          if (p.m2Y) m2 = stM[(size_t)slot * f + q];
+        } else {
+          w = p.Y[base + q];
+          if (p.cY) c = p.cY[base + q];
+          if (p.m2Y) m2 = p.m2Y[base + q];
         }
-        const float h = hx[q];
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-          if (!on[j]) continue;
-          float g = err * h - p.user_reg * w[j];
-          g = adapt(p, g, c[j], m2[j], inv1, inv2);
-          p.Y[base[j] + q] = w[j] + p.lr * g;
-          if (p.cY) p.cY[base[j] + q] = c[j];
-          if (p.m2Y) p.m2Y[base[j] + q] = m2[j];
-        }
+        float g = err * hx[q] - p.user_reg * w;
+        g = adapt(p, g, c, m2, inv1, inv2);
+        p.Y[base + q] = w + p.lr * g;
+        if (p.cY) p.cY[base + q] = c;
+        if (p.m2Y) p.m2Y[base + q] = m2;
       }
     }
     // (5) pyx:524-539: the X row of the sampled item, with the profile vector from before the Y update
@@ -172,7 +209,8 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
       p.X[c] = hx[q] + p.lr * g;
     }
     if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:544-547
-    u = nu; i = ni; r = nr; s = ns; e = ne;
+    u = nu; i = ni; r = nr; s = ns; e = ne; ids = nids;
+    nu = nnu; ni = nni; nr = nnr;
     __syncthreads();
   }
   if (tid == 0) { p.pow_out[0] = b1p; p.pow_out[1] = b2p; }
@@ -319,10 +357,14 @@ int b200_asysvd_epoch(b200_asysvd_t h, void* stream) {
     B200_CUDA(cudaMemcpyAsync(h->si.get(), h->hs_i.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(h->sr.get(), h->hs_r.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaEventRecord(h->ev0, st));
-    const size_t smem = (size_t)(WARPS + 2) * (size_t)p.f * sizeof(float);
+    // shared memory: the fixed part, then as many stashed profile rows (with their state) as fit under 200 KB
+    const size_t fixed = (size_t)(WARPS + 2) * (size_t)p.f * sizeof(float);
+    const size_t row_bytes = (size_t)p.f * sizeof(float) * (1 + (p.cY ? 1 : 0) + (p.m2Y ? 1 : 0));
+    const int cap = (int)std::min<size_t>(((size_t)200 * 1024 - fixed) / row_bytes, 4096);
+    const size_t smem = fixed + (size_t)cap * row_bytes;
     // per launch: the attribute belongs to the function, and handles with other factor counts share it
-    B200_CUDA(cudaFuncSetAttribute(asysvd_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-    asysvd_sequential_kernel<<<1, THREADS, smem, st>>>(p);
+    B200_CUDA(cudaFuncSetAttribute(asysvd_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    asysvd_sequential_kernel<<<1, THREADS, smem, st>>>(p, cap);
     B200_CUDA(cudaGetLastError());
     count_launch();
     B200_CUDA(cudaEventRecord(h->ev1, st));

@@ -111,6 +111,8 @@ class SLIM_BPR_Cython_Epoch:
             # IN PLACE and emits the non-zero cells that are left; topK=False emits them all
             _lib.check(self._lib.b200_slim_tree_prune(self._h, 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             _lib.check(self._lib.b200_slim_get_S_dense(self._h, None, d.data_ptr()))
+            if self.topK:  # every row now holds <= topK non-zero cells: the top-K kernel emits exactly them, CSR built on the device
+                return dense_topk_to_sparse(d, n, self.topK, along_columns=False, mode=0).astype(np.float64)
             return sps.csr_matrix(d.cpu().numpy().astype(np.float64))
         _lib.check(self._lib.b200_slim_get_S_dense(self._h, None, d.data_ptr()))
         if self.topK is False:
