@@ -10,6 +10,8 @@
 // an item more often than not), so ONE CTA walks the replayed sample stream in order and spreads the len_u x f reads and
 // read-modify-writes of a sample over its 16 warps (one warp per profile row, lanes over the factors).  Roofline: L2 / HBM
 // latency per sample, 2 * len_u * f * 4 bytes read + len_u * f * 4 written (+ the adaptive state), not bandwidth.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -35,6 +37,7 @@ struct Params {
   const int* su; const int* si; const float* sr;
   long long n_samples;
   double* pow_out;
+  int prof;  // B200REC_ASY_PROF=1: thread 0 times the phases of every sample and prints the averages (development hook)
 };
 
 // pyx:838-876 on register copies of the state; c is the adagrad / rmsprop cache or adam's first moment, m2 adam's second moment
@@ -61,35 +64,28 @@ __device__ __forceinline__ float adapt_at(const Params& p, float g, float* c, fl
   return r;
 }
 
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// One CTA, samples strictly in order.  Per sample:
-//  (1) every warp sums the Y rows of its share of the profile (row r of the profile belongs to warp r % WARPS), ROWS rows in
-//      flight; the rows are kept in a shared-memory stash and their adaptive state is pulled next to them with cp.async, so
-//      that step (4) reads nothing from L2 (rows beyond the stash capacity are read again);
-//  (2) the partial sums are added across the warps, the X row of the item is read, the prediction is reduced;
-//  (3) thread 0 forms the error and steps the biases;
-//  (4) every warp updates its Y rows and their state, (5) the X row.
+// One CTA, samples strictly in order.  Per sample: (1) every warp sums the Y rows of its share of the profile (row r of the
+// profile belongs to warp r % WARPS), ROWS rows in flight; (2) the partial sums are added across the warps, the X row of the
+// item is read, the prediction is reduced; (3) thread 0 forms the error and steps the biases; (4) every warp updates its Y
+// rows (ROWS rows and their adaptive state in flight; the rows were just read, so these loads hit L1), (5) the X row.
 // The item ids of a warp's rows sit in its lanes (lane t holds row warp + WARPS * t); the next sample's (user, item, rating),
 // profile bounds and ids are fetched while the current one runs.
-// dynamic shared memory: part[WARPS][f] partial sums, acc[f] the profile vector, hx[f] the X row before its update, then the
-// stash: cap rows of Y [, of the first state array [, of the second]].
-__global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params p, const int cap) {
+// dynamic shared memory: part[WARPS][f] partial profile sums, acc[f] the profile vector, hx[f] the X row before its update
+#define ASY_MARK(k) do { if (p.prof && tid == 0) { const long long t_ = clock64(); prof[k] += (unsigned long long)(t_ - tprev); tprev = t_; } } while (0)
+__global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params p) {
   extern __shared__ float sm[];
   __shared__ float red[WARPS];
-  __shared__ float s_err;
+  __shared__ float s_err, s_inv1, s_inv2;
+  __shared__ unsigned long long prof[8];
   const int f = p.f;
   float* part = sm;
   float* acc = sm + (size_t)WARPS * f;
   float* hx = acc + f;
-  float* stY = hx + f;
-  float* stC = stY + (size_t)cap * f;
-  float* stM = stC + (p.cY ? (size_t)cap * f : 0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double b1p = p.b1_pow, b2p = p.b2_pow;
+  double b1p = p.b1_pow, b2p = p.b2_pow;  // advanced by thread 0 only
+  long long tprev = 0;
+  if (tid < 8) prof[tid] = 0ull;
+  if (tid == 0) { s_inv1 = 1.f; s_inv2 = 1.f; }
   // sample n in (u, i, r, s, e, ids); sample n + 1 in (nu, ni, nr)
   int u = 0, i = 0, s = 0, e = 0, ids = -1, nu = 0, ni = 0;
   float r = 0.f, nr = 0.f;
@@ -98,6 +94,8 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
     if (s + warp + WARPS * lane < e) ids = p.indices[s + warp + WARPS * lane];
   }
   if (p.n_samples > 1) { nu = p.su[1]; ni = p.si[1]; nr = p.sr[1]; }
+  __syncthreads();
+  if (p.prof && tid == 0) tprev = clock64();
   for (long long n = 0; n < p.n_samples; ++n) {
     int nnu = 0, nni = 0;
     float nnr = 0.f;
@@ -113,31 +111,19 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
 #pragma unroll
       for (int j = 0; j < ROWS; ++j) {
         const int t = t0 + j;
-        it[j] = -1;
-        if (t < my_rows) it[j] = t < 32 ? __shfl_sync(0xffffffffu, ids, t & 31) : p.indices[s + warp + WARPS * t];
-        else if (t < 32) (void)__shfl_sync(0xffffffffu, ids, t & 31);
+        const int sh = t < 32 ? __shfl_sync(0xffffffffu, ids, t & 31) : -1;  // every lane, every j: t is warp-uniform
+        it[j] = t < my_rows ? (t < 32 ? sh : p.indices[s + warp + WARPS * t]) : -1;
       }
       for (int q = lane; q < f; q += 32) {
         float v[ROWS];
 #pragma unroll
         for (int j = 0; j < ROWS; ++j) v[j] = it[j] >= 0 ? p.Y[(size_t)it[j] * f + q] : 0.f;
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-          const int slot = warp + WARPS * (t0 + j);  // position of the row in the profile
-          if (it[j] >= 0 && slot < cap) {
-            if (p.cY) cp_async4(stC + (size_t)slot * f + q, p.cY + (size_t)it[j] * f + q);
-            if (p.m2Y) cp_async4(stM + (size_t)slot * f + q, p.m2Y + (size_t)it[j] * f + q);
-          }
-        }
         part[warp * f + q] += (v[0] + v[1]) + (v[2] + v[3]);
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-          const int slot = warp + WARPS * (t0 + j);
-          if (it[j] >= 0 && slot < cap) stY[(size_t)slot * f + q] = v[j];
-        }
       }
     }
+    ASY_MARK(0);
     __syncthreads();
+    ASY_MARK(1);
     // (2)
     const float inv_den = 1.f / sqrtf((float)(e - s));  // pyx:451-455
     float dot = 0.f;
@@ -157,10 +143,13 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
     // the next sample's item ids, one per lane (its bounds arrived during the gather)
     int nids = -1;
     if (ns + warp + WARPS * lane < ne) nids = p.indices[ns + warp + WARPS * lane];
+    ASY_MARK(2);
     __syncthreads();
-    const float inv1 = (float)(1.0 / (1.0 - b1p)), inv2 = (float)(1.0 / (1.0 - b2p));
+    ASY_MARK(3);
     // (3)
     if (tid == 0) {
+      float inv1 = 1.f, inv2 = 1.f;
+      if (p.sgd_mode == ADAM) { inv1 = (float)(1.0 / (1.0 - b1p)); inv2 = (float)(1.0 / (1.0 - b2p)); s_inv1 = inv1; s_inv2 = inv2; }
       float pred = p.use_bias ? b_mu + b_u + b_i : 0.f;  // pyx:458-461
       for (int w = 0; w < WARPS; ++w) pred += red[w];
       const float err = r - pred;  // pyx:468-471 with batch_size == 1
@@ -173,32 +162,41 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
         p.bi[i] = b_i + p.lr * gi;
         p.bu[u] = b_u + p.lr * gu;
       }
+      if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:544-547
     }
-    cp_async_wait_all();  // this thread's state copies (it reads back only what it copied itself)
+    ASY_MARK(4);
     __syncthreads();
-    const float err = s_err;
+    ASY_MARK(5);
+    const float err = s_err, inv1 = s_inv1, inv2 = s_inv2;
     // (4) pyx:505-521: every Y row of the profile (the rows are distinct items), H_i from before the X update
-    for (int t = 0; t < my_rows; ++t) {
-      const int slot = warp + WARPS * t;
-      const int item = t < 32 ? __shfl_sync(0xffffffffu, ids, t & 31) : p.indices[s + slot];
-      const size_t base = (size_t)item * f;
-      const bool stashed = slot < cap;
+    for (int t0 = 0; t0 < my_rows; t0 += ROWS) {
+      size_t base[ROWS];
+      bool on[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) {
+        const int t = t0 + j;
+        const int sh = t < 32 ? __shfl_sync(0xffffffffu, ids, t & 31) : -1;
+        on[j] = t < my_rows;
+        base[j] = on[j] ? (size_t)(t < 32 ? sh : p.indices[s + warp + WARPS * t]) * f : 0;
+      }
       for (int q = lane; q < f; q += 32) {
-        float w, c = 0.f, m2 = 0.f;
-        if (stashed) {
-          w = stY[(size_t)slot * f + q];
-          if (p.cY) c = stC[(size_t)slot * f + q];
-          if (p.m2Y) m2 = stM[(size_t)slot * f + q];
-        } else {
-          w = p.Y[base + q];
-          if (p.cY) c = p.cY[base + q];
-          if (p.m2Y) m2 = p.m2Y[base + q];
+        float w[ROWS], c[ROWS], m2[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+          w[j] = on[j] ? p.Y[base[j] + q] : 0.f;
+          c[j] = on[j] && p.cY ? p.cY[base[j] + q] : 0.f;
+          m2[j] = on[j] && p.m2Y ? p.m2Y[base[j] + q] : 0.f;
         }
-        float g = err * hx[q] - p.user_reg * w;
-        g = adapt(p, g, c, m2, inv1, inv2);
-        p.Y[base + q] = w + p.lr * g;
-        if (p.cY) p.cY[base + q] = c;
-        if (p.m2Y) p.m2Y[base + q] = m2;
+        const float h = hx[q];
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+          if (!on[j]) continue;
+          float g = err * h - p.user_reg * w[j];
+          g = adapt(p, g, c[j], m2[j], inv1, inv2);
+          p.Y[base[j] + q] = w[j] + p.lr * g;
+          if (p.cY) p.cY[base[j] + q] = c[j];
+          if (p.m2Y) p.m2Y[base[j] + q] = m2[j];
+        }
       }
     }
     // (5) pyx:524-539: the X row of the sampled item, with the profile vector from before the Y update
@@ -208,12 +206,19 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
       g = adapt_at(p, g, p.cX ? p.cX + c : nullptr, p.m2X ? p.m2X + c : nullptr, inv1, inv2);
       p.X[c] = hx[q] + p.lr * g;
     }
-    if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:544-547
     u = nu; i = ni; r = nr; s = ns; e = ne; ids = nids;
     nu = nnu; ni = nni; nr = nnr;
+    ASY_MARK(6);
     __syncthreads();
+    ASY_MARK(7);
   }
-  if (tid == 0) { p.pow_out[0] = b1p; p.pow_out[1] = b2p; }
+  if (tid == 0) {
+    p.pow_out[0] = b1p; p.pow_out[1] = b2p;
+    if (p.prof)
+      printf("asysvd phase cycles per sample: gather=%llu bar1=%llu reduce=%llu bar2=%llu thread0=%llu bar3=%llu update=%llu bar4=%llu\n",
+             prof[0] / p.n_samples, prof[1] / p.n_samples, prof[2] / p.n_samples, prof[3] / p.n_samples, prof[4] / p.n_samples,
+             prof[5] / p.n_samples, prof[6] / p.n_samples, prof[7] / p.n_samples);
+  }
 }
 
 }  // namespace asy
@@ -326,6 +331,7 @@ int b200_asysvd_epoch(b200_asysvd_t h, void* stream) {
     Params& p = h->p;
     const long long n = (long long)h->h_indices.size() + 1;
     p.n_samples = n;
+    p.prof = getenv("B200REC_ASY_PROF") != nullptr;
     h->hs_u.resize((size_t)n); h->hs_i.resize((size_t)n); h->hs_r.resize((size_t)n);
     const int* indptr = h->h_indptr.data();
     const int* indices = h->h_indices.data();
@@ -357,14 +363,10 @@ int b200_asysvd_epoch(b200_asysvd_t h, void* stream) {
     B200_CUDA(cudaMemcpyAsync(h->si.get(), h->hs_i.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(h->sr.get(), h->hs_r.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaEventRecord(h->ev0, st));
-    // shared memory: the fixed part, then as many stashed profile rows (with their state) as fit under 200 KB
-    const size_t fixed = (size_t)(WARPS + 2) * (size_t)p.f * sizeof(float);
-    const size_t row_bytes = (size_t)p.f * sizeof(float) * (1 + (p.cY ? 1 : 0) + (p.m2Y ? 1 : 0));
-    const int cap = (int)std::min<size_t>(((size_t)200 * 1024 - fixed) / row_bytes, 4096);
-    const size_t smem = fixed + (size_t)cap * row_bytes;
+    const size_t smem = (size_t)(WARPS + 2) * (size_t)p.f * sizeof(float);
     // per launch: the attribute belongs to the function, and handles with other factor counts share it
-    B200_CUDA(cudaFuncSetAttribute(asysvd_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    asysvd_sequential_kernel<<<1, THREADS, smem, st>>>(p, cap);
+    B200_CUDA(cudaFuncSetAttribute(asysvd_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    asysvd_sequential_kernel<<<1, THREADS, smem, st>>>(p);
     B200_CUDA(cudaGetLastError());
     count_launch();
     B200_CUDA(cudaEventRecord(h->ev1, st));

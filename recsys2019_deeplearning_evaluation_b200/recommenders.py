@@ -516,7 +516,7 @@ class SLIMElasticNetRecommender(BaseItemSimilarityMatrixRecommender):
             self.RECOMMENDER_NAME, l1_ratio)  # :43
         self.l1_ratio, self.positive_only, self.topK = l1_ratio, positive_only, topK
         n = self.n_items
-        G = EASE_R_Recommender._gram_device(self)
+        G = EASE_R_Recommender._gram_device(self)  # the same X^T X (it only reads URM_train / n_items)
         X = self.URM_train
         diag = torch.from_numpy(np.asarray(X.multiply(X).sum(axis=0), dtype=np.float32).ravel()).to(G.device)
         coefT = torch.empty((n, n), dtype=torch.float32, device=G.device)
