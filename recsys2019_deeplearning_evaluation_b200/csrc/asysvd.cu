@@ -8,8 +8,10 @@
 //
 // The recursion is strictly sequential (sample t+1 reads rows sample t wrote: two profiles of ~150 items out of 27 K share
 // an item more often than not), so ONE CTA walks the replayed sample stream in order and spreads the len_u x f reads and
-// read-modify-writes of a sample over its 16 warps (one warp per profile row, lanes over the factors).  Roofline: L2 / HBM
-// latency per sample, 2 * len_u * f * 4 bytes read + len_u * f * 4 written (+ the adaptive state), not bandwidth.
+// read-modify-writes of a sample over its 32 warps.  Measured with per-phase cycle counters (profiles/r02_asysvd_phase_*):
+// the scalar one-warp-per-row version was ISSUE-bound (150 warp instructions per 32-element row, 24 K per sample on four
+// schedulers), not latency-bound -- so rows are padded to a multiple of four factors and handled as float4s, min(32, f/4)
+// lanes per row and several rows per warp instruction.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -23,10 +25,11 @@ namespace asy {
 enum SgdMode { SGD = 0, ADAGRAD = 1, RMSPROP = 2, ADAM = 3 };
 constexpr int THREADS = 1024;
 constexpr int WARPS = THREADS / 32;
-constexpr int ROWS = 4;  // profile rows a warp keeps in flight
+static_assert(WARPS == 32, "step (2) keeps one partial vector per lane");
 
 struct Params {
   int n_users, n_items, f, use_bias, sgd_mode;
+  int fp, lpr;  // row stride (f rounded up to 4; the padding stays 0) and lanes per row (power of two <= min(32, fp / 8))
   float lr, user_reg, item_reg, bias_reg, gamma, beta1, beta2;
   double b1_pow, b2_pow;
   const int* __restrict__ indptr;
@@ -64,35 +67,50 @@ __device__ __forceinline__ float adapt_at(const Params& p, float g, float* c, fl
   return r;
 }
 
-// One CTA, samples strictly in order.  Per sample: (1) every warp sums the Y rows of its share of the profile (row r of the
-// profile belongs to warp r % WARPS), ROWS rows in flight; (2) the partial sums are added across the warps, the X row of the
-// item is read, the prediction is reduced; (3) thread 0 forms the error and steps the biases; (4) every warp updates its Y
-// rows (ROWS rows and their adaptive state in flight; the rows were just read, so these loads hit L1), (5) the X row.
-// The item ids of a warp's rows sit in its lanes (lane t holds row warp + WARPS * t); the next sample's (user, item, rating),
-// profile bounds and ids are fetched while the current one runs.
-// dynamic shared memory: part[WARPS][f] partial profile sums, acc[f] the profile vector, hx[f] the X row before its update
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4shfl_xor(float4 a, int off) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, a.x, off), __shfl_xor_sync(0xffffffffu, a.y, off),
+                     __shfl_xor_sync(0xffffffffu, a.z, off), __shfl_xor_sync(0xffffffffu, a.w, off));
+}
+// one float4 of a Y row: gradient, adaptive step, new value (pyx:510-521); c / m2 are updated in place
+__device__ __forceinline__ float4 step4(const Params& p, float err, float4 h, float4 w, float4& c, float4& m2, float inv1, float inv2) {
+  float4 o;
+  o.x = w.x + p.lr * adapt(p, err * h.x - p.user_reg * w.x, c.x, m2.x, inv1, inv2);
+  o.y = w.y + p.lr * adapt(p, err * h.y - p.user_reg * w.y, c.y, m2.y, inv1, inv2);
+  o.z = w.z + p.lr * adapt(p, err * h.z - p.user_reg * w.z, c.z, m2.z, inv1, inv2);
+  o.w = w.w + p.lr * adapt(p, err * h.w - p.user_reg * w.w, c.w, m2.w, inv1, inv2);
+  return o;
+}
+
+// One CTA, samples strictly in order.  A warp instruction covers 32 / lpr rows of the profile (lane = row slot * lpr + sub;
+// lane `sub` owns the float4s sub, sub + lpr of a 2 * lpr-float4 column block; rows wider than that are walked block by block).
+// Per sample: (1) every lane sums its float4s over its rows, the row slots of a warp are added by shuffles, one partial
+// vector per warp goes to shared memory; (2) warp w adds the 32 partial vectors for the factors w, w + 32, ..., reads the X
+// row of the item and reduces the prediction; (3) thread 0 forms the error and steps the biases; (4) the Y rows (just read:
+// L1) and their adaptive state are updated float4 by float4; (5) the X row.  The next sample's (user, item, rating) and
+// profile bounds are fetched while the current one runs; inside a sample the item id of the next step is requested before
+// the current step's rows.
+// dynamic shared memory: part[WARPS][fp] partial profile sums, acc[fp] the profile vector, hx[fp] the X row before its update
 #define ASY_MARK(k) do { if (p.prof && tid == 0) { const long long t_ = clock64(); prof[k] += (unsigned long long)(t_ - tprev); tprev = t_; } } while (0)
 __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   __shared__ float red[WARPS];
   __shared__ float s_err, s_inv1, s_inv2;
   __shared__ unsigned long long prof[8];
-  const int f = p.f;
+  const int f = p.f, fp = p.fp, nq4 = fp >> 2, lpr = p.lpr;
   float* part = sm;
-  float* acc = sm + (size_t)WARPS * f;
-  float* hx = acc + f;
+  float* acc = sm + (size_t)WARPS * fp;
+  float* hx = acc + fp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & (lpr - 1), rpw = 32 / lpr, myrow0 = warp * rpw + lane / lpr, NR = WARPS * rpw;
   double b1p = p.b1_pow, b2p = p.b2_pow;  // advanced by thread 0 only
   long long tprev = 0;
   if (tid < 8) prof[tid] = 0ull;
   if (tid == 0) { s_inv1 = 1.f; s_inv2 = 1.f; }
-  // sample n in (u, i, r, s, e, ids); sample n + 1 in (nu, ni, nr)
-  int u = 0, i = 0, s = 0, e = 0, ids = -1, nu = 0, ni = 0;
+  // sample n in (u, i, r, s, e); sample n + 1 in (nu, ni, nr)
+  int u = 0, i = 0, s = 0, e = 0, nu = 0, ni = 0;
   float r = 0.f, nr = 0.f;
-  if (p.n_samples > 0) {
-    u = p.su[0]; i = p.si[0]; r = p.sr[0]; s = p.indptr[u]; e = p.indptr[u + 1];
-    if (s + warp + WARPS * lane < e) ids = p.indices[s + warp + WARPS * lane];
-  }
+  if (p.n_samples > 0) { u = p.su[0]; i = p.si[0]; r = p.sr[0]; s = p.indptr[u]; e = p.indptr[u + 1]; }
   if (p.n_samples > 1) { nu = p.su[1]; ni = p.si[1]; nr = p.sr[1]; }
   __syncthreads();
   if (p.prof && tid == 0) tprev = clock64();
@@ -103,110 +121,113 @@ __global__ void __launch_bounds__(THREADS) asysvd_sequential_kernel(const Params
     const int ns = p.indptr[nu], ne = p.indptr[nu + 1];  // nu arrived an iteration ago (user 0 past the end: harmless)
     float b_mu = 0.f, b_u = 0.f, b_i = 0.f;
     if (tid == 0 && p.use_bias) { b_mu = p.mu[0]; b_u = p.bu[u]; b_i = p.bi[i]; }  // in flight during the gather
-    const int my_rows = e - s > warp ? (e - s - warp + WARPS - 1) / WARPS : 0;   // rows of this warp: t = 0 .. my_rows - 1
+    const int len = e - s;
     // (1) pyx:436-448: sum of the Y rows of the profile
-    for (int q = lane; q < f; q += 32) part[warp * f + q] = 0.f;
-    for (int t0 = 0; t0 < my_rows; t0 += ROWS) {
-      int it[ROWS];
-#pragma unroll
-      for (int j = 0; j < ROWS; ++j) {
-        const int t = t0 + j;
-        const int sh = t < 32 ? __shfl_sync(0xffffffffu, ids, t & 31) : -1;  // every lane, every j: t is warp-uniform
-        it[j] = t < my_rows ? (t < 32 ? sh : p.indices[s + warp + WARPS * t]) : -1;
+    for (int qb = 0; qb < nq4; qb += 2 * lpr) {
+      const int q0 = qb + sub, q1 = q0 + lpr;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+      int id = myrow0 < len ? p.indices[s + myrow0] : -1;
+      for (int r0 = 0; r0 < len; r0 += NR) {  // warp-uniform trip count
+        const int rn = r0 + NR + myrow0;
+        const int idn = rn < len ? p.indices[s + rn] : -1;
+        if (id >= 0) {
+          const float4* row = reinterpret_cast<const float4*>(p.Y + (size_t)id * fp);
+          if (q0 < nq4) a0 = f4add(a0, row[q0]);
+          if (q1 < nq4) a1 = f4add(a1, row[q1]);
+        }
+        id = idn;
       }
-      for (int q = lane; q < f; q += 32) {
-        float v[ROWS];
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) v[j] = it[j] >= 0 ? p.Y[(size_t)it[j] * f + q] : 0.f;
-        part[warp * f + q] += (v[0] + v[1]) + (v[2] + v[3]);
+      for (int off = lpr; off < 32; off <<= 1) { a0 = f4add(a0, f4shfl_xor(a0, off)); a1 = f4add(a1, f4shfl_xor(a1, off)); }
+      if (lane < lpr) {
+        float4* pw = reinterpret_cast<float4*>(part + (size_t)warp * fp);
+        if (q0 < nq4) pw[q0] = a0;
+        if (q1 < nq4) pw[q1] = a1;
       }
     }
     ASY_MARK(0);
     __syncthreads();
     ASY_MARK(1);
-    // (2)
-    const float inv_den = 1.f / sqrtf((float)(e - s));  // pyx:451-455
+    // (2) warp w owns the factors w, w + 32, ...: the 32 partial vectors sit one per lane
+    const float inv_den = 1.f / sqrtf((float)len);  // pyx:451-455
     float dot = 0.f;
-    for (int q = tid; q < f; q += THREADS) {
-      float a = 0.f;
-#pragma unroll 8
-      for (int w = 0; w < WARPS; ++w) a += part[w * f + q];
-      a *= inv_den;
-      const float h = p.X[(size_t)i * f + q];
-      acc[q] = a;
-      hx[q] = h;
-      dot += a * h;  // pyx:463-464
-    }
+    for (int q = warp; q < fp; q += WARPS) {
+      float a = part[(size_t)lane * fp + q];
+      const float h = q < f ? p.X[(size_t)i * fp + q] : 0.f;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      a *= inv_den;
+      if (lane == 0) { acc[q] = a; hx[q] = h; }
+      dot += a * h;  // pyx:463-464 (every lane holds the same value)
+    }
     if (lane == 0) red[warp] = dot;
-    // the next sample's item ids, one per lane (its bounds arrived during the gather)
-    int nids = -1;
-    if (ns + warp + WARPS * lane < ne) nids = p.indices[ns + warp + WARPS * lane];
     ASY_MARK(2);
     __syncthreads();
     ASY_MARK(3);
     // (3)
-    if (tid == 0) {
-      float inv1 = 1.f, inv2 = 1.f;
-      if (p.sgd_mode == ADAM) { inv1 = (float)(1.0 / (1.0 - b1p)); inv2 = (float)(1.0 / (1.0 - b2p)); s_inv1 = inv1; s_inv2 = inv2; }
-      float pred = p.use_bias ? b_mu + b_u + b_i : 0.f;  // pyx:458-461
-      for (int w = 0; w < WARPS; ++w) pred += red[w];
-      const float err = r - pred;  // pyx:468-471 with batch_size == 1
-      s_err = err;
-      if (p.use_bias) {  // pyx:476-502: global, then item and user bias, all from the same error
-        const float gm = adapt_at(p, err - p.bias_reg * b_mu, p.cmu, p.m2mu, inv1, inv2);
-        const float gi = adapt_at(p, err - p.bias_reg * b_i, p.cbi ? p.cbi + i : nullptr, p.m2bi ? p.m2bi + i : nullptr, inv1, inv2);
-        const float gu = adapt_at(p, err - p.bias_reg * b_u, p.cbu ? p.cbu + u : nullptr, p.m2bu ? p.m2bu + u : nullptr, inv1, inv2);
-        p.mu[0] = b_mu + p.lr * gm;
-        p.bi[i] = b_i + p.lr * gi;
-        p.bu[u] = b_u + p.lr * gu;
+    if (warp == 0) {
+      float pred = red[lane];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) pred += __shfl_xor_sync(0xffffffffu, pred, off);
+      if (lane == 0) {
+        float inv1 = 1.f, inv2 = 1.f;
+        if (p.sgd_mode == ADAM) { inv1 = (float)(1.0 / (1.0 - b1p)); inv2 = (float)(1.0 / (1.0 - b2p)); s_inv1 = inv1; s_inv2 = inv2; }
+        if (p.use_bias) pred += b_mu + b_u + b_i;  // pyx:458-461
+        const float err = r - pred;  // pyx:468-471 with batch_size == 1
+        s_err = err;
+        if (p.use_bias) {  // pyx:476-502: global, then item and user bias, all from the same error
+          const float gm = adapt_at(p, err - p.bias_reg * b_mu, p.cmu, p.m2mu, inv1, inv2);
+          const float gi = adapt_at(p, err - p.bias_reg * b_i, p.cbi ? p.cbi + i : nullptr, p.m2bi ? p.m2bi + i : nullptr, inv1, inv2);
+          const float gu = adapt_at(p, err - p.bias_reg * b_u, p.cbu ? p.cbu + u : nullptr, p.m2bu ? p.m2bu + u : nullptr, inv1, inv2);
+          p.mu[0] = b_mu + p.lr * gm;
+          p.bi[i] = b_i + p.lr * gi;
+          p.bu[u] = b_u + p.lr * gu;
+        }
+        if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:544-547
       }
-      if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:544-547
     }
     ASY_MARK(4);
     __syncthreads();
     ASY_MARK(5);
     const float err = s_err, inv1 = s_inv1, inv2 = s_inv2;
     // (4) pyx:505-521: every Y row of the profile (the rows are distinct items), H_i from before the X update
-    for (int t0 = 0; t0 < my_rows; t0 += ROWS) {
-      size_t base[ROWS];
-      bool on[ROWS];
-#pragma unroll
-      for (int j = 0; j < ROWS; ++j) {
-        const int t = t0 + j;
-        const int sh = t < 32 ? __shfl_sync(0xffffffffu, ids, t & 31) : -1;
-        on[j] = t < my_rows;
-        base[j] = on[j] ? (size_t)(t < 32 ? sh : p.indices[s + warp + WARPS * t]) * f : 0;
-      }
-      for (int q = lane; q < f; q += 32) {
-        float w[ROWS], c[ROWS], m2[ROWS];
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-          w[j] = on[j] ? p.Y[base[j] + q] : 0.f;
-          c[j] = on[j] && p.cY ? p.cY[base[j] + q] : 0.f;
-          m2[j] = on[j] && p.m2Y ? p.m2Y[base[j] + q] : 0.f;
+    for (int qb = 0; qb < nq4; qb += 2 * lpr) {
+      const int q0 = qb + sub, q1 = q0 + lpr;
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 h0 = q0 < nq4 ? reinterpret_cast<const float4*>(hx)[q0] : zero;
+      const float4 h1 = q1 < nq4 ? reinterpret_cast<const float4*>(hx)[q1] : zero;
+      int id = myrow0 < len ? p.indices[s + myrow0] : -1;
+      for (int r0 = 0; r0 < len; r0 += NR) {
+        const int rn = r0 + NR + myrow0;
+        const int idn = rn < len ? p.indices[s + rn] : -1;
+        if (id >= 0) {
+          const size_t base4 = (size_t)id * nq4;
+          float4* yrow = reinterpret_cast<float4*>(p.Y) + base4;
+          float4* crow = p.cY ? reinterpret_cast<float4*>(p.cY) + base4 : nullptr;
+          float4* mrow = p.m2Y ? reinterpret_cast<float4*>(p.m2Y) + base4 : nullptr;
+          if (q0 < nq4) {
+            float4 c = crow ? crow[q0] : zero, m2 = mrow ? mrow[q0] : zero;
+            yrow[q0] = step4(p, err, h0, yrow[q0], c, m2, inv1, inv2);
+            if (crow) crow[q0] = c;
+            if (mrow) mrow[q0] = m2;
+          }
+          if (q1 < nq4) {
+            float4 c = crow ? crow[q1] : zero, m2 = mrow ? mrow[q1] : zero;
+            yrow[q1] = step4(p, err, h1, yrow[q1], c, m2, inv1, inv2);
+            if (crow) crow[q1] = c;
+            if (mrow) mrow[q1] = m2;
+          }
         }
-        const float h = hx[q];
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-          if (!on[j]) continue;
-          float g = err * h - p.user_reg * w[j];
-          g = adapt(p, g, c[j], m2[j], inv1, inv2);
-          p.Y[base[j] + q] = w[j] + p.lr * g;
-          if (p.cY) p.cY[base[j] + q] = c[j];
-          if (p.m2Y) p.m2Y[base[j] + q] = m2[j];
-        }
+        id = idn;
       }
     }
     // (5) pyx:524-539: the X row of the sampled item, with the profile vector from before the Y update
     for (int q = tid; q < f; q += THREADS) {
-      const size_t c = (size_t)i * f + q;
+      const size_t c = (size_t)i * fp + q;
       float g = err * acc[q] - p.item_reg * hx[q];
       g = adapt_at(p, g, p.cX ? p.cX + c : nullptr, p.m2X ? p.m2X + c : nullptr, inv1, inv2);
       p.X[c] = hx[q] + p.lr * g;
     }
-    u = nu; i = ni; r = nr; s = ns; e = ne; ids = nids;
+    u = nu; i = ni; r = nr; s = ns; e = ne;
     nu = nnu; ni = nni; nr = nnr;
     ASY_MARK(6);
     __syncthreads();
@@ -242,11 +263,20 @@ struct b200_asysvd_s {
 };
 
 namespace {
-void upload_doubles(DevBuf<float>& dst, const double* src, size_t n) {
-  std::vector<float> tmp(n);
-  for (size_t k = 0; k < n; ++k) tmp[k] = (float)src[k];
-  dst.alloc(n);
-  B200_CUDA(cudaMemcpy(dst.get(), tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+// rows of f doubles -> rows of fp floats (zero padding)
+void upload_rows(DevBuf<float>& dst, const double* src, size_t rows, size_t f, size_t fp) {
+  std::vector<float> tmp(rows * fp, 0.f);
+  for (size_t r = 0; r < rows; ++r)
+    for (size_t k = 0; k < f; ++k) tmp[r * fp + k] = (float)src[r * f + k];
+  dst.alloc(rows * fp);
+  B200_CUDA(cudaMemcpy(dst.get(), tmp.data(), rows * fp * sizeof(float), cudaMemcpyHostToDevice));
+}
+void download_rows(double* dst, const float* src, size_t rows, size_t f, size_t fp) {
+  if (!dst) return;
+  std::vector<float> tmp(rows * fp);
+  B200_CUDA(cudaMemcpy(tmp.data(), src, rows * fp * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t r = 0; r < rows; ++r)
+    for (size_t k = 0; k < f; ++k) dst[r * f + k] = (double)tmp[r * fp + k];
 }
 void zeros(DevBuf<float>& dst, size_t n) {
   dst.alloc(n);
@@ -276,7 +306,10 @@ int b200_asysvd_create(b200_asysvd_t* out, int64_t n_users, int64_t n_items, int
     B200_REQUIRE(sgd_mode >= SGD && sgd_mode <= ADAM, "b200_asysvd_create: unknown sgd_mode %d", sgd_mode);
     h = new b200_asysvd_s();
     Params& p = h->p;
-    const size_t f = (size_t)n_factors, nf = (size_t)n_items * f;
+    const size_t f = (size_t)n_factors, fp = (f + 3) & ~(size_t)3, nf = (size_t)n_items * fp;
+    p.fp = (int)fp;
+    p.lpr = 1;
+    while (p.lpr * 2 <= std::min<int>(32, std::max<int>(1, (int)(fp / 8)))) p.lpr *= 2;  // a lane owns two float4s of a row
     p.n_users = (int)n_users; p.n_items = (int)n_items; p.f = n_factors; p.use_bias = use_bias != 0; p.sgd_mode = sgd_mode;
     p.lr = learning_rate; p.user_reg = user_reg; p.item_reg = item_reg; p.bias_reg = bias_reg;
     p.gamma = gamma; p.beta1 = beta_1; p.beta2 = beta_2;
@@ -291,8 +324,8 @@ int b200_asysvd_create(b200_asysvd_t* out, int64_t n_users, int64_t n_items, int
     B200_CUDA(cudaMemcpy(h->d_indptr.get(), h_indptr, sizeof(int) * ((size_t)n_users + 1), cudaMemcpyHostToDevice));
     B200_CUDA(cudaMemcpy(h->d_indices.get(), h_indices, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
     p.indptr = h->d_indptr.get(); p.indices = h->d_indices.get();
-    upload_doubles(h->Y, h_profile_factors, nf); p.Y = h->Y.get();
-    upload_doubles(h->X, h_item_factors, nf); p.X = h->X.get();
+    upload_rows(h->Y, h_profile_factors, (size_t)n_items, f, fp); p.Y = h->Y.get();
+    upload_rows(h->X, h_item_factors, (size_t)n_items, f, fp); p.X = h->X.get();
     zeros(h->bu, (size_t)n_users); zeros(h->bi, (size_t)n_items); zeros(h->mu, 1);  // pyx:184-186
     p.bu = h->bu.get(); p.bi = h->bi.get(); p.mu = h->mu.get();
     if (sgd_mode != SGD) {  // pyx:248-270
@@ -363,7 +396,7 @@ int b200_asysvd_epoch(b200_asysvd_t h, void* stream) {
     B200_CUDA(cudaMemcpyAsync(h->si.get(), h->hs_i.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(h->sr.get(), h->hs_r.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaEventRecord(h->ev0, st));
-    const size_t smem = (size_t)(WARPS + 2) * (size_t)p.f * sizeof(float);
+    const size_t smem = (size_t)(WARPS + 2) * (size_t)p.fp * sizeof(float);
     // per launch: the attribute belongs to the function, and handles with other factor counts share it
     B200_CUDA(cudaFuncSetAttribute(asysvd_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     asysvd_sequential_kernel<<<1, THREADS, smem, st>>>(p);
@@ -393,9 +426,8 @@ int b200_asysvd_get_factors(b200_asysvd_t h, double* profile_factors, double* it
   return guarded([&] {
     B200_REQUIRE(h != nullptr, "b200_asysvd_get_factors: NULL handle");
     B200_CUDA(cudaDeviceSynchronize());
-    const size_t nf = (size_t)h->p.n_items * (size_t)h->p.f;
-    download_doubles(profile_factors, h->Y.get(), nf);
-    download_doubles(item_factors, h->X.get(), nf);
+    download_rows(profile_factors, h->Y.get(), (size_t)h->p.n_items, (size_t)h->p.f, (size_t)h->p.fp);
+    download_rows(item_factors, h->X.get(), (size_t)h->p.n_items, (size_t)h->p.f, (size_t)h->p.fp);
     download_doubles(user_bias, h->bu.get(), (size_t)h->p.n_users);
     download_doubles(item_bias, h->bi.get(), (size_t)h->p.n_items);
     download_doubles(global_bias, h->mu.get(), 1);

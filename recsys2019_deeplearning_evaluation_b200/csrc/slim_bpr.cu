@@ -13,6 +13,8 @@
 //     the x_uij reduction and the 2*len_u updates of a sample are spread over the CTA's threads.
 //   * hogwild: all SMs, one warp per sample, float atomics on S (Hogwild races), Philox or replayed stream.
 // Roofline: HBM/L2, 4*len_u*4 bytes per sample for S (two row gathers read + written) + 4*len_u for the profile.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -37,6 +39,7 @@ struct Params {
   unsigned char* exists;   // tree mode: 1 where the reference's row tree holds a cell (add_value creates it, pyx:617-680)
   long long first;         // first sample of this launch (tree mode runs an epoch as segments between two prunings)
   int chain_pow;           // continue the Adam powers from pow_out (segment > 0) instead of b1_pow / b2_pow
+  int prof;                // B200REC_SLIM_PROF=1: thread 0 times the phases of the sequential kernel (development hook)
 };
 
 __device__ __forceinline__ size_t cell(const Params& p, int a, int b) {
@@ -64,41 +67,88 @@ __device__ __forceinline__ float adapt_item(const Params& p, float g, int item, 
 }
 
 constexpr int SEQ_THREADS = 512;
+constexpr int SEQ_WARPS = SEQ_THREADS / 32;
 
-// one CTA, samples strictly in order (pyx:231-312)
+#define SLIM_MARK(k) do { if (p.prof && tid == 0) { const long long t_ = clock64(); prof[k] += (unsigned long long)(t_ - tprev); tprev = t_; } } while (0)
+// one CTA, samples strictly in order (pyx:231-312).  The next sample's (u, i, j), its profile bounds and this thread's
+// profile entry are fetched while the current sample runs, and thread 0 requests the adaptive state of i and j before the
+// reduction: what is left on the critical path of a sample is one trip for the S cells, the reduction, the gradient, and the
+// update of cells that are in L1 by then.
 __global__ void __launch_bounds__(SEQ_THREADS) slim_sequential_kernel(const Params p) {
-  __shared__ float red[SEQ_THREADS / 32];
+  __shared__ float red[SEQ_WARPS];
   __shared__ float s_gi, s_gj;
+  __shared__ unsigned long long prof[6];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double b1p = p.chain_pow ? p.pow_out[0] : p.b1_pow, b2p = p.chain_pow ? p.pow_out[1] : p.b2_pow;
+  long long tprev = 0;
+  if (tid < 6) prof[tid] = 0ull;
   __syncthreads();  // pow_out is rewritten at the end
-  for (long long n = p.first; n < p.first + p.n_samples; ++n) {
-    const int u = p.su[n], i = p.si[n], j = p.sj[n];
-    const int s = p.indptr[u], e = p.indptr[u + 1];
-    float x = 0.f;
-    for (int k = s + tid; k < e; k += SEQ_THREADS) {
-      const int sn = p.indices[k];
-      x += p.S[cell(p, i, sn)] - p.S[cell(p, j, sn)];  // pyx:242-255
+  const long long last = p.first + p.n_samples;
+  // sample n in (u, i, j, s, e, sn0); sample n + 1 in (nu, ni, nj)
+  int u = 0, i = 0, j = 0, s = 0, e = 0, sn0 = -1, nu = 0, ni = 0, nj = 0;
+  if (p.n_samples > 0) {
+    u = p.su[p.first]; i = p.si[p.first]; j = p.sj[p.first];
+    s = p.indptr[u]; e = p.indptr[u + 1];
+    if (s + tid < e) sn0 = p.indices[s + tid];
+  }
+  if (p.n_samples > 1) { nu = p.su[p.first + 1]; ni = p.si[p.first + 1]; nj = p.sj[p.first + 1]; }
+  if (p.prof && tid == 0) tprev = clock64();
+  for (long long n = p.first; n < last; ++n) {
+    int nnu = 0, nni = 0, nnj = 0;
+    if (n + 2 < last) { nnu = p.su[n + 2]; nni = p.si[n + 2]; nnj = p.sj[n + 2]; }
+    const int ns = p.indptr[nu], ne = p.indptr[nu + 1];  // nu arrived an iteration ago (user 0 past the end: harmless)
+    // thread 0: the adaptive state of i and j, in flight during the gather (pyx:395-433 reads it after the gradient)
+    float st_i0 = 0.f, st_i1 = 0.f, st_j0 = 0.f, st_j1 = 0.f;
+    if (tid == 0) {
+      if (p.sgd_mode == ADAGRAD || p.sgd_mode == RMSPROP) { st_i0 = p.c[i]; st_j0 = p.c[j]; }
+      else if (p.sgd_mode == ADAM) { st_i0 = p.m1[i]; st_i1 = p.m2[i]; st_j0 = p.m1[j]; st_j1 = p.m2[j]; }
     }
+    float x = 0.f;
+    if (sn0 >= 0) x = p.S[cell(p, i, sn0)] - p.S[cell(p, j, sn0)];  // pyx:242-255
+    for (int k = s + tid + SEQ_THREADS; k < e; k += SEQ_THREADS) {
+      const int sn = p.indices[k];
+      x += p.S[cell(p, i, sn)] - p.S[cell(p, j, sn)];
+    }
+    int nsn0 = -1;
+    if (ns + tid < ne) nsn0 = p.indices[ns + tid];  // the next sample's profile entry of this thread
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
     if (lane == 0) red[warp] = x;
+    SLIM_MARK(0);
     __syncthreads();
-    if (tid == 0) {
-      float t = 0.f;
-      for (int w = 0; w < SEQ_THREADS / 32; ++w) t += red[w];
-      const float g = 1.f / (1.f + expf(t));  // pyx:258
-      const float inv1 = (float)(1.0 / (1.0 - b1p)), inv2 = (float)(1.0 / (1.0 - b2p));
-      s_gi = adapt_item(p, g, i, inv1, inv2);  // i first, then j (pyx:262-263)
-      s_gj = adapt_item(p, g, j, inv1, inv2);
+    SLIM_MARK(1);
+    if (warp == 0) {
+      float t = lane < SEQ_WARPS ? red[lane] : 0.f;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      if (lane == 0) {
+        const float g = 1.f / (1.f + expf(t));  // pyx:258
+        const float inv1 = (float)(1.0 / (1.0 - b1p)), inv2 = (float)(1.0 / (1.0 - b2p));
+        float gi = g, gj = g;  // i first, then j (pyx:262-263); i != j always (j is not in the profile, i is)
+        if (p.sgd_mode == ADAGRAD) {
+          st_i0 += g * g; gi = g / (sqrtf(st_i0) + 1e-8f); p.c[i] = st_i0;
+          st_j0 += g * g; gj = g / (sqrtf(st_j0) + 1e-8f); p.c[j] = st_j0;
+        } else if (p.sgd_mode == RMSPROP) {
+          st_i0 = st_i0 * p.gamma + (1.f - p.gamma) * g * g; gi = g / (sqrtf(st_i0) + 1e-8f); p.c[i] = st_i0;
+          st_j0 = st_j0 * p.gamma + (1.f - p.gamma) * g * g; gj = g / (sqrtf(st_j0) + 1e-8f); p.c[j] = st_j0;
+        } else if (p.sgd_mode == ADAM) {
+          st_i0 = st_i0 * p.beta1 + (1.f - p.beta1) * g; st_i1 = st_i1 * p.beta2 + (1.f - p.beta2) * g * g;
+          gi = (st_i0 * inv1) / (sqrtf(st_i1 * inv2) + 1e-8f); p.m1[i] = st_i0; p.m2[i] = st_i1;
+          st_j0 = st_j0 * p.beta1 + (1.f - p.beta1) * g; st_j1 = st_j1 * p.beta2 + (1.f - p.beta2) * g * g;
+          gj = (st_j0 * inv1) / (sqrtf(st_j1 * inv2) + 1e-8f); p.m1[j] = st_j0; p.m2[j] = st_j1;
+        }
+        s_gi = gi; s_gj = gj;
+      }
     }
+    SLIM_MARK(2);
     __syncthreads();
+    SLIM_MARK(3);
     const float gi = s_gi, gj = s_gj;
     // pyx:266-304.  Within one sample the cells (i, s) are distinct from each other and from the cells (j, s')
     // except in symmetric mode where (i, j) and (j, i) coincide when both i and j are in the profile -- j never is
     // (it is a sampled negative), so the cell sets are disjoint and the order inside the sample is free.
     for (int k = s + tid; k < e; k += SEQ_THREADS) {
-      const int sn = p.indices[k];
+      const int sn = k == s + tid ? sn0 : p.indices[k];
       if (sn != i) {
         const size_t c = cell(p, i, sn); const float v = p.S[c]; p.S[c] = v + p.lr * (gi - p.li_reg * v);
         if (p.exists) p.exists[c] = 1;
@@ -109,9 +159,19 @@ __global__ void __launch_bounds__(SEQ_THREADS) slim_sequential_kernel(const Para
       }
     }
     if (p.sgd_mode == ADAM) { b1p *= (double)p.beta1; b2p *= (double)p.beta2; }  // per sample, pyx:309-312
+    u = nu; i = ni; j = nj; s = ns; e = ne; sn0 = nsn0;
+    nu = nnu; ni = nni; nj = nnj;
+    SLIM_MARK(4);
     __syncthreads();
+    SLIM_MARK(5);
   }
-  if (tid == 0) { p.pow_out[0] = b1p; p.pow_out[1] = b2p; }
+  if (tid == 0) {
+    p.pow_out[0] = b1p; p.pow_out[1] = b2p;
+    if (p.prof && p.n_samples > 0)
+      printf("slim sequential phase cycles per sample: gather=%llu bar1=%llu gradient=%llu bar2=%llu update=%llu bar3=%llu\n",
+             prof[0] / p.n_samples, prof[1] / p.n_samples, prof[2] / p.n_samples, prof[3] / p.n_samples, prof[4] / p.n_samples,
+             prof[5] / p.n_samples);
+  }
 }
 
 // all SMs, one warp per sample, no ordering between samples
@@ -574,6 +634,7 @@ int b200_slim_epoch(b200_slim_t h, void* stream) {
     Params& p = h->p;
     const long long n = p.n_users;  // pyx:231: n_users samples per epoch
     p.n_samples = n;
+    p.prof = getenv("B200REC_SLIM_PROF") != nullptr;
     if (h->sampler == 0) {
       h->hs_u.resize((size_t)n); h->hs_i.resize((size_t)n); h->hs_j.resize((size_t)n);
       const int* indptr = h->h_indptr.data();

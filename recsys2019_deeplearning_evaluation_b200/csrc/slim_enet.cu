@@ -10,8 +10,9 @@
 //   Q = G with row / column j removed (the target column is zeroed, :88), q = G[:, j], ||y||^2 = G[j, j].
 // Coordinate descent is sequential in the coordinates, but a coordinate whose weight is 0 and stays 0 changes nothing
 // (q_k - H_k <= l1), so the CTA scans the coordinates 512 at a time against the current H = Q w, finds the FIRST one that
-// acts, applies it (H += (new - old) * Q[k, :], one coalesced row of G) and rescans from k + 1: exactly the cyclic sweep, at the
-// cost of one row of G per active coordinate.  w, H and q live in shared memory up to 3 * n * 4 bytes <= 200 KB (C4: 17.7 K
+// acts (per-warp ballots, one barrier), applies it (H += (new - old) * Q[k, :], one coalesced row of G, requested while thread 0
+// still computes the new weight) and rescans from k + 1: exactly the cyclic sweep, at the cost of one row of G and three
+// barriers per active coordinate.  w, H and q live in shared memory up to 3 * n * 4 bytes <= 200 KB (C4: 17.7 K
 // items = 208 KB), in an L2-resident workspace beyond that.
 // The reference draws the coordinate order at random from an unseeded generator; the cyclic order reaches the same optimum
 // within the same tolerance (tests/test_oracle_elasticnet.py pins that against the reference's own output).
@@ -25,6 +26,7 @@ namespace enet {
 
 constexpr int THREADS = 512;
 constexpr int WARPS = THREADS / 32;
+constexpr int PRE = 8;  // elements of a row of G a thread requests before the step is known
 
 struct Params {
   const float* __restrict__ G;     // [n, n] symmetric; the diagonal is taken from diag
@@ -63,7 +65,8 @@ __device__ __forceinline__ float block_max(float v, double* red) {
 __global__ void __launch_bounds__(THREADS) slim_enet_kernel(const Params p) {
   extern __shared__ float sm[];
   __shared__ double red[WARPS];
-  __shared__ int s_item, s_first;
+  __shared__ int s_item;
+  __shared__ unsigned s_ballot[WARPS];
   __shared__ float s_old, s_new, s_wmax, s_dwmax;
   const int n = p.n, tid = threadIdx.x, lane = tid & 31;
   float* w = p.work ? p.work + (size_t)blockIdx.x * 3 * n : sm;
@@ -100,12 +103,23 @@ __global__ void __launch_bounds__(THREADS) slim_enet_kernel(const Params p) {
               }
             }
           }
-          if (tid == 0) s_first = 0x7fffffff;
-          if (!__syncthreads_or(acts)) { k0 += THREADS; continue; }
           const unsigned b = __ballot_sync(0xffffffffu, acts);
-          if (b && lane == __ffs(b) - 1) atomicMin(&s_first, k);
-          __syncthreads();
-          const int kf = s_first;
+          if (lane == 0) s_ballot[tid >> 5] = b;
+          if (!__syncthreads_or(acts)) { k0 += THREADS; continue; }  // also publishes the ballots
+          int kf = k0;
+#pragma unroll
+          for (int wv = WARPS - 1; wv >= 0; --wv) {  // the lowest acting coordinate of the chunk
+            const unsigned bw = s_ballot[wv];
+            if (bw) kf = k0 + wv * 32 + __ffs(bw) - 1;
+          }
+          // its row of G is requested before the new weight is known (PRE values per thread stay in registers)
+          const float* Gk = p.G + (size_t)kf * n;
+          float gpre[PRE];
+#pragma unroll
+          for (int m = 0; m < PRE; ++m) {
+            const int c = tid + m * THREADS;
+            gpre[m] = c < n ? Gk[c] : 0.f;
+          }
           if (tid == 0) {
             const float d = p.diag[kf], wk = w[kf];
             float hk = H[kf];
@@ -122,10 +136,20 @@ __global__ void __launch_bounds__(THREADS) slim_enet_kernel(const Params p) {
           __syncthreads();
           const float wk = s_old, nw = s_new;
           if (wk != nw) {
-            const float* Gk = p.G + (size_t)kf * n;
             const float dk = p.diag[kf];
-            for (int c = tid; c < n; c += THREADS) {
-              if (c == j) continue;  // column j of Q is zero
+#pragma unroll
+            for (int m = 0; m < PRE; ++m) {
+              const int c = tid + m * THREADS;
+              if (c < n && c != j) {  // column j of Q is zero
+                const float g = c == kf ? dk : gpre[m];
+                float h = H[c];
+                h -= wk * g;
+                h += nw * g;
+                H[c] = h;
+              }
+            }
+            for (int c = tid + PRE * THREADS; c < n; c += THREADS) {
+              if (c == j) continue;
               const float g = c == kf ? dk : Gk[c];
               float h = H[c];
               h -= wk * g;
