@@ -211,3 +211,25 @@ def test_check_matrix_formats_and_dtypes():
     assert isinstance(same, sps.csr_matrix) and same.dtype == np.float64
     assert isinstance(check_matrix(C, "npy"), np.ndarray) and check_matrix(C, "npy").dtype == np.float32
     assert np.array_equal(check_matrix(D, "npy"), D)
+
+
+def test_argument_rules_of_the_next_row_trainers_are_checked_before_any_device_work():
+    """The mirrors refuse what the reference refuses (same exception types) before they touch CUDA, so these run on a CPU box:
+    ASY_SVD with a batch (pyx:399) or off the reference's sample stream, the tree-sparse SLIM mode in the throughput mode,
+    SLIM ElasticNet with l1_ratio outside [0, 1] (SLIMElasticNetRecommender.py:43)."""
+    from recsys2019_deeplearning_evaluation_b200.mf_epoch import MatrixFactorization_Cython_Epoch
+    from recsys2019_deeplearning_evaluation_b200.recommenders import SLIMElasticNetRecommender
+    from recsys2019_deeplearning_evaluation_b200.slim_bpr_epoch import SLIM_BPR_Cython_Epoch
+    X = synth_urm(40, 15, 0.2, values="ratings")
+    with pytest.raises(AssertionError, match="Batch size other than 1"):
+        MatrixFactorization_Cython_Epoch(X, n_factors=4, algorithm_name="ASY_SVD", batch_size=2, random_seed=1)
+    with pytest.raises(ValueError, match="ASY_SVD"):
+        MatrixFactorization_Cython_Epoch(X, n_factors=4, algorithm_name="ASY_SVD", batch_size=1, sampler="philox", random_seed=1)
+    with pytest.raises(ValueError, match="ASY_SVD"):
+        MatrixFactorization_Cython_Epoch(X, n_factors=4, algorithm_name="ASY_SVD", batch_size=1, hogwild=True, random_seed=1)
+    with pytest.raises(ValueError, match="algorithm_name"):
+        MatrixFactorization_Cython_Epoch(X, n_factors=4, algorithm_name="SVD++")
+    with pytest.raises(ValueError, match="train_with_sparse_weights"):
+        SLIM_BPR_Cython_Epoch(X, train_with_sparse_weights=True, hogwild=True, sampler="philox", random_seed=1)
+    with pytest.raises(AssertionError, match="l1_ratio must be between 0 and 1"):
+        SLIMElasticNetRecommender(X, verbose=False).fit(l1_ratio=1.5)
