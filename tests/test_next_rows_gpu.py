@@ -156,6 +156,22 @@ def test_asysvd_wide_factors_and_argument_rules():
         _mf()(X, n_factors=4, batch_size=1, sampler="philox", **common)
 
 
+@pytest.mark.parametrize("f,mode", [(10, "adagrad"), (50, "adam"), (3, "sgd"), (17, "rmsprop")])
+def test_asysvd_factor_counts_that_are_not_multiples_of_four(f, mode):
+    """The device rows are padded to float4s (the padding stays 0 under every optimiser); the reference's usual factor counts
+    (10, 50, ...) take this path."""
+    kw = dict(n_factors=f, algorithm_name="ASY_SVD", batch_size=1, learning_rate=0.01, random_seed=42, sgd_mode=mode, use_bias=True,
+              negative_interactions_quota=0.3, user_reg=1e-3, item_reg=2e-3, bias_reg=1e-3)
+    X = asy_urm()
+    g, o = _mf()(X, **kw), MFOracle(X, **kw)
+    g.epochIteration_Cython()
+    o.epochIteration_Cython()
+    assert g.get_USER_factors().shape == (X.shape[1], f) and g.get_ITEM_factors().shape == (X.shape[1], f)
+    for name in ("get_USER_factors", "get_ITEM_factors", "get_USER_bias", "get_ITEM_bias"):
+        a, b = getattr(g, name)(), getattr(o, name)()
+        assert np.allclose(a, b, rtol=ASY_RTOL, atol=ASY_ATOL), "%s: max abs diff %.3e" % (name, float(np.abs(a - b).max()))
+
+
 def test_asysvd_recommender_estimates_user_factors_from_profiles():
     from recsys2019_deeplearning_evaluation_b200.recommenders import MatrixFactorization_AsySVD_Cython
     X = asy_urm()
